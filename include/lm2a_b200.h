@@ -1,0 +1,151 @@
+/*
+ * lm2a_b200.h — C ABI of the B200-native LM2A reverse-diffusion sampling path.
+ *
+ * One shared library (liblm2a_b200.so), `extern "C"`, plain pointers and sizes.
+ * Every entry point:
+ *   - takes DEVICE pointers borrowed from the caller (never allocates, frees or
+ *     synchronises), launches on the `stream` handle given (a cudaStream_t cast
+ *     to void*), and is therefore CUDA-Graph capturable;
+ *   - returns 0 on success, non-zero on an argument / shape / architecture
+ *     violation *before* any launch (message via lm2a_last_error());
+ *   - is sm_100a only: no fallback, no CPU path.
+ *
+ * Activation layout ("slab"): channels-last bf16 [R, Tp, ld] flattened to
+ * M = R*Tp slots; slot (r, t) is valid for t < T, every slot t >= T is ZERO.
+ * The shared zero slot between consecutive clips is the conv zero padding, so
+ * a k=3 conv is three shifted 2-D TMA boxes over the flattened slab.
+ *
+ * Reference symbols replaced (paths relative to the reference repo):
+ *   lm2a_conv1d_bf16   nn.Conv1d k1/k3/k4s2 + bias (+FiLM, +skip conv, +residual)
+ *                      models/unet1d_ultimate.py:87-88,115,138-148,159,216-221,
+ *                      255-261,295,364 and every nn.Linear / MHA in/out
+ *                      projection of models/cross_attention.py:19-36,46-65
+ *   lm2a_gn_silu_bf16  nn.GroupNorm + nn.SiLU, unet1d_ultimate.py:91-95,136-137,
+ *                      146-147,362-363
+ *   lm2a_cross_attn_bf16  softmax(q k^T) v core of nn.MultiheadAttention as used
+ *                      at models/cross_attention.py:50-61
+ *   lm2a_time_mlp / lm2a_film   models/embedding.py:19-43, unet1d_ultimate.py:43-65
+ *   lm2a_upsample2x_bf16  F.interpolate(linear, align_corners=True) :231-236
+ *   lm2a_ingest_x      torch.cat([x, x]) + layout change, sample.py:162
+ *   lm2a_cfg_posterior sample.py:167-174 (CFG blend + clamps) and
+ *                      sample.py:186-210 == models/diffusion.py:71-102
+ */
+#ifndef LM2A_B200_H
+#define LM2A_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM2A_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------- */
+int lm2a_abi_version(void);
+const char* lm2a_last_error(void);
+/* 0 iff the current device is compute capability 10.x (B200). */
+int lm2a_check_device(void);
+/* number of kernels launched by this library since load / last reset */
+int64_t lm2a_launch_count(void);
+void lm2a_reset_launch_count(void);
+
+/* ---- implicit-GEMM conv1d / linear (tcgen05 + TMEM + TMA) ------------- */
+enum { LM2A_TAPS_K1 = 0, LM2A_TAPS_K3 = 1, LM2A_TAPS_K4S2 = 2 };
+enum { LM2A_OUT_BF16_SLAB = 0, LM2A_OUT_F32_NCT = 1 };
+
+typedef struct lm2a_conv_seg {
+  const void* x;      /* bf16 slab base (already offset to first channel)     */
+  int64_t rows;       /* slots in the slab (R*Tp of the INPUT)                */
+  int32_t ld;         /* slot pitch in elements (multiple of 8)               */
+  int32_t cin;        /* channels consumed (multiple of 64)                   */
+  int32_t taps;       /* LM2A_TAPS_*; K4S2 needs rows == 2 * M                */
+  int32_t _pad;
+} lm2a_conv_seg;
+
+typedef struct lm2a_conv_desc {
+  lm2a_conv_seg seg[2];   /* seg[1].x == NULL when unused (fused skip conv /
+                             second operand of a virtual concat)              */
+  const void* w;          /* bf16 [n_pad, k_total], k = seg, tap, channel     */
+  int32_t n_pad;          /* rows of w, multiple of 128                       */
+  int32_t n_valid;        /* real output channels                             */
+  int64_t m;              /* output slots = R * tp                            */
+  int32_t tp;             /* output slot pitch per clip                       */
+  int32_t t_valid;        /* output slots t >= t_valid are written as zero    */
+  const float* bias;      /* [n_pad] fp32                                     */
+  const float* film;      /* NULL or fp32 [R, film_ld]: scale at col n,
+                             shift at col film_shift_off + n                  */
+  int32_t film_ld;
+  int32_t film_shift_off;
+  const void* residual;   /* NULL or bf16 slab added in the epilogue          */
+  int32_t res_ld;
+  int32_t out_mode;       /* LM2A_OUT_*                                       */
+  void* out;              /* bf16 slab [m, out_ld] or fp32 [R, n_valid, t_valid] */
+  int32_t out_ld;
+  int32_t block_n;        /* 0 = auto, else 128 or 256                        */
+} lm2a_conv_desc;
+
+int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);
+
+/* ---- GroupNorm + SiLU over a slab -------------------------------------- */
+/* x,y: bf16 slabs [R, tp, ld*]; stats over t < t_valid and c/groups channels */
+int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                      int32_t y_ld, const float* gamma, const float* beta,
+                      int32_t rows, int32_t tp, int32_t t_valid, int32_t c,
+                      int32_t groups, float eps, int32_t apply_silu);
+
+/* ---- cross-attention core ------------------------------------------------ */
+/* q,o: bf16 slabs [R*tp, ld]; stream s, head h live at channel s*e + h*dh.
+ * q is pre-scaled by log2(e)/sqrt(dh). k_s/v_s: bf16 [slots, lk, kv_ld]
+ * (first e channels used). kv_slot[r] selects the cache slot of clip-row r. */
+int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                         int32_t o_ld, const void* k_motion,
+                         const void* v_motion, const void* k_text,
+                         const void* v_text, int32_t kv_ld,
+                         const int32_t* kv_slot, int32_t rows, int32_t tp,
+                         int32_t t_valid, int32_t lk, int32_t e, int32_t heads);
+
+/* ---- timestep embedding + FiLM tables ----------------------------------- */
+/* silu_temb[r,:] = SiLU(SiLU(W sinus(t[r]) + b))  (the SiLU that opens every
+ * FiLM net is folded in); dim must be 256-thread friendly (<= 1024, even).  */
+int lm2a_time_mlp(void* stream, const int64_t* t, const float* w,
+                  const float* b, float* silu_temb, int32_t rows, int32_t dim);
+/* film[r, j] = sum_k silu_temb[r,k] * w[j,k] + b[j], j < cols (all FiLM nets
+ * of the model concatenated).                                               */
+int lm2a_film(void* stream, const float* silu_temb, const float* w,
+              const float* b, float* film, int32_t rows, int32_t dim,
+              int32_t cols);
+
+/* ---- layout / resampling helpers ---------------------------------------- */
+/* x fp32 [B, c, T] -> bf16 slab rows [copies*B, tp, ld] (channels >= c and
+ * slots >= T zero); copy k of clip b lands in row k*B + b.                  */
+int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t batch,
+                  int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld);
+/* fp32 [rows, t, c] -> bf16 slab [rows, tp, ld] (channels >= c zero)        */
+int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t rows,
+                    int32_t t, int32_t c, int32_t tp, int32_t ld);
+/* linear x2, align_corners=True: [R, tp_in, ld_in] (t_in valid) ->
+ * [R, tp_out, ld_out] (2*t_in valid, rest zero)                             */
+int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                         int32_t y_ld, int32_t rows, int32_t tp_in,
+                         int32_t t_in, int32_t tp_out, int32_t c);
+
+/* ---- CFG blend + clamps + DDPM posterior update -------------------------- */
+/* x [B,c,T] fp32 updated in place. eps: fp32 [2B,c,T] (uncond rows first)
+ * when guided != 0, else [B,c,T]. sched: fp32 [steps,4] rows
+ * {1/sqrt(alpha_t), beta_t/sqrt(1-abar_t), sqrt(beta_t), 0}; t_dev: int64[rows]
+ * device timestep vector (element 0 indexes sched); noise may be NULL only if
+ * every call has t == 0. If advance != 0 the kernel's last block decrements
+ * all n_t entries of t_dev afterwards (graph replay); `ticket` is a zeroed
+ * device uint32 used to elect that block. eps_out (optional) receives the
+ * blended eps [B,c,T].                                                      */
+int lm2a_cfg_posterior(void* stream, float* x, const float* eps,
+                       const float* noise, const float* sched,
+                       int64_t* t_dev, int32_t n_t, uint32_t* ticket,
+                       int32_t batch, int64_t elems_per_clip, float guidance,
+                       int32_t guided, int32_t advance, float* eps_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM2A_B200_H */

@@ -1,0 +1,48 @@
+// Library-level entry points of the C ABI: version, error string, device check,
+// launch counter (bench.py reports it as `gpu_launches`).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/lm2a_b200.h"
+#include "common.cuh"
+
+namespace lm2a {
+
+static thread_local char g_error[1024] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace lm2a
+
+extern "C" int lm2a_abi_version(void) { return LM2A_ABI_VERSION; }
+
+extern "C" const char* lm2a_last_error(void) { return lm2a::g_error; }
+
+extern "C" int lm2a_check_device(void) {
+  using namespace lm2a;
+  int dev = 0;
+  LM2A_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  LM2A_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  LM2A_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  LM2A_REQUIRE(major == 10, "lm2a_b200 kernels are sm_100a only; device %d is sm_%d%d", dev,
+               major, minor);
+  return 0;
+}
+
+extern "C" int64_t lm2a_launch_count(void) {
+  return lm2a::g_launches.load(std::memory_order_relaxed);
+}
+
+extern "C" void lm2a_reset_launch_count(void) {
+  lm2a::g_launches.store(0, std::memory_order_relaxed);
+}

@@ -1,0 +1,464 @@
+// Implicit-GEMM Conv1d / Linear for channels-last bf16 slabs on sm_100a.
+//
+//   out[m, n] = sum_{seg, tap, c} A_seg[m + shift(tap), c] * W[n, k(seg,tap,c)] + bias[n]
+//
+// Replaces nn.Conv1d (k=1, k=3 p=1, k=4 s=2 p=1) and every nn.Linear / MHA
+// projection on the sampling path (reference models/unet1d_ultimate.py:87-88,
+// 115,216-221,255-261,295,364; models/cross_attention.py:19-36). The FiLM
+// modulation h*(1+scale)+shift (:141-143), the ResBlock skip 1x1 conv (second K
+// segment accumulating into the same TMEM tile) and the residual add (:159) are
+// fused into the epilogue.
+//
+// Structure (one CTA per SM, persistent over 128 x BLOCK_N output tiles):
+//   warp 0     TMA producer: per K-block one 128x64 A box (a tap is a row shift of
+//              the flattened slab; the zero slot between clips and TMA's
+//              out-of-bounds zero fill are the conv padding) and one BLOCK_Nx64 W box
+//   warp 1     tcgen05.mma issuer (single thread), accumulators in TMEM,
+//              double-buffered so tile i+1's MMAs overlap tile i's epilogue
+//   warps 2-5  epilogue: tcgen05.ld -> bias/FiLM/residual -> bf16 slab (or the
+//              final fp32 [R, C, T] eps tensor)
+#include "../../include/lm2a_b200.h"
+#include "common.cuh"
+
+namespace lm2a {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;
+constexpr int kThreads = 192;
+
+struct ConvArgs {
+  int seg_cblk[2];   // cin / 64 per segment
+  int seg_taps[2];   // LM2A_TAPS_*
+  int seg_half[2];   // K4S2: channel offset of the odd slot inside a slot pair
+  int num_kb;
+  int m_tiles, n_tiles;
+  long long m;
+  int tp, t_valid, n_valid;
+  const float* bias;
+  const float* film;
+  int film_ld, film_shift_off;
+  const __nv_bfloat16* residual;
+  int res_ld;
+  void* out;
+  int out_ld;
+  int out_mode;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
+                 const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + L::kBarOffset;
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto a_tile = [&](int s) { return smem_base + s * L::kStageBytes; };
+  auto b_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * kBlockM;
+        const int n0 = (tile % p.n_tiles) * BLOCK_N;
+        int kb = 0;
+#pragma unroll 1
+        for (int seg = 0; seg < 2; ++seg) {
+          const int cblk = p.seg_cblk[seg];
+          if (cblk == 0) continue;
+          const CUtensorMap* tm = seg ? &tmA1 : &tmA0;
+          const int mode = p.seg_taps[seg];
+          const int ntaps = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4);
+#pragma unroll 1
+          for (int tap = 0; tap < ntaps; ++tap) {
+            int shift = 0, choff = 0;
+            if (mode == LM2A_TAPS_K3) {
+              shift = tap - 1;
+            } else if (mode == LM2A_TAPS_K4S2) {
+              // x[2t-1+tap] over slot pairs: tap0 -> pair t-1 odd half, tap1 -> pair t
+              // even half, tap2 -> pair t odd half, tap3 -> pair t+1 even half
+              shift = tap == 0 ? -1 : (tap == 3 ? 1 : 0);
+              choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
+            }
+#pragma unroll 1
+            for (int cb = 0; cb < cblk; ++cb, ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              mbar_expect_tx(full_bar(stage), L::kStageBytes);
+              tma_load_2d(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift,
+                          full_bar(stage));
+              tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after_sync();
+          const uint64_t adesc = umma_desc_sw128_kmajor(a_tile(stage));
+          const uint64_t bdesc = umma_desc_sw128_kmajor(b_tile(stage));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
+            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ----------------------------------------------------------------- epilogue
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const long long m = (long long)(tile / p.n_tiles) * kBlockM + row;
+      const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      const bool in_range = m < p.m;
+      const int r = in_range ? (int)(m / p.tp) : 0;
+      const int t = in_range ? (int)(m - (long long)r * p.tp) : 0;
+      const bool valid = in_range && t < p.t_valid;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int n = n0 + c0;
+        if (n >= p.n_valid) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+          f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        }
+        if (p.film != nullptr) {
+          const float* sc = p.film + (size_t)r * p.film_ld + n;
+          const float* sh = sc + p.film_shift_off;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(sh + j));
+            f[j + 0] = fmaf(f[j + 0], 1.0f + s4.x, h4.x);
+            f[j + 1] = fmaf(f[j + 1], 1.0f + s4.y, h4.y);
+            f[j + 2] = fmaf(f[j + 2], 1.0f + s4.z, h4.z);
+            f[j + 3] = fmaf(f[j + 3], 1.0f + s4.w, h4.w);
+          }
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* rp =
+              reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.res_ld + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 q = __ldg(rp + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 a = unpack_bf16x2(w[e]);
+              f[j * 8 + e * 2 + 0] += a.x;
+              f[j * 8 + e * 2 + 1] += a.y;
+            }
+          }
+        }
+        if (p.out_mode == LM2A_OUT_BF16_SLAB) {
+          if (in_range) {
+            uint4* op = reinterpret_cast<uint4*>(
+                reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              if (valid) {
+                q.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+                q.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+                q.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+                q.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+              } else {
+                q = make_uint4(0u, 0u, 0u, 0u);  // keep the inter-clip zero slots zero
+              }
+              op[j] = q;
+            }
+          }
+        } else {
+          // fp32 [R, n_valid, t_valid]: lanes are consecutive t -> coalesced per channel
+          if (valid) {
+            float* op = reinterpret_cast<float*>(p.out) +
+                        ((size_t)r * p.n_valid + n) * p.t_valid + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n + j < p.n_valid) op[(size_t)j * p.t_valid] = f[j];
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(tempty_bar(acc));
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  }
+  return fn;
+}
+
+// 2-D bf16 map: inner = channels (box 64 -> 128 B, SWIZZLE_128B), outer = slots / rows.
+int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+              uint64_t pitch_elems, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  LM2A_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult res = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LM2A_REQUIRE(res == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu pitch=%llu",
+               (int)res, base, (unsigned long long)inner, (unsigned long long)outer,
+               (unsigned long long)pitch_elems);
+  return 0;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
+           const CUtensorMap& b, const ConvArgs& args) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    LM2A_CUDA_OK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+    configured = true;
+  }
+  const int tiles = args.m_tiles * args.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, kThreads, L::kBytes, stream>>>(a0, a1, b, args);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+}  // namespace lm2a
+
+extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
+  using namespace lm2a;
+  LM2A_REQUIRE(d != nullptr, "conv1d: null descriptor");
+  LM2A_REQUIRE(d->seg[0].x != nullptr && d->w != nullptr && d->bias != nullptr &&
+                   d->out != nullptr,
+               "conv1d: null x / w / bias / out pointer");
+  LM2A_REQUIRE(d->m > 0 && d->tp > 0 && d->t_valid > 0 && d->t_valid <= d->tp &&
+                   d->m % d->tp == 0,
+               "conv1d: bad slab geometry m=%lld tp=%d t_valid=%d", (long long)d->m, d->tp,
+               d->t_valid);
+  LM2A_REQUIRE(d->n_pad > 0 && d->n_pad % 128 == 0 && d->n_valid > 0 && d->n_valid <= d->n_pad,
+               "conv1d: n_pad=%d must be a positive multiple of 128 (n_valid=%d)", d->n_pad,
+               d->n_valid);
+  LM2A_REQUIRE(d->m < (1ll << 31) - 256, "conv1d: too many slots");
+
+  ConvArgs a{};
+  CUtensorMap tmA[2];
+  int k_total = 0;
+  for (int s = 0; s < 2; ++s) {
+    const lm2a_conv_seg& g = d->seg[s];
+    if (g.x == nullptr) {
+      a.seg_cblk[s] = 0;
+      a.seg_taps[s] = 0;
+      a.seg_half[s] = 0;
+      tmA[s] = tmA[0];
+      continue;
+    }
+    LM2A_REQUIRE(g.cin > 0 && g.cin % 64 == 0, "conv1d: seg %d cin=%d not a multiple of 64", s,
+                 g.cin);
+    LM2A_REQUIRE(g.ld >= g.cin && g.ld % 8 == 0, "conv1d: seg %d ld=%d invalid (cin=%d)", s,
+                 g.ld, g.cin);
+    LM2A_REQUIRE((reinterpret_cast<uintptr_t>(g.x) & 15) == 0,
+                 "conv1d: seg %d base not 16-byte aligned", s);
+    LM2A_REQUIRE(g.taps >= LM2A_TAPS_K1 && g.taps <= LM2A_TAPS_K4S2, "conv1d: seg %d taps=%d",
+                 s, g.taps);
+    a.seg_cblk[s] = g.cin / 64;
+    a.seg_taps[s] = g.taps;
+    int ntaps = 1;
+    if (g.taps == LM2A_TAPS_K4S2) {
+      LM2A_REQUIRE(g.rows == 2 * d->m,
+                   "conv1d: k4s2 needs input slots (%lld) == 2 * output slots (%lld)",
+                   (long long)g.rows, (long long)d->m);
+      a.seg_half[s] = g.ld;
+      ntaps = 4;
+      if (encode_2d(&tmA[s], g.x, (uint64_t)g.ld + g.cin, (uint64_t)g.rows / 2,
+                    (uint64_t)g.ld * 2, kBlockM))
+        return 1;
+    } else {
+      LM2A_REQUIRE(g.rows == d->m, "conv1d: seg %d slots (%lld) != output slots (%lld)", s,
+                   (long long)g.rows, (long long)d->m);
+      a.seg_half[s] = 0;
+      ntaps = g.taps == LM2A_TAPS_K3 ? 3 : 1;
+      if (encode_2d(&tmA[s], g.x, (uint64_t)g.cin, (uint64_t)g.rows, (uint64_t)g.ld, kBlockM))
+        return 1;
+    }
+    k_total += ntaps * g.cin;
+  }
+  int block_n = d->block_n;
+  if (block_n == 0) block_n = (d->n_pad % 256 == 0) ? 256 : 128;
+  LM2A_REQUIRE((block_n == 128 || block_n == 256) && d->n_pad % block_n == 0,
+               "conv1d: block_n=%d incompatible with n_pad=%d", block_n, d->n_pad);
+  LM2A_REQUIRE((reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0,
+               "conv1d: w / out / bias must be 16-byte aligned");
+  CUtensorMap tmB;
+  if (encode_2d(&tmB, d->w, (uint64_t)k_total, (uint64_t)d->n_pad, (uint64_t)k_total,
+                (uint32_t)block_n))
+    return 1;
+
+  a.num_kb = k_total / 64;
+  a.m_tiles = (int)((d->m + kBlockM - 1) / kBlockM);
+  a.n_tiles = d->n_pad / block_n;
+  a.m = d->m;
+  a.tp = d->tp;
+  a.t_valid = d->t_valid;
+  a.n_valid = d->n_valid;
+  a.bias = d->bias;
+  a.film = d->film;
+  a.film_ld = d->film_ld;
+  a.film_shift_off = d->film_shift_off;
+  if (d->film != nullptr) {
+    LM2A_REQUIRE((reinterpret_cast<uintptr_t>(d->film) & 15) == 0 && d->film_ld % 4 == 0 &&
+                     d->film_shift_off % 4 == 0,
+                 "conv1d: film table must be 16-byte aligned with ld / offset multiples of 4");
+  }
+  a.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  a.res_ld = d->res_ld;
+  if (d->residual != nullptr) {
+    LM2A_REQUIRE((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && d->res_ld % 8 == 0,
+                 "conv1d: residual slab must be 16-byte aligned, ld multiple of 8");
+  }
+  a.out = d->out;
+  a.out_ld = d->out_ld;
+  a.out_mode = d->out_mode;
+  if (d->out_mode == LM2A_OUT_BF16_SLAB) {
+    LM2A_REQUIRE(d->out_ld % 8 == 0 && d->out_ld >= d->n_valid && d->n_valid % 32 == 0,
+                 "conv1d: bf16 slab output needs ld %% 8 == 0 and n_valid %% 32 == 0 (ld=%d n=%d)",
+                 d->out_ld, d->n_valid);
+  } else {
+    LM2A_REQUIRE(d->out_mode == LM2A_OUT_F32_NCT, "conv1d: bad out_mode %d", d->out_mode);
+  }
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return launch<256, 4>(st, tmA[0], tmA[1], tmB, a);
+  return launch<128, 6>(st, tmA[0], tmA[1], tmB, a);
+}

@@ -1,0 +1,321 @@
+// HBM-bound helpers of the sampling step: layout ingest, x2 linear upsampling,
+// timestep embedding MLP, FiLM tables, and the fused CFG blend + DDPM posterior
+// update. All launch on the caller's stream and never synchronise.
+#include "../../include/lm2a_b200.h"
+#include "common.cuh"
+
+namespace lm2a {
+namespace {
+
+// ---------------------------------------------------------------------------
+// x fp32 [B, c, T] -> bf16 slab [copies*B, tp, ld]. CFG doubles the batch by
+// feeding the same x to the uncond and cond rows (reference sample.py:162), so
+// one read of x feeds `copies` rows.
+__global__ void __launch_bounds__(256)
+ingest_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, int batch,
+                int copies, int c, int T, int tp, int ld) {
+  __shared__ float tile[32][129];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int ch = ty; ch < c; ch += 8) {
+    const int t = t0 + tx;
+    tile[tx][ch] = (t < T) ? __ldg(x + ((size_t)b * c + ch) * T + t) : 0.f;
+  }
+  __syncthreads();
+  for (int tl = ty; tl < 32; tl += 8) {
+    const int t = t0 + tl;
+    if (t >= tp) break;
+    for (int cc = tx; cc < ld; cc += 32) {
+      const float v = (cc < c && t < T) ? tile[tl][cc] : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      for (int k = 0; k < copies; ++k)
+        slab[((size_t)(k * batch + b) * tp + t) * ld + cc] = h;
+    }
+  }
+}
+
+// fp32 [rows, T, c] -> bf16 slab [rows, tp, ld]
+__global__ void __launch_bounds__(256)
+ingest_seq_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, long long total,
+                  int T, int c, int tp, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cc = (int)(i % ld);
+  const long long slot = i / ld;
+  const int t = (int)(slot % tp);
+  const long long r = slot / tp;
+  float v = 0.f;
+  if (t < T && cc < c) v = __ldg(x + ((size_t)r * T + t) * c + cc);
+  slab[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------
+// F.interpolate(scale_factor=2, mode='linear', align_corners=True) on a slab:
+// src = i * (T-1)/(2T-1); out = (1-w) x[floor(src)] + w x[min(floor(src)+1, T-1)]
+// (reference models/unet1d_ultimate.py:231-236).
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+                  int y_ld, long long total_vec, int tp_in, int t_in, int tp_out, int c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int vpr = c >> 3;
+  const int cv = (int)(i % vpr);
+  const long long slot = i / vpr;
+  const int t = (int)(slot % tp_out);
+  const long long r = slot / tp_out;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  const int t_out = 2 * t_in;
+  if (t < t_out) {
+    const float scale = t_out > 1 ? (float)(t_in - 1) / (float)(t_out - 1) : 0.f;
+    const float src = scale * (float)t;
+    const int i0 = (int)src;
+    const int i1 = i0 + (i0 < t_in - 1 ? 1 : 0);
+    const float w1 = src - (float)i0;
+    const float w0 = 1.0f - w1;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(
+        x + ((size_t)r * tp_in + i0) * x_ld + cv * 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(
+        x + ((size_t)r * tp_in + i1) * x_ld + cv * 8));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = unpack_bf16x2(aw[e]);
+      const float2 fb = unpack_bf16x2(bw[e]);
+      ow[e] = pack_bf16x2(w0 * fa.x + w1 * fb.x, w0 * fa.y + w1 * fb.y);
+    }
+    o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  *reinterpret_cast<uint4*>(y + ((size_t)r * tp_out + t) * y_ld + cv * 8) = o;
+}
+
+// ---------------------------------------------------------------------------
+// SinusoidalPosEmb -> Linear -> SiLU (reference models/embedding.py:19-43) and the
+// SiLU that opens every FiLM net (unet1d_ultimate.py:50-53). One CTA per row;
+// each warp produces outputs with a shuffle reduction over the input dim.
+__global__ void __launch_bounds__(256)
+time_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w,
+                const float* __restrict__ b, float* __restrict__ out, int dim) {
+  extern __shared__ float emb[];
+  const int r = blockIdx.x;
+  const int half = dim / 2;
+  const float tv = (float)t[r];
+  const float step = (float)(-(log(10000.0) / (double)(half - 1)));
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const int k = i < half ? i : i - half;
+    const float f = expf((float)k * step);
+    const float a = tv * f;
+    emb[i] = i < half ? sinf(a) : cosf(a);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < dim; j += blockDim.x / 32) {
+    float acc = 0.f;
+    for (int k = lane; k < dim; k += 32) acc = fmaf(emb[k], __ldg(w + (size_t)j * dim + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = silu_accurate(acc + __ldg(b + j));
+      out[(size_t)r * dim + j] = silu_accurate(v);
+    }
+  }
+}
+
+// film[r, j] = <silu_temb[r, :], w[j, :]> + b[j]; one warp per output column j,
+// the weight row lives in registers and is reused across all rows.
+template <int KPL>  // dim / 32
+__global__ void __launch_bounds__(256)
+film_kernel(const float* __restrict__ s, const float* __restrict__ w,
+            const float* __restrict__ b, float* __restrict__ film, int rows, int cols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= cols) return;
+  constexpr int dim = KPL * 32;
+  float wr[KPL];
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) wr[i] = __ldg(w + (size_t)j * dim + lane + 32 * i);
+  const float bj = __ldg(b + j);
+  for (int r = 0; r < rows; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) acc = fmaf(wr[i], __ldg(s + (size_t)r * dim + lane + 32 * i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) film[(size_t)r * cols + j] = acc + bj;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Classifier-free-guidance blend with both clamps (reference sample.py:167-174)
+// and the DDPM posterior update (sample.py:186-210 == models/diffusion.py:71-102)
+// in one pass: 5 fp32 streams per element (x, eps_u, eps_c, noise in; x out).
+// Arithmetic keeps the reference's operation order with explicit round-to-
+// nearest mul/add/sub (no FMA contraction), so given the same eps and noise the
+// update is bit-identical to the PyTorch elementwise sequence.
+__global__ void __launch_bounds__(256)
+cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                     const float* __restrict__ noise, const float* __restrict__ sched,
+                     int64_t* __restrict__ t_dev, int n_t, unsigned int* __restrict__ ticket,
+                     long long total_vec, long long clip_vec, int batch, float gw, int guided,
+                     int advance, float* __restrict__ eps_out) {
+  const long long t_now = t_dev[0];
+  const float4 co = __ldg(reinterpret_cast<const float4*>(sched) + t_now);
+  const float coef1 = co.x, coef2 = co.y, sigma = co.z;
+  const bool add_noise = t_now > 0 && noise != nullptr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long uncond_to_cond = (long long)batch * clip_vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += stride) {
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    float4 e;
+    if (guided) {
+      const float4 eu = __ldg(reinterpret_cast<const float4*>(eps) + i);
+      const float4 ec = __ldg(reinterpret_cast<const float4*>(eps) + i + uncond_to_cond);
+      const float u[4] = {eu.x, eu.y, eu.z, eu.w};
+      const float c[4] = {ec.x, ec.y, ec.z, ec.w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float d = __fsub_rn(c[k], u[k]);
+        d = fminf(fmaxf(d, -5.0f), 5.0f);
+        float g = __fadd_rn(u[k], __fmul_rn(gw, d));
+        o[k] = fminf(fmaxf(g, -10.0f), 10.0f);
+      }
+      e = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      e = __ldg(reinterpret_cast<const float4*>(eps) + i);
+    }
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add_noise) nz = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(coef1, __fsub_rn(xv.x, __fmul_rn(coef2, e.x))), __fmul_rn(sigma, nz.x));
+    o.y = __fadd_rn(__fmul_rn(coef1, __fsub_rn(xv.y, __fmul_rn(coef2, e.y))), __fmul_rn(sigma, nz.y));
+    o.z = __fadd_rn(__fmul_rn(coef1, __fsub_rn(xv.z, __fmul_rn(coef2, e.z))), __fmul_rn(sigma, nz.z));
+    o.w = __fadd_rn(__fmul_rn(coef1, __fsub_rn(xv.w, __fmul_rn(coef2, e.w))), __fmul_rn(sigma, nz.w));
+    reinterpret_cast<float4*>(x)[i] = o;
+    if (eps_out != nullptr) reinterpret_cast<float4*>(eps_out)[i] = e;
+  }
+  if (advance) {
+    // the last CTA to finish steps the device-side timestep (graph replay needs no host)
+    __shared__ unsigned int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(ticket, 1u);
+      is_last = (done == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+      for (int k = threadIdx.x; k < n_t; k += blockDim.x) t_dev[k] = t_now - 1;
+      if (threadIdx.x == 0) *ticket = 0u;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace lm2a
+
+extern "C" int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t batch,
+                             int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && slab, "ingest_x: null pointer");
+  LM2A_REQUIRE(batch > 0 && copies > 0 && c > 0 && c <= 128 && ld <= 128 && ld >= c && t > 0 &&
+                   tp >= t,
+               "ingest_x: bad geometry (c=%d ld=%d t=%d tp=%d; c, ld <= 128)", c, ld, t, tp);
+  dim3 grid((tp + 31) / 32, batch);
+  ingest_x_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(slab), batch, copies, c, t, tp, ld);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t rows,
+                               int32_t t, int32_t c, int32_t tp, int32_t ld) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && slab, "ingest_seq: null pointer");
+  LM2A_REQUIRE(rows > 0 && t > 0 && tp >= t && c > 0 && ld >= c, "ingest_seq: bad geometry");
+  const long long total = (long long)rows * tp * ld;
+  const int blocks = (int)((total + 255) / 256);
+  ingest_seq_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(slab), total, t, c, tp, ld);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                                    int32_t y_ld, int32_t rows, int32_t tp_in, int32_t t_in,
+                                    int32_t tp_out, int32_t c) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && y, "upsample2x: null pointer");
+  LM2A_REQUIRE(rows > 0 && t_in > 0 && tp_in >= t_in && tp_out >= 2 * t_in && c % 8 == 0 &&
+                   x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+               "upsample2x: bad geometry");
+  const long long total_vec = (long long)rows * tp_out * (c / 8);
+  const int blocks = (int)((total_vec + 255) / 256);
+  upsample2x_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
+      total_vec, tp_in, t_in, tp_out, c);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_time_mlp(void* stream, const int64_t* t, const float* w, const float* b,
+                             float* silu_temb, int32_t rows, int32_t dim) {
+  using namespace lm2a;
+  LM2A_REQUIRE(t && w && b && silu_temb, "time_mlp: null pointer");
+  LM2A_REQUIRE(rows > 0 && dim >= 4 && dim % 2 == 0 && dim <= 4096, "time_mlp: bad dim %d", dim);
+  time_mlp_kernel<<<rows, 256, dim * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      t, w, b, silu_temb, dim);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_film(void* stream, const float* silu_temb, const float* w, const float* b,
+                         float* film, int32_t rows, int32_t dim, int32_t cols) {
+  using namespace lm2a;
+  LM2A_REQUIRE(silu_temb && w && b && film, "film: null pointer");
+  LM2A_REQUIRE(rows > 0 && cols > 0, "film: bad geometry");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = (cols + 7) / 8;
+  switch (dim) {
+    case 128: film_kernel<4><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
+    case 256: film_kernel<8><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
+    case 512: film_kernel<16><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
+    default:
+      LM2A_REQUIRE(false, "film: time_emb_dim %d unsupported (128, 256 or 512)", dim);
+  }
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_cfg_posterior(void* stream, float* x, const float* eps, const float* noise,
+                                  const float* sched, int64_t* t_dev, int32_t n_t,
+                                  uint32_t* ticket, int32_t batch, int64_t elems_per_clip,
+                                  float guidance, int32_t guided, int32_t advance,
+                                  float* eps_out) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && eps && sched && t_dev, "cfg_posterior: null pointer");
+  LM2A_REQUIRE(batch > 0 && elems_per_clip > 0 && elems_per_clip % 4 == 0,
+               "cfg_posterior: elems_per_clip must be a positive multiple of 4");
+  LM2A_REQUIRE(!advance || (ticket != nullptr && n_t > 0),
+               "cfg_posterior: advance needs a ticket counter and n_t > 0");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
+                 reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(sched) |
+                 reinterpret_cast<uintptr_t>(eps_out)) & 15) == 0,
+               "cfg_posterior: tensors must be 16-byte aligned");
+  const long long clip_vec = elems_per_clip / 4;
+  const long long total_vec = clip_vec * batch;
+  long long blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cfg_posterior_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, eps, noise, sched, t_dev, n_t, ticket, total_vec, clip_vec, batch, guidance, guided,
+      advance, eps_out);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}

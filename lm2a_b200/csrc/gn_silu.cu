@@ -1,0 +1,150 @@
+// GroupNorm (biased variance, per-channel affine) + SiLU over a channels-last
+// bf16 slab. One CTA per (clip-row, group): the (t_valid x C/G) sub-slab is read
+// from HBM once into shared memory, mean and variance are computed two-pass in
+// fp32 from that copy, and the normalised/activated result is written once.
+// Replaces nn.GroupNorm + nn.SiLU of the reference (models/unet1d_ultimate.py:
+// 91-95,136-137,146-147,362-363; eps = 1e-5, F.group_norm semantics).
+// HBM-bound: algorithmic bytes = 2 B read + 2 B written per element.
+#include "../../include/lm2a_b200.h"
+#include "common.cuh"
+
+namespace lm2a {
+namespace {
+
+constexpr int kGnThreads = 512;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < kGnThreads / 32; ++w) s += red[w];
+  return s;
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(kGnThreads)
+gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+               int y_ld, const float* __restrict__ gamma, const float* __restrict__ beta,
+               int tp, int t_valid, int cg, float eps, int apply_silu) {
+  extern __shared__ uint4 cache[];
+  __shared__ float red[kGnThreads / 32];
+  const int g = blockIdx.x, r = blockIdx.y;
+  const int vpr = cg >> 3;              // 16-byte vectors per slot
+  const int nvec = t_valid * vpr;
+  const int cv = threadIdx.x % vpr;     // fixed per thread: kGnThreads % vpr == 0
+  const int tstep = kGnThreads / vpr;
+  const int t0 = threadIdx.x / vpr;
+  const size_t row_base = (size_t)r * tp;
+  const __nv_bfloat16* xg = x + (size_t)g * cg + cv * 8;
+  __nv_bfloat16* yg = y + (size_t)g * cg + cv * 8;
+
+  // pass 1: sum
+  float s = 0.f;
+  for (int t = t0, i = threadIdx.x; t < t_valid; t += tstep, i += kGnThreads) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(xg + (row_base + t) * x_ld));
+    if (CACHED) cache[i] = q;
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = unpack_bf16x2(w[e]);
+      s += a.x + a.y;
+    }
+  }
+  const float inv_n = 1.0f / (float)(nvec * 8);
+  const float mean = block_sum(s, red) * inv_n;
+
+  // pass 2: centred sum of squares
+  float ss = 0.f;
+  for (int t = t0, i = threadIdx.x; t < t_valid; t += tstep, i += kGnThreads) {
+    const uint4 q = CACHED ? cache[i]
+                           : __ldg(reinterpret_cast<const uint4*>(xg + (row_base + t) * x_ld));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = unpack_bf16x2(w[e]);
+      const float d0 = a.x - mean, d1 = a.y - mean;
+      ss += d0 * d0 + d1 * d1;
+    }
+  }
+  const float var = block_sum(ss, red) * inv_n;
+  const float rstd = rsqrtf(var + eps);
+
+  float ga[8], be[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float gm = __ldg(gamma + g * cg + cv * 8 + e) * rstd;
+    ga[e] = gm;
+    be[e] = __ldg(beta + g * cg + cv * 8 + e) - mean * gm;
+  }
+
+  // pass 3: normalise + SiLU, write; slots t >= t_valid stay zero
+  for (int t = t0, i = threadIdx.x; t < tp; t += tstep, i += kGnThreads) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t_valid) {
+      const uint4 q = CACHED ? cache[i]
+                             : __ldg(reinterpret_cast<const uint4*>(xg + (row_base + t) * x_ld));
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = unpack_bf16x2(w[e]);
+        float v0 = fmaf(a.x, ga[2 * e], be[2 * e]);
+        float v1 = fmaf(a.y, ga[2 * e + 1], be[2 * e + 1]);
+        if (apply_silu) {
+          v0 = silu_f(v0);
+          v1 = silu_f(v1);
+        }
+        ow[e] = pack_bf16x2(v0, v1);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    *reinterpret_cast<uint4*>(yg + (row_base + t) * y_ld) = o;
+  }
+}
+
+}  // namespace
+}  // namespace lm2a
+
+extern "C" int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                                 int32_t y_ld, const float* gamma, const float* beta,
+                                 int32_t rows, int32_t tp, int32_t t_valid, int32_t c,
+                                 int32_t groups, float eps, int32_t apply_silu) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && y && gamma && beta, "gn_silu: null pointer");
+  LM2A_REQUIRE(rows > 0 && tp > 0 && t_valid > 0 && t_valid <= tp, "gn_silu: bad geometry");
+  LM2A_REQUIRE(groups > 0 && c % groups == 0, "gn_silu: c=%d not divisible by groups=%d", c,
+               groups);
+  const int cg = c / groups;
+  LM2A_REQUIRE(cg % 8 == 0 && kGnThreads % (cg / 8) == 0 && cg / 8 <= kGnThreads,
+               "gn_silu: channels per group (%d) must be 8 * a divisor of %d", cg, kGnThreads);
+  LM2A_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+               "gn_silu: ld must be a multiple of 8 and >= c");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+               "gn_silu: slabs must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t cache_bytes = (size_t)t_valid * cg * 2;
+  dim3 grid(groups, rows);
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  if (cache_bytes <= 200 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      LM2A_CUDA_OK(cudaFuncSetAttribute(gn_silu_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+      configured = true;
+    }
+    gn_silu_kernel<true><<<grid, kGnThreads, cache_bytes, st>>>(
+        xp, x_ld, yp, y_ld, gamma, beta, tp, t_valid, cg, eps, apply_silu);
+  } else {
+    gn_silu_kernel<false><<<grid, kGnThreads, 0, st>>>(xp, x_ld, yp, y_ld, gamma, beta, tp,
+                                                       t_valid, cg, eps, apply_silu);
+  }
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}

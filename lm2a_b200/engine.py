@@ -1,0 +1,424 @@
+"""Launch planner for UNet1D_ultimate on B200.
+
+Turns the parameter tree of models/unet1d_ultimate.py into
+  (1) packed device weights: bf16 K-major GEMM operands with the algebraic folds
+      (q-scale*log2e into W_q, kv_proj into the MHA K/V in-projection, out_proj+concat+
+      fuse_proj into one matrix, ResBlock skip conv appended as a second K segment),
+  (2) a static plan: pre-allocated bf16 slabs + a flat list of C-ABI launches that
+      computes reference UNet1D_ultimate.forward (unet1d_ultimate.py:367-426).
+
+Slab geometry: level l has T_l valid slots per clip-row and pitch Tp_l, with
+Tp_last = T_last + 1 and Tp_l = 2 * Tp_{l+1}; slots t >= T_l are zero. The zero slot is
+the conv padding, and Tp_l = 2 Tp_{l+1} makes the stride-2 conv a plain 4-tap GEMM over
+slot *pairs* of the flattened slab.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import OUT_BF16_SLAB, OUT_F32_NCT, TAPS_K1, TAPS_K3, TAPS_K4S2, Seg
+
+LOG2E = 1.4426950408889634
+BF16 = torch.bfloat16
+
+
+def _pad_to(n, m):
+    return (n + m - 1) // m * m
+
+
+class Geometry:
+    def __init__(self, rows, t, n_down):
+        self.rows = rows
+        self.T = [int(t)]
+        for _ in range(n_down):
+            self.T.append(self.T[-1] // 2)
+        if self.T[-1] < 1 or any(tl < 4 for tl in self.T[:-1]):
+            raise RuntimeError(f"sequence length {t} too short for {n_down} stride-2 stages")
+        self.Tp = [0] * (n_down + 1)
+        self.Tp[-1] = self.T[-1] + 1
+        for lvl in reversed(range(n_down)):
+            self.Tp[lvl] = 2 * self.Tp[lvl + 1]
+        for lvl in range(n_down + 1):
+            assert self.Tp[lvl] >= self.T[lvl] + 1
+        self.M = [rows * tp for tp in self.Tp]
+
+
+# ------------------------------------------------------------------------ weight packing
+def _f64(p):
+    return p.detach().to(torch.float64)
+
+
+def _conv_w(w, cin_pad=None):
+    """Conv1d weight [Cout, Cin, k] -> [Cout, k*Cin_pad] (tap-major K), fp64."""
+    w = _f64(w)
+    cout, cin, k = w.shape
+    cin_pad = cin_pad or cin
+    out = torch.zeros(cout, k, cin_pad, dtype=torch.float64, device=w.device)
+    out[:, :, :cin] = w.permute(0, 2, 1)
+    return out.reshape(cout, k * cin_pad)
+
+
+def _finish(w, b, dev):
+    """Pad rows to a multiple of 128, cast: W -> bf16, bias -> fp32."""
+    n = w.shape[0]
+    n_pad = _pad_to(n, 128)
+    wp = torch.zeros(n_pad, w.shape[1], dtype=torch.float64, device=w.device)
+    wp[:n] = w
+    bp = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
+    bp[:n] = b
+    return wp.to(dev, BF16).contiguous(), bp.to(dev, torch.float32).contiguous()
+
+
+def _gn(gn, dev):
+    return (gn.weight.detach().to(dev, torch.float32).contiguous(),
+            gn.bias.detach().to(dev, torch.float32).contiguous(), gn.num_groups, float(gn.eps))
+
+
+class PackedBlock:
+    pass
+
+
+def _check_channels(c, what):
+    if c % 64 != 0:
+        raise RuntimeError(f"{what}={c}: the sm_100a path needs channel counts that are "
+                           "multiples of 64 (64-wide K blocks, 8-channel GroupNorm vectors)")
+
+
+def pack_block(blk, heads, dev, film_col):
+    cin, cout = blk.in_channels, blk.out_channels
+    _check_channels(cin, "in_channels")
+    _check_channels(cout, "out_channels")
+    p = PackedBlock()
+    p.cin, p.cout, p.attn = cin, cout, bool(blk.use_attn)
+    p.gn1, p.gn2 = _gn(blk.gn1, dev), _gn(blk.gn2, dev)
+    p.film_col = film_col
+    p.w1, p.b1 = _finish(_conv_w(blk.conv1.weight), _f64(blk.conv1.bias), dev)
+    has_skip = not isinstance(blk.skip, torch.nn.Identity)
+    p.has_skip = has_skip
+    w2, b2 = _conv_w(blk.conv2.weight), _f64(blk.conv2.bias)
+    wskip = _f64(blk.skip.weight)[:, :, 0] if has_skip else None
+    bskip = _f64(blk.skip.bias) if has_skip else None
+    # plain variant (also used when forward is called without conditions)
+    if has_skip:
+        p.w2s, p.b2s = _finish(torch.cat([w2, wskip], dim=1), b2 + bskip, dev)
+    else:
+        p.w2s, p.b2s = _finish(w2, b2, dev)
+    if p.attn:
+        ca = blk.cross_attn
+        e = cout
+        if e % heads != 0 or (e // heads) not in (32, 64, 128):
+            raise RuntimeError(f"attention head dim {e}/{heads} unsupported on the sm_100a path "
+                               "(needs 32, 64 or 128)")
+        p.e, p.heads = e, heads
+        p.w2, p.b2 = _finish(w2, b2, dev)
+        qs = LOG2E / math.sqrt(e // heads)
+        wq, bq, wkv, bkv, wo, bo = [], [], [], [], [], []
+        for mha, kvp in ((ca.attn_motion, ca.motion_kv_proj), (ca.attn_text, ca.text_kv_proj)):
+            ipw, ipb = _f64(mha.in_proj_weight), _f64(mha.in_proj_bias)
+            wq.append(ipw[:e] * qs)
+            bq.append(ipb[:e] * qs)
+            wp_, bp_ = _f64(kvp.weight), _f64(kvp.bias)  # cond_dim -> e
+            wk, wv = ipw[e:2 * e], ipw[2 * e:]
+            # K = (c Wp^T + bp) Wk^T + bk  ==  c (Wk Wp)^T + (Wk bp + bk); same for V
+            wkv.append(torch.cat([wk @ wp_, wv @ wp_], dim=0))
+            bkv.append(torch.cat([wk @ bp_ + ipb[e:2 * e], wv @ bp_ + ipb[2 * e:]], dim=0))
+            wo.append(_f64(mha.out_proj.weight))
+            bo.append(_f64(mha.out_proj.bias))
+        p.wq, p.bq = _finish(torch.cat(wq, dim=0), torch.cat(bq, dim=0), dev)
+        p.wkv_m, p.bkv_m = _finish(wkv[0], bkv[0], dev)
+        p.wkv_t, p.bkv_t = _finish(wkv[1], bkv[1], dev)
+        wf, bf = _f64(ca.fuse_proj.weight), _f64(ca.fuse_proj.bias)
+        # fuse(cat(Om Wo_m^T + bo_m, Ot Wo_t^T + bo_t)) = [Om Ot] [Wf1 Wo_m, Wf2 Wo_t]^T + b
+        wof = torch.cat([wf[:, :e] @ wo[0], wf[:, e:] @ wo[1]], dim=1)
+        bof = wf[:, :e] @ bo[0] + wf[:, e:] @ bo[1] + bf
+        if has_skip:
+            wof = torch.cat([wof, wskip], dim=1)
+            bof = bof + bskip
+        p.wof, p.bof = _finish(wof, bof, dev)
+    return p
+
+
+class PackedModel:
+    def __init__(self, model, dev):
+        self.in_dim = model.in_dim
+        self.in_pad = _pad_to(model.in_dim, 64)
+        self.base = model.base_dim
+        self.dims = [model.base_dim * m for m in model.dim_mults]
+        self.cond_dim = model.cond_dim
+        _check_channels(model.cond_dim, "cond_dim")
+        self.time_dim = model.time_emb_dim
+        heads = model.attn_heads
+        lin = model.time_embedding.time_mlp[1]
+        self.time_w = lin.weight.detach().to(dev, torch.float32).contiguous()
+        self.time_b = lin.bias.detach().to(dev, torch.float32).contiguous()
+        self.w_in, self.b_in = _finish(_conv_w(model.in_proj.weight, self.in_pad),
+                                       _f64(model.in_proj.bias), dev)
+        film_w, film_b = [], []
+        col = [0]
+
+        def pack(blk):
+            pb = pack_block(blk, heads, dev, col[0])
+            film_w.append(blk.film.net[1].weight.detach().float())
+            film_b.append(blk.film.net[1].bias.detach().float())
+            col[0] += 2 * blk.out_channels
+            return pb
+
+        self.downs = []
+        for stage in model.downs:
+            blocks = [pack(b) for b in stage["blocks"]]
+            wd, bd = _finish(_conv_w(stage["down"].conv.weight), _f64(stage["down"].conv.bias), dev)
+            self.downs.append((blocks, wd, bd))
+        self.mid = [pack(b) for b in model.mid.blocks]
+        self.ups = []
+        for stage in model.ups:
+            wu, bu = _finish(_conv_w(stage["up"].conv.weight), _f64(stage["up"].conv.bias), dev)
+            blocks = [pack(b) for b in stage["blocks"]]
+            self.ups.append((wu, bu, blocks))
+        self.film_cols = col[0]
+        self.film_w = torch.cat(film_w, dim=0).to(dev).contiguous()
+        self.film_b = torch.cat(film_b, dim=0).to(dev).contiguous()
+        self.gn_out = _gn(model.out_proj[0], dev)
+        self.w_out, self.b_out = _finish(_conv_w(model.out_proj[2].weight),
+                                         _f64(model.out_proj[2].bias), dev)
+        self.attn_blocks = [b for blocks, _, _ in self.downs for b in blocks if b.attn]
+        self.attn_blocks += [b for b in self.mid if b.attn]
+        self.attn_blocks += [b for _, _, blocks in self.ups for b in blocks if b.attn]
+
+
+# ------------------------------------------------------------------------------ the plan
+class UNetPlan:
+    """Static launch list for `rows` clip-rows of length T attending to `lk` condition
+    frames held in `nslots` K/V cache slots. `copies` rows share each input clip
+    (CFG: copies=2, rows = 2B, row k*B+b reads clip b)."""
+
+    def __init__(self, pm, rows, t, lk, nslots, copies, use_cond, dev):
+        self.pm, self.rows, self.t, self.lk, self.nslots = pm, rows, t, lk, nslots
+        self.copies, self.use_cond, self.dev = copies, use_cond, dev
+        assert rows % copies == 0
+        self.batch = rows // copies
+        n_down = len(pm.dims)
+        g = self.geo = Geometry(rows, t, n_down)
+        z = lambda m, c, dt=BF16: torch.zeros(m, c, dtype=dt, device=dev)  # noqa: E731
+
+        # static I/O
+        self.x_in = torch.zeros(self.batch, pm.in_dim, t, dtype=torch.float32, device=dev)
+        self.t_in = torch.zeros(rows, dtype=torch.int64, device=dev)
+        self.eps = torch.zeros(rows, pm.in_dim, t, dtype=torch.float32, device=dev)
+        self.kv_slot = torch.zeros(rows, dtype=torch.int32, device=dev)
+        self.silu_temb = torch.zeros(rows, pm.time_dim, dtype=torch.float32, device=dev)
+        self.film = torch.zeros(rows, pm.film_cols, dtype=torch.float32, device=dev)
+
+        # scratch slabs shared by all blocks (sized for the largest level)
+        cmax = 0
+        for lvl in range(n_down + 1):
+            width = 2 * pm.dims[min(lvl, n_down - 1)]
+            if lvl < n_down:
+                width = max(width, pm.dims[min(lvl + 1, n_down - 1)])  # upsampled input
+            cmax = max(cmax, g.M[lvl] * max(width, pm.base))
+        flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
+        self._norm, self._h1, self._norm2, self._h2, self._q, self._o, self._xup = (
+            flat(), flat(), flat(), flat(), flat(), flat(), flat())
+        self._pp = [flat(), flat()]  # block outputs ping-pong
+        self.x_slab = z(g.M[0], pm.in_pad)
+        self.cat = [z(g.M[lvl], 2 * pm.dims[lvl]) for lvl in range(n_down)]
+
+        # K/V caches: per attention block [nslots*lk, 2E] per stream (K | V)
+        self.kv = []
+        if use_cond:
+            self.cond_m = z(nslots * lk, pm.cond_dim)
+            self.cond_t = z(nslots * lk, pm.cond_dim)
+            for b in pm.attn_blocks:
+                self.kv.append((z(nslots * lk, 2 * b.e), z(nslots * lk, 2 * b.e)))
+        self.ops = []
+        self.kv_ops = []
+        self._build()
+
+    # -- helpers -------------------------------------------------------------------------
+    def _view(self, flat, m, c):
+        return flat[: m * c].view(m, c)
+
+    def _add(self, fn, *args):
+        self.ops.append((fn, args))
+
+    def _conv(self, *a, **k):
+        self._add(ops.conv1d, ops.make_conv_desc(*a, **k))
+
+    def _resblock(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv):
+        """xin/out: (tensor, ld, channel offset) views of slabs at level `lvl`."""
+        g, rows = self.geo, self.rows
+        m, tp, tv = g.M[lvl], g.Tp[lvl], g.T[lvl]
+        cin, cout = p.cin, p.cout
+        norm = self._view(self._norm, m, cin)
+        h1 = self._view(self._h1, m, cout)
+        norm2 = self._view(self._norm2, m, cout)
+        gm, bt, groups, eps = p.gn1
+        self._add(ops.gn_silu, xin, xin_ld, norm, cin, gm, bt, rows, tp, tv, cin, groups, eps,
+                  True, xin_off, 0)
+        self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
+                   film=self.film, film_col=p.film_col, film_shift_off=cout)
+        gm, bt, groups, eps = p.gn2
+        self._add(ops.gn_silu, h1, cout, norm2, cout, gm, bt, rows, tp, tv, cout, groups, eps,
+                  True, 0, 0)
+        skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xin_off)] if p.has_skip else []
+        res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xin_off)
+        if not (p.attn and self.use_cond):
+            self._conv([Seg(norm2, cout, cout, TAPS_K3, m)] + skip_seg, p.w2s, p.b2s, cout, m,
+                       tp, tv, out, out_ld, out_chan_off=out_off, **res)
+            return
+        e = p.e
+        h2 = self._view(self._h2, m, cout)
+        q = self._view(self._q, m, 2 * e)
+        o = self._view(self._o, m, 2 * e)
+        kv_m, kv_t = kv
+        self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.w2, p.b2, cout, m, tp, tv, h2, cout)
+        self._conv([Seg(h2, cout, cout, TAPS_K1, m)], p.wq, p.bq, 2 * e, m, tp, tv, q, 2 * e)
+        self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e),
+                  ops._ptr(kv_t), ops._ptr(kv_t, e), 2 * e, self.kv_slot, rows, tp, tv, self.lk,
+                  e, p.heads)
+        self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
+                   out, out_ld, out_chan_off=out_off, **res)
+
+    # -- plan construction ----------------------------------------------------------------
+    def _build(self):
+        pm, g, rows = self.pm, self.geo, self.rows
+        n_down = len(pm.dims)
+        kv_iter = iter(self.kv) if self.use_cond else iter(())
+        next_kv = lambda p: next(kv_iter) if (p.attn and self.use_cond) else None  # noqa: E731
+
+        if self.use_cond:
+            for p, (kv_m, kv_t) in zip(pm.attn_blocks, self.kv):
+                n = self.nslots * self.lk
+                for cond, w, b, dst in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m),
+                                        (self.cond_t, p.wkv_t, p.bkv_t, kv_t)):
+                    self.kv_ops.append((ops.conv1d, (ops.make_conv_desc(
+                        [Seg(cond, pm.cond_dim, pm.cond_dim, TAPS_K1, n)], w, b, 2 * p.e, n,
+                        self.lk, self.lk, dst, 2 * p.e),)))
+
+        # timestep embedding + all FiLM tables, once per step
+        self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, rows,
+                  pm.time_dim)
+        self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, rows, pm.time_dim,
+                  pm.film_cols)
+        # x -> bf16 slab (CFG row duplication happens here), in_proj
+        self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
+                  self.t, g.Tp[0], pm.in_pad)
+        cur = self._view(self._pp[0], g.M[0], pm.base)
+        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
+                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base)
+        cur_c, pp = pm.base, 1
+
+        # down path: the last block of each stage writes straight into the second half of
+        # the level's concat slab (= the skip connection), the stride-2 conv reads it there
+        for lvl, (blocks, wd, bd) in enumerate(pm.downs):
+            dim = pm.dims[lvl]
+            cur_ld, cur_off = cur_c, 0
+            for bi, p in enumerate(blocks):
+                last = bi == len(blocks) - 1
+                if last:
+                    out, out_ld, out_off = self.cat[lvl], 2 * dim, dim
+                else:
+                    out = self._view(self._pp[pp], g.M[lvl], p.cout)
+                    out_ld, out_off = p.cout, 0
+                    pp ^= 1
+                self._resblock(p, lvl, cur, cur_ld, cur_off, out, out_ld, out_off, next_kv(p))
+                cur, cur_ld, cur_off, cur_c = out, out_ld, out_off, p.cout
+            nxt = self._view(self._pp[pp], g.M[lvl + 1], dim)
+            pp ^= 1
+            self._conv([Seg(cur, cur_ld, dim, TAPS_K4S2, g.M[lvl], cur_off)], wd, bd, dim,
+                       g.M[lvl + 1], g.Tp[lvl + 1], g.T[lvl + 1], nxt, dim)
+            cur, cur_c = nxt, dim
+
+        lvl = n_down
+        for p in pm.mid:
+            out = self._view(self._pp[pp], g.M[lvl], p.cout)
+            pp ^= 1
+            self._resblock(p, lvl, cur, cur_c, 0, out, p.cout, 0, next_kv(p))
+            cur, cur_c = out, p.cout
+
+        # up path: interp x2 -> conv k3 into the first half of the concat slab (slots past
+        # 2*T_{l+1} stay zero = F.pad), then the ResBlocks read the concat slab directly
+        for i, (wu, bu, blocks) in enumerate(pm.ups):
+            lvl = n_down - 1 - i
+            dim = pm.dims[lvl]
+            t_up = 2 * g.T[lvl + 1]
+            assert t_up <= g.T[lvl]
+            xup = self._view(self._xup, g.M[lvl], cur_c)
+            self._add(ops.upsample2x, cur, cur_c, xup, cur_c, rows, g.Tp[lvl + 1], g.T[lvl + 1],
+                      g.Tp[lvl], cur_c)
+            self._conv([Seg(xup, cur_c, cur_c, TAPS_K3, g.M[lvl])], wu, bu, dim, g.M[lvl],
+                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim)
+            cur, cur_ld, cur_c = self.cat[lvl], 2 * dim, 2 * dim
+            for p in blocks:
+                out = self._view(self._pp[pp], g.M[lvl], p.cout)
+                pp ^= 1
+                self._resblock(p, lvl, cur, cur_ld, 0, out, p.cout, 0, next_kv(p))
+                cur, cur_ld, cur_c = out, p.cout, p.cout
+
+        # out_proj: GN + SiLU + 1x1 conv, written as fp32 [rows, in_dim, T]
+        gm, bt, groups, eps = pm.gn_out
+        norm = self._view(self._norm, g.M[0], cur_c)
+        self._add(ops.gn_silu, cur, cur_c, norm, cur_c, gm, bt, rows, g.Tp[0], g.T[0], cur_c,
+                  groups, eps, True, 0, 0)
+        self._conv([Seg(norm, cur_c, cur_c, TAPS_K1, g.M[0])], pm.w_out, pm.b_out, pm.in_dim,
+                   g.M[0], g.Tp[0], g.T[0], self.eps, 0, out_mode=OUT_F32_NCT, block_n=128)
+
+    # -- execution --------------------------------------------------------------------
+    def set_conditions(self, motion_f, text_f, kv_slot):
+        """motion_f / text_f: fp32 [nslots, lk, cond_dim]; builds every layer's K/V cache
+        (step-invariant: reference recomputes them every step, cross_attention.py:46-61)."""
+        assert self.use_cond
+        n, lk, c = self.nslots, self.lk, self.pm.cond_dim
+        if tuple(motion_f.shape) != (n, lk, c) or tuple(text_f.shape) != (n, lk, c):
+            raise RuntimeError(f"conditions must be ({n}, {lk}, {c}); got "
+                               f"{tuple(motion_f.shape)} / {tuple(text_f.shape)}")
+        ops.ingest_seq(motion_f.contiguous().float(), self.cond_m, n, lk, c, lk, c)
+        ops.ingest_seq(text_f.contiguous().float(), self.cond_t, n, lk, c, lk, c)
+        for fn, args in self.kv_ops:
+            fn(*args)
+        self.kv_slot.copy_(kv_slot.to(torch.int32))
+
+    def run(self):
+        for fn, args in self.ops:
+            fn(*args)
+        return self.eps
+
+
+class UNetEngine:
+    def __init__(self, model):
+        p = next(model.parameters())
+        ops.require_device(p)
+        self.dev = p.device
+        self.pm = PackedModel(model, self.dev)
+        self.plans = {}
+        self._cond_key = None
+
+    def plan(self, rows, t, lk, nslots, copies=1, use_cond=True):
+        key = (rows, t, lk, nslots, copies, use_cond)
+        if key not in self.plans:
+            self.plans[key] = UNetPlan(self.pm, rows, t, lk, nslots, copies, use_cond, self.dev)
+        return self.plans[key]
+
+    def forward(self, x, t, motion_f=None, text_f=None):
+        ops.require_device(x)
+        if x.dim() != 3 or x.shape[1] != self.pm.in_dim:
+            raise RuntimeError(f"expected x of shape (B, {self.pm.in_dim}, T); got {tuple(x.shape)}")
+        b, _, tlen = x.shape
+        use_cond = motion_f is not None and text_f is not None
+        lk = motion_f.shape[1] if use_cond else 0
+        if use_cond and (motion_f.shape[0] != b or text_f.shape[0] != b
+                         or text_f.shape[1] != lk):
+            raise RuntimeError("motion_f / text_f must be (B, Lk, cond_dim) with matching B, Lk")
+        plan = self.plan(b, tlen, lk, b if use_cond else 0, 1, use_cond)
+        if use_cond:
+            key = (id(plan), motion_f.data_ptr(), motion_f._version, text_f.data_ptr(),
+                   text_f._version)
+            if key != self._cond_key:
+                plan.set_conditions(motion_f, text_f,
+                                    torch.arange(b, device=self.dev, dtype=torch.int32))
+                self._cond_key = key
+        if not torch.is_tensor(t):
+            t = torch.full((b,), int(t), device=self.dev, dtype=torch.int64)
+        plan.x_in.copy_(x)
+        plan.t_in.copy_(t.reshape(-1).expand(b) if t.numel() == 1 else t)
+        return plan.run().clone()

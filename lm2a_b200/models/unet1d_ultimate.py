@@ -1,0 +1,178 @@
+"""UNet1D_ultimate — drop-in for the reference noise predictor
+(reference models/unet1d_ultimate.py:273-426).
+
+The nn.Module tree below only *holds parameters* under the reference's names, so
+`state_dict()` / `load_state_dict()` / `.to()` / `.eval()` and checkpoints are
+interchangeable with the reference (306 tensors, same keys, same shapes, same
+construction order -> same seeded init). `forward` does not run a single PyTorch op on
+activations: it hands raw device pointers to the sm_100a kernels through the C ABI
+(lm2a_b200/engine.py builds the launch plan).
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .cross_attention import CrossAttentionFusion
+from .embedding import TimestepEmbedding
+
+
+def default_num_groups(channels: int) -> int:
+    """Largest of 8/4/2/1 dividing `channels` (reference unet1d_ultimate.py:29-40)."""
+    for g in (8, 4, 2, 1):
+        if channels % g == 0:
+            return g
+    return 1
+
+
+def _no_standalone(name):
+    def forward(self, *a, **k):
+        raise RuntimeError(f"{name} runs only inside UNet1D_ultimate.forward on the fused "
+                           "sm_100a path (lm2a_b200 has no per-module PyTorch fallback)")
+    return forward
+
+
+class FiLMMOD(nn.Module):
+    """t_emb -> (scale, shift); reference unet1d_ultimate.py:43-65."""
+
+    def __init__(self, time_emb_dim: int, out_channels: int):
+        super().__init__()
+        self.net = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, out_channels * 2))
+
+    forward = _no_standalone("FiLMMOD")
+
+
+class ResBlock1D(nn.Module):
+    """GN-SiLU-conv3 -> FiLM -> GN-SiLU-conv3 -> [cross-attn replaces h] -> + skip(x);
+    reference unet1d_ultimate.py:68-159."""
+
+    def __init__(self, in_channels: int, out_channels: int, time_emb_dim: int,
+                 cond_dim: int = 128, use_attn: bool = False, num_heads: int = 4):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.conv1 = nn.Conv1d(in_channels, out_channels, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv1d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.gn1 = nn.GroupNorm(default_num_groups(in_channels), in_channels)
+        self.gn2 = nn.GroupNorm(default_num_groups(out_channels), out_channels)
+        self.act = nn.SiLU()
+        self.film = FiLMMOD(time_emb_dim, out_channels)
+        self.dropout = nn.Dropout(p=0.1)  # identity at sampling time
+        self.use_attn = use_attn
+        if use_attn:
+            self.cross_attn = CrossAttentionFusion(mel_dim=out_channels, cond_dim=cond_dim,
+                                                   num_heads=num_heads)
+        if in_channels != out_channels:
+            self.skip = nn.Conv1d(in_channels, out_channels, kernel_size=1)
+        else:
+            self.skip = nn.Identity()
+
+    forward = _no_standalone("ResBlock1D")
+
+
+class MidBlock(nn.Module):
+    """Reference unet1d_ultimate.py:162-207."""
+
+    def __init__(self, channels: int, time_emb_dim: int, cond_dim: int = 128,
+                 num_blocks: int = 3, attn_every: int = 1, num_heads: int = 4):
+        super().__init__()
+        self.blocks = nn.ModuleList([
+            ResBlock1D(channels, channels, time_emb_dim, cond_dim,
+                       use_attn=(i % attn_every == 0), num_heads=num_heads)
+            for i in range(num_blocks)])
+
+    forward = _no_standalone("MidBlock")
+
+
+class UpSampleConv(nn.Module):
+    """x2 linear interpolation (align_corners=True) + conv k3; reference :210-239."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 3):
+        super().__init__()
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size,
+                              padding=kernel_size // 2)
+
+    forward = _no_standalone("UpSampleConv")
+
+
+class DownSampleConv(nn.Module):
+    """conv k4 s2 p1; reference :242-270."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int = 4,
+                 stride: int = 2, padding: int = 1):
+        super().__init__()
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride,
+                              padding=padding)
+
+    forward = _no_standalone("DownSampleConv")
+
+
+class UNet1D_ultimate(nn.Module):
+    def __init__(self, in_dim: int = 80, base_dim: int = 128,
+                 dim_mults: Tuple[int, ...] = (1, 2, 4), cond_dim: int = 128,
+                 time_emb_dim: int = 256, num_res_blocks: int = 2, mid_blocks: int = 3,
+                 attn_heads: int = 4):
+        super().__init__()
+        self.in_dim, self.base_dim, self.dim_mults = in_dim, base_dim, tuple(dim_mults)
+        self.cond_dim, self.time_emb_dim = cond_dim, time_emb_dim
+        self.num_res_blocks, self.attn_heads = num_res_blocks, attn_heads
+
+        self.time_embedding = TimestepEmbedding(time_emb_dim)
+        self.in_proj = nn.Conv1d(in_dim, base_dim, kernel_size=1)
+        dims = [base_dim * m for m in dim_mults]
+
+        self.downs = nn.ModuleList()
+        prev = base_dim
+        for dim in dims:
+            blocks = nn.ModuleList()
+            for b in range(num_res_blocks):
+                blocks.append(ResBlock1D(prev, dim, time_emb_dim, cond_dim,
+                                         use_attn=(b == num_res_blocks - 1),
+                                         num_heads=attn_heads))
+                prev = dim
+            self.downs.append(nn.ModuleDict({
+                "blocks": blocks,
+                "down": DownSampleConv(dim, dim, kernel_size=4, stride=2, padding=1)}))
+
+        self.mid = MidBlock(prev, time_emb_dim, cond_dim, num_blocks=mid_blocks, attn_every=1,
+                            num_heads=attn_heads)
+
+        self.ups = nn.ModuleList()
+        for dim in reversed(dims):
+            up = UpSampleConv(prev, dim)
+            blocks = nn.ModuleList()
+            for b in range(num_res_blocks):
+                blocks.append(ResBlock1D(dim * 2 if b == 0 else dim, dim, time_emb_dim, cond_dim,
+                                         use_attn=(b == 0), num_heads=attn_heads))
+            self.ups.append(nn.ModuleDict({"up": up, "blocks": blocks}))
+            prev = dim
+
+        self.out_proj = nn.Sequential(
+            nn.GroupNorm(default_num_groups(prev), prev), nn.SiLU(),
+            nn.Conv1d(prev, in_dim, kernel_size=1))
+
+        self._engine = None  # built lazily on the first CUDA forward
+
+    # -- engine plumbing ---------------------------------------------------------------
+    def engine(self):
+        from ..engine import UNetEngine
+        if self._engine is None:
+            self._engine = UNetEngine(self)
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None  # device / dtype moved: packed weights are stale
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor,
+                motion_f: Optional[torch.Tensor] = None,
+                text_f: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x (B, in_dim, T) fp32, t (B,) long, motion_f / text_f (B, Lk, cond_dim)
+        -> predicted noise (B, in_dim, T) fp32. Same contract as the reference forward
+        (unet1d_ultimate.py:367-426); inference only."""
+        return self.engine().forward(x, t, motion_f, text_f)

@@ -1,0 +1,130 @@
+"""Python-side launchers for the C ABI (include/lm2a_b200.h).
+
+Tensors are only carriers of device memory here: every function passes raw device
+pointers, sizes and torch's *current* CUDA stream to liblm2a_b200.so, so the launches
+are captured when called under torch.cuda.graph().
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (OUT_BF16_SLAB, OUT_F32_NCT, TAPS_K1, TAPS_K3, TAPS_K4S2,  # noqa: F401
+                   ConvDesc)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, elem_offset=0):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
+
+
+def require_device(t):
+    if not t.is_cuda:
+        raise RuntimeError("lm2a_b200 runs on CUDA sm_100a only (no CPU path); got a CPU tensor")
+    _lib.check(_lib.load().lm2a_check_device(), "lm2a_check_device")
+
+
+def launch_count():
+    return int(_lib.load().lm2a_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().lm2a_reset_launch_count()
+
+
+class Seg:
+    """One K segment of the implicit GEMM: a bf16 slab view (tensor + channel offset)."""
+
+    def __init__(self, slab, ld, cin, taps, rows, chan_off=0):
+        self.slab, self.ld, self.cin, self.taps, self.rows, self.chan_off = (
+            slab, ld, cin, taps, rows, chan_off)
+
+
+def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan_off=0,
+                   film=None, film_col=0, film_shift_off=0, residual=None, res_ld=0,
+                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0):
+    """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
+    alive by attaching them to the descriptor object."""
+    d = ConvDesc()
+    for i, s in enumerate(segs):
+        d.seg[i].x = s.slab.data_ptr() + s.chan_off * 2
+        d.seg[i].rows = s.rows
+        d.seg[i].ld = s.ld
+        d.seg[i].cin = s.cin
+        d.seg[i].taps = s.taps
+    d.w = w.data_ptr()
+    d.n_pad = w.shape[0]
+    d.n_valid = n_valid
+    d.m = m
+    d.tp = tp
+    d.t_valid = t_valid
+    d.bias = bias.data_ptr()
+    if film is not None:
+        d.film = film.data_ptr() + film_col * 4
+        d.film_ld = film.shape[1]
+        d.film_shift_off = film_shift_off
+    if residual is not None:
+        d.residual = residual.data_ptr() + res_chan_off * 2
+        d.res_ld = res_ld
+    d.out_mode = out_mode
+    d.out = out.data_ptr() + out_chan_off * out.element_size()
+    d.out_ld = out_ld
+    d.block_n = block_n
+    d._keep = (segs, w, bias, film, residual, out)
+    return d
+
+
+def conv1d(desc):
+    _lib.check(_lib.load().lm2a_conv1d_bf16(_stream(), ctypes.byref(desc)), "lm2a_conv1d_bf16")
+
+
+def gn_silu(x, x_ld, y, y_ld, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-5, silu=True,
+            x_chan_off=0, y_chan_off=0):
+    _lib.check(_lib.load().lm2a_gn_silu_bf16(
+        _stream(), _ptr(x, x_chan_off), x_ld, _ptr(y, y_chan_off), y_ld, _ptr(gamma), _ptr(beta),
+        rows, tp, t_valid, c, groups, eps, 1 if silu else 0), "lm2a_gn_silu_bf16")
+
+
+def cross_attn(q, q_ld, o, o_ld, k_m, v_m, k_t, v_t, kv_ld, kv_slot, rows, tp, t_valid, lk, e,
+               heads):
+    _lib.check(_lib.load().lm2a_cross_attn_bf16(
+        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, v_m, k_t, v_t, kv_ld, _ptr(kv_slot), rows,
+        tp, t_valid, lk, e, heads), "lm2a_cross_attn_bf16")
+
+
+def time_mlp(t, w, b, out, rows, dim):
+    _lib.check(_lib.load().lm2a_time_mlp(_stream(), _ptr(t), _ptr(w), _ptr(b), _ptr(out), rows,
+                                         dim), "lm2a_time_mlp")
+
+
+def film(s, w, b, out, rows, dim, cols):
+    _lib.check(_lib.load().lm2a_film(_stream(), _ptr(s), _ptr(w), _ptr(b), _ptr(out), rows, dim,
+                                     cols), "lm2a_film")
+
+
+def ingest_x(x, slab, batch, copies, c, t, tp, ld):
+    _lib.check(_lib.load().lm2a_ingest_x(_stream(), _ptr(x), _ptr(slab), batch, copies, c, t, tp,
+                                         ld), "lm2a_ingest_x")
+
+
+def ingest_seq(x, slab, rows, t, c, tp, ld):
+    _lib.check(_lib.load().lm2a_ingest_seq(_stream(), _ptr(x), _ptr(slab), rows, t, c, tp, ld),
+               "lm2a_ingest_seq")
+
+
+def upsample2x(x, x_ld, y, y_ld, rows, tp_in, t_in, tp_out, c):
+    _lib.check(_lib.load().lm2a_upsample2x_bf16(_stream(), _ptr(x), x_ld, _ptr(y), y_ld, rows,
+                                                tp_in, t_in, tp_out, c), "lm2a_upsample2x_bf16")
+
+
+def cfg_posterior(x, eps, noise, sched, t_dev, ticket, batch, elems_per_clip, guidance, guided,
+                  advance, eps_out=None):
+    _lib.check(_lib.load().lm2a_cfg_posterior(
+        _stream(), _ptr(x), _ptr(eps), _ptr(noise), _ptr(sched), _ptr(t_dev), t_dev.numel(),
+        _ptr(ticket), batch, elems_per_clip, float(guidance), 1 if guided else 0,
+        1 if advance else 0, _ptr(eps_out)), "lm2a_cfg_posterior")

@@ -1,0 +1,106 @@
+"""Pins oracle/lm2a_oracle.py against outputs of the reference itself
+(tests/golden/*.npz, produced by oracle/make_golden.py importing /root/reference).
+CPU only. fp32 oracle vs fp32 reference: same torch primitives -> agreement to rounding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import lm2a_oracle as orc
+
+
+def _cfg_from(arr):
+    a = [int(v) for v in arr]
+    return orc.UNetConfig(a[0], a[1], tuple(a[7:]), a[2], a[3], a[4], a[5], a[6])
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_default", "unet_production", "unet_b64"])
+def test_unet_forward_matches_reference(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = _cfg_from(d["cfg"])
+    sd = orc.random_state_dict(cfg, int(d["seed"]))
+    x, t = torch.from_numpy(d["x"]), torch.from_numpy(d["t"])
+    mf, tf = torch.from_numpy(d["motion_f"]), torch.from_numpy(d["text_f"])
+    with torch.no_grad():
+        eps = orc.unet_forward(sd, cfg, x, t, mf, tf)
+        eps_nc = orc.unet_forward(sd, cfg, x, t)
+    assert eps.shape == d["eps"].shape
+    assert _rel(eps.numpy(), d["eps"]) < 2e-5
+    assert _rel(eps_nc.numpy(), d["eps_nocond"]) < 2e-5
+    # fp64 arbiter agrees with the fp32 reference to fp32 rounding
+    sd64 = orc.cast_state_dict(sd, torch.float64)
+    with torch.no_grad():
+        eps64 = orc.unet_forward(sd64, cfg, x.double(), t, mf.double(), tf.double())
+    assert _rel(eps64.numpy(), d["eps"]) < 1e-4
+
+
+def test_state_dict_spec_matches_production_inventory():
+    # 134 292 816 params in 306 tensors for the production config
+    spec = orc.state_dict_spec(orc.UNetConfig.production())
+    assert len(spec) == 306
+    assert sum(int(np.prod(s)) for _, s in spec) == 134292816
+
+
+def test_cond_projection(golden_dir):
+    d = np.load(os.path.join(golden_dir, "cond_proj.npz"))
+    sd = orc.random_cond_proj_state_dict(seed=7)
+    mf, tf = orc.cond_projection(sd, torch.from_numpy(d["motion"]), torch.from_numpy(d["lyrics"]))
+    assert _rel(mf.numpy(), d["motion_f"]) < 1e-6
+    assert _rel(tf.numpy(), d["text_f"]) < 1e-6
+
+
+def test_tables_and_p_sample(golden_dir):
+    d = np.load(os.path.join(golden_dir, "p_sample.npz"))
+    betas, alphas, abars = orc.diffusion_tables(50)
+    np.testing.assert_array_equal(betas.numpy(), d["betas"])
+    np.testing.assert_array_equal(alphas.numpy(), d["alphas"])
+    np.testing.assert_array_equal(abars.numpy(), d["alpha_bars"])
+    cfg = orc.UNetConfig(80, 16, (1, 2, 4), 32, 32, 2, 3, 4)
+    sd = orc.random_state_dict(cfg, 3)
+    x = torch.from_numpy(d["x"])
+    mf, tf = torch.from_numpy(d["motion_f"]), torch.from_numpy(d["text_f"])
+    for tt in (49, 7, 0):
+        with torch.no_grad():
+            eps = orc.cfg_step_eps(sd, cfg, x, tt, mf, tf, 1.0)
+            xp = orc.posterior_step(x, eps, tt, (betas, alphas, abars),
+                                    torch.from_numpy(d[f"noise_t{tt}"]))
+        assert _rel(xp.numpy(), d[f"x_prev_t{tt}"]) < 1e-5
+
+
+def test_match_len_interp(golden_dir):
+    d = np.load(os.path.join(golden_dir, "sample_from_npz.npz"))
+    t = d["mel"].shape[1]
+    np.testing.assert_array_equal(orc.match_len_interp(d["motion"], t), d["motion_rs"])
+    np.testing.assert_array_equal(orc.match_len_interp(d["lyrics"], t), d["lyrics_rs"])
+
+
+@pytest.mark.parametrize("gw", [1.0, 2.1])
+def test_sample_loop_matches_sample_from_npz(golden_dir, gw):
+    """The restated batched loop reproduces reference sample.sample_from_npz (sample.py:42-278)
+    for B=1 with the reference's RNG draw order (one randn for x_T, one randn_like per t>0)."""
+    d = np.load(os.path.join(golden_dir, "sample_from_npz.npz"))
+    key = "gw%d" % int(gw * 10)
+    cfg = orc.UNetConfig.production()
+    sd = orc.random_state_dict(cfg, 5)
+    cp = orc.random_cond_proj_state_dict(seed=7)
+    t_len = d["mel"].shape[1]
+    motion = torch.from_numpy(orc.match_len_interp(d["motion"], t_len)[None])
+    lyrics = torch.from_numpy(orc.match_len_interp(d["lyrics"], t_len)[None])
+    steps = 4
+    with torch.no_grad():
+        mf, tf = orc.cond_projection(cp, motion, lyrics)
+        np.testing.assert_allclose(mf.numpy(), d[key + "_motion_proj"], rtol=1e-5, atol=1e-6)
+        torch.manual_seed(42)
+        x_init = torch.randn((1, 80, t_len))
+        noises = [torch.randn_like(x_init) for _ in range(steps - 1)]
+        x = orc.sample_loop(sd, cfg, mf, tf, (1, 80, t_len), steps, gw, x_init, noises)
+    mel = x.numpy()[0] * 2.0 + (-4.5)
+    assert _rel(mel, d[key + "_mel"]) < 1e-4
+    mse, cos = orc.mel_metrics(mel, d[key + "_mel"])
+    assert mse < 1e-6 and cos > 0.99999
