@@ -134,7 +134,7 @@ int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
 /* x [B,c,T] fp32 updated in place. eps: fp32 [2B,c,T] (uncond rows first)
  * when guided != 0, else [B,c,T]. sched: fp32 [steps,4] rows
  * {1/sqrt(alpha_t), beta_t/sqrt(1-abar_t), sqrt(beta_t), 0}; t_dev: int64[rows]
- * device timestep vector (element 0 indexes sched); noise may be NULL only if
+ * device timestep vector (entry b < B is clip b's t and indexes sched); noise may be NULL only if
  * every call has t == 0. If advance != 0 the kernel's last block decrements
  * all n_t entries of t_dev afterwards (graph replay); `ticket` is a zeroed
  * device uint32 used to elect that block. eps_out (optional) receives the

@@ -158,14 +158,15 @@ cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
                      int64_t* __restrict__ t_dev, int n_t, unsigned int* __restrict__ ticket,
                      long long total_vec, long long clip_vec, int batch, float gw, int guided,
                      int advance, float* __restrict__ eps_out) {
-  const long long t_now = t_dev[0];
-  const float4 co = __ldg(reinterpret_cast<const float4*>(sched) + t_now);
-  const float coef1 = co.x, coef2 = co.y, sigma = co.z;
-  const bool add_noise = t_now > 0 && noise != nullptr;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long uncond_to_cond = (long long)batch * clip_vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += stride) {
+    // per-clip timestep (GaussianDiffusion.p_sample accepts a (B,) tensor of mixed t)
+    const long long t_now = t_dev[i / clip_vec];
+    const float4 co = __ldg(reinterpret_cast<const float4*>(sched) + t_now);
+    const float coef1 = co.x, coef2 = co.y, sigma = co.z;
+    const bool add_noise = t_now > 0 && noise != nullptr;
     const float4 xv = reinterpret_cast<const float4*>(x)[i];
     float4 e;
     if (guided) {
@@ -206,7 +207,7 @@ cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
     }
     __syncthreads();
     if (is_last) {
-      for (int k = threadIdx.x; k < n_t; k += blockDim.x) t_dev[k] = t_now - 1;
+      for (int k = threadIdx.x; k < n_t; k += blockDim.x) t_dev[k] = t_dev[k] - 1;
       if (threadIdx.x == 0) *ticket = 0u;
     }
   }

@@ -1,0 +1,291 @@
+"""Per-kernel parity tests on a real B200: every C-ABI entry point against the matching
+torch primitive (the op the reference dispatches to), on the same bf16-rounded operands so
+only accumulation order and the final bf16 store differ. Tolerances are written per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lm2a_b200 import ops as _ops
+    _ops.require_device(torch.zeros(1, device="cuda"))
+    return _ops
+
+
+def to_slab(x_nct, tp, ld=None, chan_off=0):
+    """fp32 [R, C, T] -> bf16 slab [R*tp, ld] with zero pad slots / channels."""
+    r, c, t = x_nct.shape
+    ld = ld or c
+    s = torch.zeros(r, tp, ld, dtype=BF16, device=x_nct.device)
+    s[:, :t, chan_off:chan_off + c] = x_nct.permute(0, 2, 1).to(BF16)
+    return s.view(r * tp, ld)
+
+
+def from_slab(slab, r, tp, t, c, chan_off=0):
+    return slab.view(r, tp, -1)[:, :t, chan_off:chan_off + c].permute(0, 2, 1).float()
+
+
+def pads_are_zero(slab, r, tp, t):
+    return bool((slab.view(r, tp, -1)[:, t:, :] == 0).all())
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+def pack_w(w, n_pad=None, cin_pad=None):
+    cout, cin, k = w.shape
+    cin_pad = cin_pad or cin
+    n_pad = n_pad or (cout + 127) // 128 * 128
+    out = torch.zeros(n_pad, k, cin_pad, device=w.device)
+    out[:cout, :, :cin] = w.permute(0, 2, 1)
+    return out.reshape(n_pad, k * cin_pad).to(BF16).contiguous()
+
+
+def pad_bias(b, n_pad):
+    out = torch.zeros(n_pad, device=b.device)
+    out[: b.numel()] = b
+    return out
+
+
+def bf(x):
+    return x.to(BF16).float()
+
+
+def assert_close(got, ref, rel=1e-2, what=""):
+    err = (got - ref).norm() / ref.norm().clamp_min(1e-20)
+    mx = (got - ref).abs().max()
+    assert torch.isfinite(got).all(), what
+    assert err < rel, f"{what}: rel-L2 {err:.3e} max-abs {mx:.3e}"
+
+
+@pytest.mark.parametrize("r,t,tp,cin,cout,block_n", [
+    (2, 60, 64, 64, 128, 128),      # single M tile
+    (3, 129, 130, 128, 256, 256),   # tiles span clip boundaries
+    (5, 258, 260, 256, 512, 0),     # multi-tile persistent, auto block_n
+    (64, 64, 65, 1024, 1024, 256),  # production mid level: K = 3072, all SMs busy
+])
+def test_conv_k3(ops, r, t, tp, cin, cout, block_n):
+    x = rnd(r, cin, t, seed=1)
+    w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=2)
+    b = rnd(cout, scale=0.1, seed=3)
+    xs = to_slab(x, tp)
+    out = torch.full((r * tp, cout), 7.0, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, r * tp)], pack_w(w), pad_bias(b, (cout + 127) // 128 * 128),
+                           cout, r * tp, tp, t, out, cout, block_n=block_n)
+    ops.conv1d(d)
+    torch.cuda.synchronize()
+    ref = F.conv1d(bf(x), bf(w), b, padding=1)
+    assert_close(from_slab(out, r, tp, t, cout), ref, 6e-3, "conv k3")
+    assert pads_are_zero(out, r, tp, t)
+
+
+def test_conv_k1_film_residual_and_strided_io(ops):
+    """k=1 conv reading a channel-offset view, FiLM epilogue, residual add, strided output."""
+    r, t, tp, cin, cout = 4, 100, 104, 128, 128
+    x = rnd(r, cin, t, seed=4)
+    res = rnd(r, cout, t, seed=5)
+    w = rnd(cout, cin, 1, scale=1 / math.sqrt(cin), seed=6)
+    b = rnd(cout, scale=0.1, seed=7)
+    film = rnd(r, 2 * cout + 64, scale=0.5, seed=8)  # table with a column offset of 64
+    xs = to_slab(x, tp, ld=2 * cin, chan_off=cin)     # x lives in the second half of a wider slab
+    rs = to_slab(res, tp)
+    out = torch.zeros(r * tp, 2 * cout, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(xs, 2 * cin, cin, ops.TAPS_K1, r * tp, chan_off=cin)], pack_w(w),
+                           pad_bias(b, 128), cout, r * tp, tp, t, out, 2 * cout, out_chan_off=cout,
+                           film=film, film_col=64, film_shift_off=cout, residual=rs, res_ld=cout)
+    ops.conv1d(d)
+    torch.cuda.synchronize()
+    h = F.conv1d(bf(x), bf(w), b)
+    sc, sh = film[:, 64:64 + cout], film[:, 64 + cout:64 + 2 * cout]
+    ref = h * (1 + sc[:, :, None]) + sh[:, :, None] + bf(res)
+    assert_close(from_slab(out, r, tp, t, cout, chan_off=cout), ref, 6e-3, "k1+film+res")
+    assert bool((out[:, :cout] == 0).all()), "first half of the output slab must be untouched"
+
+
+@pytest.mark.parametrize("r,t_in,c", [(2, 64, 128), (3, 129, 256), (9, 516, 256)])
+def test_conv_k4s2(ops, r, t_in, c):
+    t_out = t_in // 2
+    tp_out = t_out + 1
+    tp_in = 2 * tp_out
+    x = rnd(r, c, t_in, seed=9)
+    w = rnd(c, c, 4, scale=1 / math.sqrt(4 * c), seed=10)
+    b = rnd(c, scale=0.1, seed=11)
+    # input lives in the second half of a concat slab, exactly like the skip connection
+    xs = to_slab(x, tp_in, ld=2 * c, chan_off=c)
+    out = torch.zeros(r * tp_out, c, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(xs, 2 * c, c, ops.TAPS_K4S2, r * tp_in, chan_off=c)], pack_w(w),
+                           pad_bias(b, (c + 127) // 128 * 128), c, r * tp_out, tp_out, t_out, out, c)
+    ops.conv1d(d)
+    torch.cuda.synchronize()
+    ref = F.conv1d(bf(x), bf(w), b, stride=2, padding=1)
+    assert ref.shape[2] == t_out
+    assert_close(from_slab(out, r, tp_out, t_out, c), ref, 6e-3, "conv k4s2")
+    assert pads_are_zero(out, r, tp_out, t_out)
+
+
+def test_conv_two_segments_and_f32_nct(ops):
+    """conv2 + fused 1x1 skip conv (second K segment), and the fp32 [R, C, T] eps epilogue."""
+    r, t, tp, c1, c2, cout = 3, 77, 80, 128, 256, 128
+    a = rnd(r, c1, t, seed=12)
+    x = rnd(r, c2, t, seed=13)
+    w2 = rnd(cout, c1, 3, scale=1 / math.sqrt(3 * c1), seed=14)
+    ws = rnd(cout, c2, 1, scale=1 / math.sqrt(c2), seed=15)
+    b = rnd(cout, scale=0.1, seed=16)
+    wcat = torch.cat([pack_w(w2), pack_w(ws)], dim=1).contiguous()
+    out = torch.zeros(r * tp, cout, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(to_slab(a, tp), c1, c1, ops.TAPS_K3, r * tp),
+                            ops.Seg(to_slab(x, tp), c2, c2, ops.TAPS_K1, r * tp)], wcat,
+                           pad_bias(b, 128), cout, r * tp, tp, t, out, cout)
+    ops.conv1d(d)
+    ref = F.conv1d(bf(a), bf(w2), b, padding=1) + F.conv1d(bf(x), bf(ws))
+    torch.cuda.synchronize()
+    assert_close(from_slab(out, r, tp, t, cout), ref, 6e-3, "two segments")
+
+    n_valid = 80
+    wo = rnd(n_valid, c1, 1, scale=1 / math.sqrt(c1), seed=17)
+    bo = rnd(n_valid, scale=0.1, seed=18)
+    eps = torch.zeros(r, n_valid, t, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(to_slab(a, tp), c1, c1, ops.TAPS_K1, r * tp)], pack_w(wo, 128),
+                           pad_bias(bo, 128), n_valid, r * tp, tp, t, eps, 0,
+                           out_mode=ops.OUT_F32_NCT, block_n=128)
+    ops.conv1d(d)
+    torch.cuda.synchronize()
+    assert_close(eps, F.conv1d(bf(a), bf(wo), bo), 2e-3, "f32 nct epilogue")
+
+
+def test_conv_rejects_bad_arguments(ops):
+    x = torch.zeros(64, 64, dtype=BF16, device="cuda")
+    w = torch.zeros(128, 64, dtype=BF16, device="cuda")
+    b = torch.zeros(128, device="cuda")
+    out = torch.zeros(64, 128, dtype=BF16, device="cuda")
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        ops.conv1d(ops.make_conv_desc([ops.Seg(x, 64, 40, ops.TAPS_K1, 64)], w, b, 128, 64, 64, 64, out, 128))
+    with pytest.raises(RuntimeError, match="slots"):
+        ops.conv1d(ops.make_conv_desc([ops.Seg(x, 64, 64, ops.TAPS_K1, 32)], w, b, 128, 64, 64, 64, out, 128))
+
+
+@pytest.mark.parametrize("r,t,tp,c,groups", [(2, 37, 40, 64, 8), (3, 129, 130, 2048, 8),
+                                             (4, 516, 520, 256, 8), (2, 2064, 2080, 512, 8)])
+def test_gn_silu(ops, r, t, tp, c, groups):
+    x = rnd(r, c, t, seed=20) * 1.7 + 0.3
+    gamma = 1 + 0.1 * rnd(c, seed=21)
+    beta = 0.1 * rnd(c, seed=22)
+    xs = to_slab(x, tp)
+    y = torch.full((r * tp, c), 3.0, dtype=BF16, device="cuda")
+    ops.gn_silu(xs, c, y, c, gamma, beta, r, tp, t, c, groups)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(bf(x), groups, gamma, beta, 1e-5))
+    assert_close(from_slab(y, r, tp, t, c), ref, 5e-3, "gn+silu")
+    assert pads_are_zero(y, r, tp, t)
+
+
+@pytest.mark.parametrize("e,heads,t,lk", [(256, 8, 100, 77), (512, 8, 258, 516), (1024, 8, 64, 516),
+                                          (128, 4, 33, 64)])
+def test_cross_attention_core(ops, e, heads, t, lk):
+    r, slots, tp = 3, 2, t + 2
+    dh = e // heads
+    q = rnd(r, 2 * e, t, seed=30)
+    kv_m = rnd(slots * lk, 2 * e, seed=31).to(BF16)
+    kv_t = rnd(slots * lk, 2 * e, seed=32).to(BF16)
+    kv_slot = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
+    scale = 1.0 / math.sqrt(dh)
+    qs = to_slab(q * (scale * 1.4426950408889634), tp)
+    o = torch.zeros(r * tp, 2 * e, dtype=BF16, device="cuda")
+    ops.cross_attn(qs, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e), ops._ptr(kv_t),
+                   ops._ptr(kv_t, e), 2 * e, kv_slot, r, tp, t, lk, e, heads)
+    torch.cuda.synchronize()
+    got = from_slab(o, r, tp, t, 2 * e)
+    for s, kv in enumerate((kv_m, kv_t)):
+        kvf = kv.float().view(slots, lk, 2 * e)[kv_slot.long()]
+        k = kvf[:, :, :e].view(r, lk, heads, dh).transpose(1, 2)
+        v = kvf[:, :, e:].view(r, lk, heads, dh).transpose(1, 2)
+        qq = qs.float().view(r, tp, 2 * e)[:, :t, s * e:(s + 1) * e] / 1.4426950408889634
+        qq = qq.reshape(r, t, heads, dh).transpose(1, 2)
+        p = torch.softmax(qq @ k.transpose(-1, -2), dim=-1)
+        ref = (p @ v).transpose(1, 2).reshape(r, t, e).permute(0, 2, 1)
+        assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"attention stream {s}")
+
+
+def test_upsample2x(ops):
+    r, t_in, c = 3, 129, 128
+    tp_in, tp_out = 130, 260
+    x = rnd(r, c, t_in, seed=40)
+    y = torch.full((r * tp_out, c), 5.0, dtype=BF16, device="cuda")
+    ops.upsample2x(to_slab(x, tp_in), c, y, c, r, tp_in, t_in, tp_out, c)
+    torch.cuda.synchronize()
+    ref = F.interpolate(bf(x), scale_factor=2, mode="linear", align_corners=True)
+    assert_close(from_slab(y, r, tp_out, 2 * t_in, c), ref, 4e-3, "upsample")
+    assert pads_are_zero(y, r, tp_out, 2 * t_in)
+
+
+def test_ingest(ops):
+    b, c, t, tp, ld = 3, 80, 77, 80, 128
+    x = rnd(b, c, t, seed=41)
+    slab = torch.full((2 * b * tp, ld), 9.0, dtype=BF16, device="cuda")
+    ops.ingest_x(x, slab, b, 2, c, t, tp, ld)
+    torch.cuda.synchronize()
+    ref = to_slab(torch.cat([x, x], 0), tp, ld)
+    assert torch.equal(slab, ref)
+    seq = rnd(2, 50, 234, seed=42)
+    s2 = torch.full((2 * 50, 256), 9.0, dtype=BF16, device="cuda")
+    ops.ingest_seq(seq, s2, 2, 50, 234, 50, 256)
+    torch.cuda.synchronize()
+    ref2 = torch.zeros(2, 50, 256, dtype=BF16, device="cuda")
+    ref2[:, :, :234] = seq.to(BF16)
+    assert torch.equal(s2.view(2, 50, 256), ref2)
+
+
+def test_time_mlp_and_film(ops):
+    import lm2a_oracle as orc
+    rows, dim, cols = 5, 256, 1536
+    t = torch.tensor([999, 500, 1, 0, 37], dtype=torch.int64, device="cuda")
+    w = rnd(dim, dim, scale=1 / 16, seed=50)
+    b = rnd(dim, scale=0.02, seed=51)
+    fw = rnd(cols, dim, scale=1 / 16, seed=52)
+    fb = rnd(cols, scale=0.02, seed=53)
+    s = torch.zeros(rows, dim, device="cuda")
+    film = torch.zeros(rows, cols, device="cuda")
+    ops.time_mlp(t, w, b, s, rows, dim)
+    ops.film(s, fw, fb, film, rows, dim, cols)
+    torch.cuda.synchronize()
+    emb = orc.sinusoidal_pos_emb(t.cpu(), dim).double()
+    temb = F.silu(F.linear(emb, w.cpu().double(), b.cpu().double()))
+    ref = F.linear(F.silu(temb), fw.cpu().double(), fb.cpu().double())
+    # fp32 sin/cos of arguments up to ~1e3 rad: absolute error ~1e-4 on the embedding
+    assert_close(film.cpu().double(), ref, 2e-4, "time mlp + film")
+
+
+@pytest.mark.parametrize("guided", [True, False])
+def test_cfg_posterior_bit_exact(ops, guided):
+    """Same operation order as the reference's elementwise sequence -> bit-identical."""
+    import lm2a_oracle as orc
+    b, c, t, steps = 3, 80, 516, 1000
+    x = rnd(b, c, t, seed=60)
+    eps = rnd(2 * b if guided else b, c, t, scale=3.0, seed=61)
+    noise = rnd(b, c, t, seed=62)
+    betas, alphas, abars = orc.diffusion_tables(steps, "cuda")
+    sched = torch.stack([1.0 / alphas.sqrt(), betas / (1.0 - abars).sqrt(), betas.sqrt(),
+                         torch.zeros_like(betas)], dim=1).contiguous()
+    for tt in (999, 1, 0):
+        xx = x.clone()
+        t_dev = torch.full((2 * b,), tt, dtype=torch.int64, device="cuda")
+        ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+        eps_out = torch.zeros(b, c, t, device="cuda")
+        ops.cfg_posterior(xx, eps, noise, sched, t_dev, ticket, b, c * t, 2.1, guided, True, eps_out)
+        torch.cuda.synchronize()
+        e = orc.cfg_eps(eps[:b], eps[b:], 2.1) if guided else eps
+        ref = orc.posterior_step(x, e, tt, (betas, alphas, abars), noise)
+        assert torch.equal(eps_out, e)
+        assert torch.equal(xx, ref), f"t={tt}: max diff {(xx - ref).abs().max()}"
+        assert bool((t_dev == tt - 1).all()) and int(ticket) == 0

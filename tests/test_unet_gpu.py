@@ -1,0 +1,78 @@
+"""UNet1D_ultimate on B200 (bf16 tensor-core path through the C ABI) against
+(a) the committed reference outputs in tests/golden/ and (b) the fp32 CPU oracle.
+Tolerance: BASELINE.json north_star — single-step eps within 2e-2 relative (bf16)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import lm2a_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL_BF16 = 2e-2
+
+
+def _cfg_from(arr):
+    a = [int(v) for v in arr]
+    return orc.UNetConfig(a[0], a[1], tuple(a[7:]), a[2], a[3], a[4], a[5], a[6])
+
+
+def _model(cfg, sd):
+    from lm2a_b200.models import UNet1D_ultimate
+    net = UNet1D_ultimate(in_dim=cfg.in_dim, base_dim=cfg.base_dim, dim_mults=cfg.dim_mults,
+                          cond_dim=cfg.cond_dim, time_emb_dim=cfg.time_emb_dim,
+                          num_res_blocks=cfg.num_res_blocks, mid_blocks=cfg.mid_blocks,
+                          attn_heads=cfg.attn_heads)
+    assert list(net.state_dict().keys()) == list(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    return net.to("cuda").eval()
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name", ["unet_b64", "unet_default", "unet_production"])
+def test_forward_matches_reference_golden(golden_dir, name):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = _cfg_from(d["cfg"])
+    net = _model(cfg, orc.random_state_dict(cfg, int(d["seed"])))
+    x = torch.from_numpy(d["x"]).cuda()
+    t = torch.from_numpy(d["t"]).cuda()
+    mf, tf = torch.from_numpy(d["motion_f"]).cuda(), torch.from_numpy(d["text_f"]).cuda()
+    eps = net(x, t, mf, tf)
+    torch.cuda.synchronize()
+    assert eps.shape == x.shape and eps.dtype == torch.float32
+    err = _rel(eps, torch.from_numpy(d["eps"]))
+    assert err < TOL_BF16, f"{name}: eps rel-L2 {err:.3e}"
+    # no conditions -> attention blocks fall back to plain residual blocks (reference :152)
+    err_nc = _rel(net(x, t), torch.from_numpy(d["eps_nocond"]))
+    assert err_nc < TOL_BF16, f"{name}: no-cond eps rel-L2 {err_nc:.3e}"
+    # repeat call reuses the cached plan and K/V cache and must be deterministic
+    assert torch.equal(net(x, t, mf, tf), eps)
+
+
+def test_forward_full_length_vs_oracle():
+    """Production architecture at the canonical clip length T = Lk = 516 with CFG-style rows
+    (uncond = zeroed conditions, sample.py:155-163) against the fp32 oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = orc.UNetConfig.production()
+    sd = orc.random_state_dict(cfg, 5)
+    net = _model(cfg, sd)
+    g = torch.Generator().manual_seed(77)
+    x1 = torch.randn(1, 80, 516, generator=g)
+    mf1 = torch.randn(1, 516, 128, generator=g)
+    tf1 = torch.randn(1, 516, 128, generator=g)
+    x = torch.cat([x1, x1])
+    mf, tf = torch.cat([mf1 * 0, mf1]), torch.cat([tf1 * 0, tf1])
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        ref = orc.unet_forward(sd, cfg, x, t, mf, tf)
+    eps = net(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
+    err = _rel(eps, ref)
+    assert err < TOL_BF16, f"eps rel-L2 {err:.3e}"
