@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — CFG reverse-diffusion sampling throughput of the B200 path (and the CPU
+reference arm), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): production UNet1D_ultimate (base 256, mults 1/2/4,
+8 heads, 134 M params, random init), B = 32 clips per GPU under classifier-free guidance
+(64 rows), mel (80, 516), conditions (516, 128) per stream, guidance 2.1, bf16 tensor-core
+path. A "step" is ONE denoising step of the whole batch = one CUDA Graph replay
+(x ingest -> UNet -> CFG blend + clamps + DDPM posterior, timestep advanced on device).
+`value` = clips/s for the reference's 1000-step trajectory = N*B / (1000 * s_per_step),
+inputs resident in HBM. `e2e` = the same metric through lm2a_b200.sample.sample_clips with
+HOST inputs: pinned H2D of motion/lyrics, CondProjection, K/V cache build, all 1000 steps,
+D2H of the mels (+ one all-gather when N > 1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "cfg_step_B32_R64_T516_Lk516_unet_base256_gw2.1"
+TRAJ_STEPS = 1000
+BATCH = 32
+T_MEL = 516
+GW = 2.1
+METRIC = "cfg_sampling_mel_clips_per_sec"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1399.4), d.get("hbm_gbs", 6546.2), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_conditions(orc, first_clip, count):
+    import numpy as np
+    motions, lyrics = [], []
+    for i in range(count):
+        clip = orc.synthetic_clip(first_clip + i, t_mel=T_MEL, time_varying_lyrics=True)
+        motions.append(orc.match_len_interp(clip["motion"], T_MEL))
+        lyrics.append(orc.match_len_interp(clip["lyrics"], T_MEL))
+    return np.stack(motions), np.stack(lyrics)
+
+
+def cpu_reference_step(orc, torch, steps, warmup):
+    """Times the oracle port of the reference's CFG loop body (sample.py:144-210) on the host
+    cores: one clip (2 rows) of the same workload per step. Returns seconds per step."""
+    cfg = orc.UNetConfig.production()
+    sd = orc.random_state_dict(cfg, 5)
+    cp = orc.random_cond_proj_state_dict(seed=7)
+    motions, lyrics = synthetic_conditions(orc, 0, 1)
+    tables = orc.diffusion_tables(TRAJ_STEPS)
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        mf, tf = orc.cond_projection(cp, torch.from_numpy(motions), torch.from_numpy(lyrics))
+        x = torch.randn(1, 80, T_MEL, generator=g)
+        times = []
+        for i in range(warmup + steps):
+            t = TRAJ_STEPS - 1 - i
+            t0 = time.perf_counter()
+            eps = orc.cfg_step_eps(sd, cfg, x, t, mf, tf, GW)
+            x = orc.posterior_step(x, eps, t, tables, torch.randn(x.shape, generator=g))
+            times.append(time.perf_counter() - t0)
+    return sum(times[warmup:]) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import lm2a_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 3))
+    steps = min(steps, 40)  # bounded sample: ~0.3-0.5 s per CPU step
+    s = cpu_reference_step(orc, torch, steps, warmup)
+    value = 1.0 / (TRAJ_STEPS * s)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": s * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "1 clip (2 CFG rows) per step on host cores"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} CFG denoising steps of 1 clip (2 rows), fp32 torch CPU "
+                                   "oracle port of sample.py:144-210; x1000-step extrapolation"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lm2a_oracle as orc  # synthetic data recipe + cpu_baseline leg only
+    from lm2a_b200 import distributed as ldist
+    from lm2a_b200 import ops
+    from lm2a_b200.models import CondProjection, GaussianDiffusion, UNet1D_ultimate
+    from lm2a_b200.sample import sample_clips
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the lm2a_b200 path has no CPU fallback")
+    rank, world, local_rank = ldist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    cfg = orc.UNetConfig.production()
+    unet = UNet1D_ultimate(80, cfg.base_dim, cfg.dim_mults, cfg.cond_dim, cfg.time_emb_dim,
+                           cfg.num_res_blocks, cfg.mid_blocks, cfg.attn_heads)
+    unet.load_state_dict(orc.random_state_dict(cfg, 5))
+    unet = unet.to(dev).eval()
+    cond_proj = CondProjection(234, 768, 128)
+    cond_proj.load_state_dict(orc.random_cond_proj_state_dict(seed=7))
+    cond_proj = cond_proj.to(dev).eval()
+    diffusion = GaussianDiffusion(unet, timesteps=TRAJ_STEPS, device=dev,
+                                  dataset_mean=-4.63706636428833, dataset_std=1.8648223876953125)
+
+    motions, lyrics = synthetic_conditions(orc, rank * BATCH, BATCH)
+    sampler = diffusion.sampler(BATCH, T_MEL, T_MEL, guided=True)
+    sampler.gw = GW
+    with torch.no_grad():
+        mf, tf = cond_proj(torch.from_numpy(motions).to(dev), torch.from_numpy(lyrics).to(dev))
+        sampler.set_conditions(mf, tf)
+        torch.manual_seed(42 + rank)
+        ops.reset_launch_count()
+        sampler._ensure_graph()  # one eager warm-up step + one captured step
+        launches_per_step = ops.launch_count() // 2
+        plan = sampler.plan
+        plan.x_in.normal_()
+        plan.t_in.fill_(TRAJ_STEPS - 1)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        for _ in range(warmup):
+            sampler.graph.replay()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stream = torch.cuda.current_stream(dev)
+        e0.record(stream)
+        for _ in range(steps):
+            sampler.graph.replay()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+        finite = bool(torch.isfinite(plan.x_in).all())
+
+        # ---- dominant kernel (tcgen05 implicit-GEMM conv) timed live, launch by launch
+        plan.t_in.fill_(500)
+        prof = plan.profile(iters=5)
+        conv = [(m, s) for k, m, s in prof if k == "conv_gemm"]
+        conv_s = sum(s for _, s in conv)
+        conv_flops = sum(m["flops"] for m, _ in conv)
+        by_kind = {}
+        for k, m, s in prof:
+            by_kind[k] = by_kind.get(k, 0.0) + s
+
+        # ---- end to end through the public API with host buffers (full 1000-step trajectory)
+        barrier()
+        t0 = time.perf_counter()
+        mel, _, _ = sample_clips(unet, cond_proj, diffusion, motions, lyrics, T_MEL, GW)
+        if world > 1:
+            mine = torch.from_numpy(mel).to(dev)
+            allm = torch.empty((world * BATCH, 80, T_MEL), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(allm, mine)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_finite = bool(torch.isfinite(torch.from_numpy(mel)).all())
+
+    tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(tms[0]), float(tms[1])
+    ms_per_step = ms / steps
+    value = world * BATCH / (TRAJ_STEPS * ms_per_step * 1e-3)
+
+    if rank == 0:
+        tf_peak, hbm_peak, src = peaks()
+        step_flops = plan.flops()
+        achieved = conv_flops / conv_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "batch_per_gpu": BATCH, "rows_per_gpu": 2 * BATCH,
+                "trajectory_steps": TRAJ_STEPS, "guidance": GW, "cuda_graph": True,
+                "l2": "per-step working set (0.27 GB weights + 0.9 GB K/V cache + activations) "
+                      "exceeds the 126 MB L2; no flush between steps",
+                "parallelism": f"clip-sharded x{world}, no collective in the loop"},
+            "unet_step_us": ms_per_step * 1e3,
+            "step_gflop": step_flops / 1e9,
+            "step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
+            "step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / tf_peak,
+            "finite": finite and e2e_finite,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, "
+                         f"{len(conv)} launches/step)", "achieved": achieved, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                         "peak_source": src + " bf16_tflops_sustained",
+                         "share_of_step": conv_s / sum(by_kind.values())},
+            "kernel_ms": {k: v * 1e3 for k, v in sorted(by_kind.items())},
+            "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "clips/s",
+                    "seconds": e2e_ms * 1e-3,
+                    "h2d_bytes_per_step": int(motions.nbytes + lyrics.nbytes),
+                    "d2h_bytes_per_step": int(mel.nbytes),
+                    "note": "one step of e2e = one full 1000-step trajectory of the batch via "
+                            "lm2a_b200.sample.sample_clips (host in, host out)"},
+            "gpu_launches": int(launches_per_step * steps),
+            "launches_per_step": int(launches_per_step),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n = 20
+            s = cpu_reference_step(orc, torch, n, 2)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (TRAJ_STEPS * s), "unit": "clips/s", "cores": cores, "kind": "port",
+                "ms_per_step": s * 1e3,
+                "sample": f"{n} CFG denoising steps of 1 clip (2 rows) after 2 warm-up, fp32 torch "
+                          "CPU oracle port of sample.py:144-210; x1000-step extrapolation"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

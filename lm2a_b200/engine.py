@@ -238,11 +238,18 @@ class UNetPlan:
     def _view(self, flat, m, c):
         return flat[: m * c].view(m, c)
 
-    def _add(self, fn, *args):
-        self.ops.append((fn, args))
+    def _add(self, fn, *args, meta=None):
+        self.ops.append((fn, args, meta or {"kind": fn.__name__, "flops": 0}))
 
-    def _conv(self, *a, **k):
-        self._add(ops.conv1d, ops.make_conv_desc(*a, **k))
+    def _conv(self, segs, w, bias, n_valid, m, tp, t_valid, *a, **k):
+        """Queues one implicit-GEMM launch; meta carries its ALGORITHMIC flops
+        (valid slots x real output channels x K, no padding counted)."""
+        ntaps = {TAPS_K1: 1, TAPS_K3: 3, TAPS_K4S2: 4}
+        k_total = k.pop("k_real", None) or sum(ntaps[s.taps] * s.cin for s in segs)
+        meta = {"kind": "conv_gemm", "flops": 2 * self.rows * t_valid * n_valid * k_total,
+                "m": m, "n": n_valid, "k": k_total}
+        self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
+                  meta=meta)
 
     def _resblock(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv):
         """xin/out: (tensor, ld, channel offset) views of slabs at level `lvl`."""
@@ -275,7 +282,7 @@ class UNetPlan:
         self._conv([Seg(h2, cout, cout, TAPS_K1, m)], p.wq, p.bq, 2 * e, m, tp, tv, q, 2 * e)
         self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e),
                   ops._ptr(kv_t), ops._ptr(kv_t, e), 2 * e, self.kv_slot, rows, tp, tv, self.lk,
-                  e, p.heads)
+                  e, p.heads, meta={"kind": "cross_attn", "flops": 2 * 4 * rows * tv * self.lk * e})
         self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
                    out, out_ld, out_chan_off=out_off, **res)
 
@@ -305,7 +312,7 @@ class UNetPlan:
                   self.t, g.Tp[0], pm.in_pad)
         cur = self._view(self._pp[0], g.M[0], pm.base)
         self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
-                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base)
+                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim)
         cur_c, pp = pm.base, 1
 
         # down path: the last block of each stage writes straight into the second half of
@@ -379,9 +386,30 @@ class UNetPlan:
         self.kv_slot.copy_(kv_slot.to(torch.int32))
 
     def run(self):
-        for fn, args in self.ops:
+        for fn, args, _ in self.ops:
             fn(*args)
         return self.eps
+
+    def flops(self):
+        """Algorithmic FLOPs of one forward over all rows (K/V hoisted, out_proj.fuse folded)."""
+        return sum(meta["flops"] for _, _, meta in self.ops)
+
+    def profile(self, iters=5):
+        """Per-launch device time (CUDA events on the current stream), for bench.py's roofline
+        line and profiles/: returns [(kind, meta, seconds)] in launch order."""
+        stream = torch.cuda.current_stream(self.dev)
+        out = []
+        for fn, args, meta in self.ops:
+            fn(*args)  # warm
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+            evs[0].record(stream)
+            for i in range(iters):
+                fn(*args)
+                evs[i + 1].record(stream)
+            torch.cuda.synchronize(self.dev)
+            ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
+            out.append((meta["kind"], meta, ts[len(ts) // 2] * 1e-3))
+        return out
 
 
 class UNetEngine:

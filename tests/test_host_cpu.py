@@ -1,0 +1,161 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the
+drop-in modules keep the reference's state_dict layout, slab geometry / launch plan host logic,
+and the clip-sharding driver under gloo with world_size 2. No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import lm2a_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lm2a_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "lm2a_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(lm2a_[a-z0-9_]+)\s*\(", code))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by liblm2a_b200.so"
+    assert declared == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+    assert _lib.load().lm2a_abi_version() == 1
+
+
+def test_conv_desc_struct_matches_header_layout():
+    from lm2a_b200 import _lib
+    assert ctypes.sizeof(_lib.ConvSeg) == 32
+    assert ctypes.sizeof(_lib.ConvDesc) == 152
+    assert _lib.ConvDesc.out.offset == 136 and _lib.ConvDesc.m.offset == 80
+
+
+def test_state_dict_layout_matches_reference_inventory():
+    from lm2a_b200.models import CondProjection, UNet1D_ultimate
+    net = UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8)
+    spec = orc.state_dict_spec(orc.UNetConfig.production())  # pinned to the reference in make_golden
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(tuple(sd[k].shape) == s for k, s in spec)
+    assert sum(v.numel() for v in sd.values()) == 134292816
+    # class defaults are the reference's (base 128, 4 heads: 35.4 M params)
+    small = UNet1D_ultimate()
+    assert abs(sum(p.numel() for p in small.parameters()) - 35.4e6) < 0.1e6
+    assert set(CondProjection().state_dict()) == {"motion_proj.weight", "motion_proj.bias",
+                                                  "text_proj.weight", "text_proj.bias"}
+    res = net.load_state_dict({"in_proj.bias": torch.zeros(256)}, strict=False)  # silent partial load
+    assert len(res.missing_keys) == 305
+
+
+def test_cpu_tensors_are_refused():
+    from lm2a_b200.models import UNet1D_ultimate
+    net = UNet1D_ultimate(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 80, 64), torch.zeros(1, dtype=torch.long))
+
+
+def test_geometry_and_plan():
+    from lm2a_b200.engine import Geometry, PackedModel, UNetPlan
+    from lm2a_b200.models import UNet1D_ultimate
+    g = Geometry(64, 516, 3)
+    assert g.T == [516, 258, 129, 64] and g.Tp == [520, 260, 130, 65]
+    g = Geometry(2, 517, 3)
+    assert g.T == [517, 258, 129, 64] and all(tp >= t + 1 for tp, t in zip(g.Tp, g.T))
+    with pytest.raises(RuntimeError):
+        Geometry(1, 7, 3)
+    net = UNet1D_ultimate(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    pm = PackedModel(net, torch.device("cpu"))
+    plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
+    kinds = [m["kind"] for _, _, m in plan.ops]
+    assert kinds.count("conv_gemm") == 56 and kinds.count("gn_silu") == 31
+    assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 18
+    # K/V hoisted + out_proj.fuse folded: production net = 28.23 GFLOP per row-step at T=516
+    big = PackedModel(UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8), torch.device("cpu"))
+    gf = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu")).flops() / 2 / 1e9
+    assert abs(gf - 28.23) < 0.02
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
+
+
+def test_weight_folds_are_exact_in_fp64():
+    """q-scale, kv_proj o in_proj and out_proj o fuse_proj folds (engine.pack_block) reproduce
+    CrossAttentionFusion (cross_attention.py:38-67) when evaluated in fp64."""
+    from lm2a_b200 import engine
+    cfg = orc.UNetConfig(80, 64, (1,), 128, 64, 1, 1, 2)
+    sd = orc.cast_state_dict(orc.random_state_dict(cfg, 2), torch.float64)
+    pre = "mid.blocks.0.cross_attn"
+    e, heads, lk, tq = 64, 2, 11, 7
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(1, tq, e, generator=g, dtype=torch.float64)
+    mf = torch.randn(1, lk, 128, generator=g, dtype=torch.float64)
+    tf = torch.randn(1, lk, 128, generator=g, dtype=torch.float64)
+    ref = orc.cross_attention_fusion(sd, pre, h, mf, tf, heads)
+
+    class Holder:
+        pass
+    outs = []
+    for s, cond in (("attn_motion", mf), ("attn_text", tf)):
+        ipw, ipb = sd[f"{pre}.{s}.in_proj_weight"], sd[f"{pre}.{s}.in_proj_bias"]
+        kvn = "motion_kv_proj" if s == "attn_motion" else "text_kv_proj"
+        wp, bp = sd[f"{pre}.{kvn}.weight"], sd[f"{pre}.{kvn}.bias"]
+        qs = engine.LOG2E / np.sqrt(e // heads)
+        q = (h @ (ipw[:e] * qs).T + ipb[:e] * qs).view(1, tq, heads, -1).transpose(1, 2)
+        k = (cond @ (ipw[e:2 * e] @ wp).T + ipw[e:2 * e] @ bp + ipb[e:2 * e]).view(1, lk, heads, -1).transpose(1, 2)
+        v = (cond @ (ipw[2 * e:] @ wp).T + ipw[2 * e:] @ bp + ipb[2 * e:]).view(1, lk, heads, -1).transpose(1, 2)
+        sc = q @ k.transpose(-1, -2)
+        p = torch.exp2(sc - sc.max(-1, keepdim=True).values)
+        outs.append(((p / p.sum(-1, keepdim=True)) @ v).transpose(1, 2).reshape(1, tq, e))
+    wf, bf = sd[f"{pre}.fuse_proj.weight"], sd[f"{pre}.fuse_proj.bias"]
+    wo = [sd[f"{pre}.{s}.out_proj.weight"] for s in ("attn_motion", "attn_text")]
+    bo = [sd[f"{pre}.{s}.out_proj.bias"] for s in ("attn_motion", "attn_text")]
+    wof = torch.cat([wf[:, :e] @ wo[0], wf[:, e:] @ wo[1]], dim=1)
+    bof = wf[:, :e] @ bo[0] + wf[:, e:] @ bo[1] + bf
+    got = torch.cat(outs, dim=-1) @ wof.T + bof
+    assert float((got - ref).abs().max()) < 1e-12
+
+
+def test_match_len_modes():
+    from lm2a_b200.sample import match_len
+    a = np.arange(20, dtype=np.float32).reshape(10, 2)
+    np.testing.assert_array_equal(match_len(a, 25, "interp"), orc.match_len_interp(a, 25))
+    assert match_len(a, 10, "interp") is not None and match_len(a, 4).shape == (4, 2)
+    np.testing.assert_array_equal(match_len(a, 12)[-1], a[-1])
+
+
+def _shard_worker(rank, world, port, n_clips, batch, ret):
+    import torch.distributed as dist
+    from lm2a_b200 import distributed as ldist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = ldist.init_from_env("gloo")
+    calls = []
+
+    def fake_sampler(idx):  # "mel" of clip c is filled with c
+        calls.append(list(idx))
+        return torch.stack([torch.full((3, 5), float(c)) for c in idx])
+
+    full = ldist.sample_sharded(n_clips, batch, fake_sampler, (3, 5), "cpu", r, w)
+    ok = full.shape == (n_clips, 3, 5) and all(bool((full[c] == c).all()) for c in range(n_clips))
+    ok = ok and sorted(sum(calls, [])) == ldist.shard_indices(n_clips, r, w)
+    ok = ok and all(len(c) <= batch for c in calls)
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_clip_sharding_world2_gloo():
+    from lm2a_b200 import distributed as ldist
+    assert ldist.shard_indices(7, 1, 2) == [1, 3, 5] and ldist.padded_shard_len(1868, 8) == 234
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, 7, 2, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert ret.get(0) is True and ret.get(1) is True

@@ -1,0 +1,174 @@
+"""Guided sampling on B200 vs the oracle / the reference's own outputs.
+
+Stated tolerances (BASELINE.json north_star): single-step eps within 2e-2 relative (bf16);
+full trajectory: relative MSE (MSE / var of the reference mel) < 2e-3 and mean frame cosine
+(val.py:81-87 definition) > 0.999 against the fp32 reference with identical injected noise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import lm2a_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _b64():
+    from lm2a_b200.models import UNet1D_ultimate
+    cfg = orc.UNetConfig(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    sd = orc.random_state_dict(cfg, 6)
+    net = UNet1D_ultimate(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    net.load_state_dict(sd)
+    return cfg, sd, net.cuda().eval()
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("gw", [2.1, 1.0])
+def test_short_trajectory_vs_oracle(gw):
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    cfg, sd, net = _b64()
+    steps, bsz, t_len, lk = 8, 3, 100, 60
+    g = torch.Generator().manual_seed(123)
+    x0 = torch.randn(bsz, 80, t_len, generator=g)
+    mf = torch.randn(bsz, lk, 128, generator=g)
+    tf = torch.randn(bsz, lk, 128, generator=g)
+    noises = torch.randn(steps - 1, bsz, 80, t_len, generator=g)
+    diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    got = diff.sample_cfg((bsz, 80, t_len), mf.cuda(), tf.cuda(), gw, x_init=x0.cuda(),
+                          noises=noises.cuda())
+    with torch.no_grad():
+        ref = orc.sample_loop(sd, cfg, mf, tf, (bsz, 80, t_len), steps, gw, x0, list(noises))
+    assert torch.isfinite(got).all()
+    for b in range(bsz):
+        mse, cos = orc.mel_metrics(got[b].cpu().numpy(), ref[b].numpy())
+        assert mse / float(ref[b].var()) < 2e-3, f"clip {b}: rel MSE {mse / float(ref[b].var()):.3e}"
+        assert cos > 0.999, f"clip {b}: frame cosine {cos:.6f}"
+
+
+def test_graph_replay_equals_eager():
+    """The CUDA-Graph path (noise drawn inside the graph, timestep advanced on device) and the
+    eager path fed the SAME noise give bit-identical trajectories."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    cfg, sd, net = _b64()
+    steps, bsz, t_len = 6, 2, 72
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(bsz, 80, t_len, generator=g).cuda()
+    mf = torch.randn(bsz, t_len, 128, generator=g).cuda()
+    tf = torch.randn(bsz, t_len, 128, generator=g).cuda()
+    diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    s = diff.sampler(bsz, t_len, t_len, guided=True)
+    s.gw = 2.1
+    s.set_conditions(mf, tf)
+    s._ensure_graph()
+    s.plan.x_in.copy_(x0)
+    s.plan.t_in.fill_(steps - 1)
+    used = []
+    for i in range(steps):
+        s.graph.replay()
+        used.append(s.noise.clone())
+        assert int(s.plan.t_in[0]) == steps - 2 - i
+    x_graph = s.plan.x_in.clone()
+    x_eager = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, x_init=x0, noises=used)
+    assert torch.equal(x_graph, x_eager)
+    # and the public entry point in graph mode runs end to end
+    x_pub = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, x_init=x0)
+    assert torch.isfinite(x_pub).all() and x_pub.shape == x0.shape
+
+
+def test_p_sample_matches_oracle():
+    """GaussianDiffusion.p_sample / sample (diffusion.py:62-119) incl. mixed per-row t."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    cfg, sd, net = _b64()
+    diff = GaussianDiffusion(net, timesteps=50, device="cuda")
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(3, 80, 64, generator=g)
+    mf = torch.randn(3, 64, 128, generator=g)
+    tf = torch.randn(3, 64, 128, generator=g)
+    t = torch.tensor([49, 7, 0])
+    torch.manual_seed(77)
+    got = diff.p_sample(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
+    torch.manual_seed(77)
+    noise = torch.randn_like(x.cuda()).cpu()
+    tables = orc.diffusion_tables(50)
+    with torch.no_grad():
+        eps = orc.unet_forward(sd, cfg, x, t, mf, tf)
+    for b in range(3):
+        ref = orc.posterior_step(x[b:b + 1], eps[b:b + 1], int(t[b]), tables, noise[b:b + 1])
+        assert _rel(got[b:b + 1], ref) < 5e-3
+    # same expressions as diffusion.py:14-18; cumprod on the GPU may reorder the products
+    assert torch.equal(diff.betas.cpu(), tables[0])
+    assert torch.allclose(diff.alpha_bars.cpu(), tables[2], rtol=1e-5, atol=0)
+    out = GaussianDiffusion(net, timesteps=3, device="cuda").sample((2, 80, 64), mf[:2].cuda(), tf[:2].cuda())
+    assert out.shape == (2, 80, 64) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("gw", [1.0, 2.1])
+def test_trajectory_vs_reference_sample_from_npz(golden_dir, gw):
+    """Full pipeline (CondProjection -> K/V cache -> 4-step guided trajectory) on the production
+    network against the mel the REFERENCE's sample.sample_from_npz produced (tests/golden),
+    with the reference's CPU RNG draws re-created and injected."""
+    _need_gpu()
+    from lm2a_b200.models import CondProjection, GaussianDiffusion
+    from lm2a_b200.sample import build_models, match_len, sample_clips
+    d = np.load(os.path.join(golden_dir, "sample_from_npz.npz"))
+    key = "gw%d" % int(gw * 10)
+    unet, cond_proj = build_models(device="cuda")
+    unet.load_state_dict(orc.random_state_dict(orc.UNetConfig.production(), 5))
+    cond_proj.load_state_dict(orc.random_cond_proj_state_dict(seed=7))
+    assert isinstance(cond_proj, CondProjection)
+    t_len = d["mel"].shape[1]
+    motion = match_len(d["motion"], t_len, "interp")
+    lyrics = match_len(d["lyrics"], t_len, "interp")
+    np.testing.assert_array_equal(motion, d["motion_rs"])
+    np.testing.assert_array_equal(lyrics, d["lyrics_rs"])
+    steps = 4
+    diff = GaussianDiffusion(unet, timesteps=steps, device="cuda", dataset_mean=-4.5, dataset_std=2.0)
+    torch.manual_seed(42)
+    x_init = torch.randn((1, 80, t_len))
+    noises = [torch.randn_like(x_init).cuda() for _ in range(steps - 1)]
+    mel_norm, motion_f, _ = sample_clips(unet, cond_proj, diff, motion[None], lyrics[None], t_len,
+                                         gw, x_init=x_init.cuda(), noises=noises)
+    assert _rel(motion_f, torch.from_numpy(d[key + "_motion_proj"])) < 1e-2  # bf16 GEMM
+    mel = mel_norm[0] * 2.0 - 4.5
+    ref = d[key + "_mel"]
+    mse, cos = orc.mel_metrics(mel, ref)
+    assert mse / float(ref.var()) < 2e-3, f"rel MSE {mse / float(ref.var()):.3e}"
+    assert cos > 0.999, f"frame cosine {cos:.6f}"
+
+
+def test_sample_from_npz_file_contract(tmp_path, golden_dir):
+    """Drop-in surface: same call, same output file keys / shapes as reference sample.py:250-256."""
+    _need_gpu()
+    from lm2a_b200 import sample
+    d = np.load(os.path.join(golden_dir, "sample_from_npz.npz"))
+    npz = tmp_path / "clip0.npz"
+    np.savez(npz, mel=d["mel"], motion=d["motion"], lyrics=d["lyrics"], sr=22050, hop_length=256)
+    ck = {"unet": orc.random_state_dict(orc.UNetConfig.production(), 5),
+          "cond_proj": orc.random_cond_proj_state_dict(seed=7), "timesteps": 4,
+          "guidance_weight": 2.1, "dataset_mean": -4.5, "dataset_std": 2.0}
+    ckpt = tmp_path / "ck.pt"
+    torch.save(ck, ckpt)
+    out = sample.sample_from_npz(str(npz), str(ckpt), str(tmp_path / "out"), device="cuda")
+    assert out.endswith("clip0_gen.npz")
+    r = np.load(out)
+    t_len = d["mel"].shape[1]
+    assert r["mel"].shape == (80, t_len) and r["mel"].dtype == np.float32
+    assert r["motion"].shape == (t_len, 234) and r["lyrics"].shape == (t_len, 768)
+    assert r["motion_proj"].shape == (1, t_len, 128) and r["lyrics_proj"].shape == (1, t_len, 128)
+    assert int(r["sr"]) == 22050 and int(r["hop_length"]) == 256
+    assert np.isfinite(r["mel"]).all()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        sample.sample_from_npz(str(npz), str(ckpt), str(tmp_path / "out"), device="cpu")
