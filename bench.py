@@ -255,6 +255,9 @@ def run_b200(args):
             "config": {
                 "workload": WORKLOAD, "batch_per_gpu": BATCH, "rows_per_gpu": 2 * BATCH,
                 "trajectory_steps": TRAJ_STEPS, "guidance": GW, "cuda_graph": True,
+                "uncond_shortcut": bool(sampler.plan.uncond_rows),
+                "flops_counted": "executed only (K/V hoisted, out_proj.fuse folded, uncond-row "
+                                 "attention branch skipped)",
                 "l2": "per-step working set (0.27 GB weights + 0.9 GB K/V cache + activations) "
                       "exceeds the 126 MB L2; no flush between steps",
                 "parallelism": f"clip-sharded x{world}, no collective in the loop"},

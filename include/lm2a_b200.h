@@ -130,6 +130,13 @@ int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                          int32_t y_ld, int32_t rows, int32_t tp_in,
                          int32_t t_in, int32_t tp_out, int32_t c);
 
+/* y[slot,:c] = x[slot,:c] + bias[:c] for slots with t < t_valid, zero otherwise
+ * (identity-skip ResBlock of an all-zero-condition row: its attention output is
+ * a constant vector — the classifier-free-guidance uncond shortcut).         */
+int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                       int32_t y_ld, const float* bias, int64_t slots,
+                       int32_t tp, int32_t t_valid, int32_t c);
+
 /* ---- CFG blend + clamps + DDPM posterior update -------------------------- */
 /* x [B,c,T] fp32 updated in place. eps: fp32 [2B,c,T] (uncond rows first)
  * when guided != 0, else [B,c,T]. sched: fp32 [steps,4] rows

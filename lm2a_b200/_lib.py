@@ -52,6 +52,8 @@ SIGNATURES = {
                                   c_int32, c_int32]),
     "lm2a_upsample2x_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, c_int32]),
+    "lm2a_bias_add_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                     c_int64, c_int32, c_int32, c_int32]),
     "lm2a_cfg_posterior": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_int32, c_int64, c_float, c_int32,
                                      c_int32, c_void_p]),

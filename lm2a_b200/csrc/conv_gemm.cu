@@ -413,7 +413,19 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     k_total += ntaps * g.cin;
   }
   int block_n = d->block_n;
-  if (block_n == 0) block_n = (d->n_pad % 256 == 0) ? 256 : 128;
+  if (block_n == 0) {
+    block_n = 128;
+    if (d->n_pad % 256 == 0) {
+      // wave model: cost = waves x tile width; 128-wide tiles pay ~15 % for the higher
+      // shared-memory operand traffic per MMA. Narrow tiles win when 256-wide ones would
+      // leave most SMs idle (e.g. the cond-only half batch at the deepest level).
+      const long long m_tiles = (d->m + kBlockM - 1) / kBlockM;
+      const long long sms = num_sms();
+      const long long w256 = (m_tiles * (d->n_pad / 256) + sms - 1) / sms;
+      const long long w128 = (m_tiles * (d->n_pad / 128) + sms - 1) / sms;
+      block_n = (w128 * 128 * 115 < w256 * 256 * 100) ? 128 : 256;
+    }
+  }
   LM2A_REQUIRE((block_n == 128 || block_n == 256) && d->n_pad % block_n == 0,
                "conv1d: block_n=%d incompatible with n_pad=%d", block_n, d->n_pad);
   LM2A_REQUIRE((reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&

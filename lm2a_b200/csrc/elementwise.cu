@@ -91,6 +91,32 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* 
   *reinterpret_cast<uint4*>(y + ((size_t)r * tp_out + t) * y_ld + cv * 8) = o;
 }
 
+// y[slot, :] = x[slot, :] + bias for valid slots (zero for the pad slots): the
+// identity-skip ResBlock of an all-zero-condition row, whose attention output is a
+// constant vector (reference unet1d_ultimate.py:152-159 with cross_attention.py:38-67).
+__global__ void __launch_bounds__(256)
+bias_add_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+                int y_ld, const float* __restrict__ bias, long long total_vec, int tp,
+                int t_valid, int c) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_vec) return;
+  const int vpr = c >> 3;
+  const int cv = (int)(i % vpr);
+  const long long slot = i / vpr;
+  const int t = (int)(slot % tp);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (t < t_valid) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (size_t)slot * x_ld + cv * 8));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8 + 4));
+    const float2 f0 = unpack_bf16x2(a.x), f1 = unpack_bf16x2(a.y);
+    const float2 f2 = unpack_bf16x2(a.z), f3 = unpack_bf16x2(a.w);
+    o = make_uint4(pack_bf16x2(f0.x + b0.x, f0.y + b0.y), pack_bf16x2(f1.x + b0.z, f1.y + b0.w),
+                   pack_bf16x2(f2.x + b1.x, f2.y + b1.y), pack_bf16x2(f3.x + b1.z, f3.y + b1.w));
+  }
+  *reinterpret_cast<uint4*>(y + (size_t)slot * y_ld + cv * 8) = o;
+}
+
 // ---------------------------------------------------------------------------
 // SinusoidalPosEmb -> Linear -> SiLU (reference models/embedding.py:19-43) and the
 // SiLU that opens every FiLM net (unet1d_ultimate.py:50-53). One CTA per row;
@@ -110,8 +136,10 @@ time_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w,
     emb[i] = i < half ? sinf(a) : cosf(a);
   }
   __syncthreads();
+  // blockIdx.y selects a group of 8 outputs (one per warp): the weight rows of different
+  // outputs stream in parallel instead of serially through one CTA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < dim; j += blockDim.x / 32) {
+  for (int j = blockIdx.y * 8 + warp; j < dim; j += gridDim.y * 8) {
     float acc = 0.f;
     for (int k = lane; k < dim; k += 32) acc = fmaf(emb[k], __ldg(w + (size_t)j * dim + k), acc);
     acc = warp_sum(acc);
@@ -263,12 +291,34 @@ extern "C" int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, v
   return 0;
 }
 
+extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                                  int32_t y_ld, const float* bias, int64_t slots, int32_t tp,
+                                  int32_t t_valid, int32_t c) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && y && bias, "bias_add: null pointer");
+  LM2A_REQUIRE(slots > 0 && tp > 0 && t_valid > 0 && t_valid <= tp && slots % tp == 0 &&
+                   c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+               "bias_add: bad geometry");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                 reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+               "bias_add: tensors must be 16-byte aligned");
+  const long long total_vec = (long long)slots * (c / 8);
+  const int blocks = (int)((total_vec + 255) / 256);
+  bias_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
+      bias, total_vec, tp, t_valid, c);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 extern "C" int lm2a_time_mlp(void* stream, const int64_t* t, const float* w, const float* b,
                              float* silu_temb, int32_t rows, int32_t dim) {
   using namespace lm2a;
   LM2A_REQUIRE(t && w && b && silu_temb, "time_mlp: null pointer");
   LM2A_REQUIRE(rows > 0 && dim >= 4 && dim % 2 == 0 && dim <= 4096, "time_mlp: bad dim %d", dim);
-  time_mlp_kernel<<<rows, 256, dim * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+  time_mlp_kernel<<<dim3(rows, (dim + 7) / 8), 256, dim * sizeof(float),
+                    reinterpret_cast<cudaStream_t>(stream)>>>(
       t, w, b, silu_temb, dim);
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();

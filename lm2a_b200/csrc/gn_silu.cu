@@ -1,17 +1,19 @@
 // GroupNorm (biased variance, per-channel affine) + SiLU over a channels-last
-// bf16 slab. One CTA per (clip-row, group): the (t_valid x C/G) sub-slab is read
-// from HBM once into shared memory, mean and variance are computed two-pass in
+// bf16 slab. One CTA per (clip-row, group): the (t_valid x C/G) sub-slab is streamed
+// from HBM/L2 once into shared memory with cp.async (every 16-byte request of the CTA
+// is in flight at once, no registers held), mean and variance are computed two-pass in
 // fp32 from that copy, and the normalised/activated result is written once.
 // Replaces nn.GroupNorm + nn.SiLU of the reference (models/unet1d_ultimate.py:
 // 91-95,136-137,146-147,362-363; eps = 1e-5, F.group_norm semantics).
-// HBM-bound: algorithmic bytes = 2 B read + 2 B written per element.
+// HBM-bound: algorithmic bytes = 2 B read + 2 B written per element. Small CTAs
+// (256 threads, 33-66 KB of shared memory) keep 3-6 sub-slabs in flight per SM.
 #include "../../include/lm2a_b200.h"
 #include "common.cuh"
 
 namespace lm2a {
 namespace {
 
-constexpr int kGnThreads = 512;
+constexpr int kGnThreads = 256;
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -23,6 +25,10 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int w = 0; w < kGnThreads / 32; ++w) s += red[w];
   return s;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 template <bool CACHED>
@@ -42,11 +48,20 @@ gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __r
   const __nv_bfloat16* xg = x + (size_t)g * cg + cv * 8;
   __nv_bfloat16* yg = y + (size_t)g * cg + cv * 8;
 
+  if (CACHED) {
+    const uint32_t cbase = smem_u32(cache);
+    for (int t = t0, i = threadIdx.x; t < t_valid; t += tstep, i += kGnThreads)
+      cp_async16(cbase + (uint32_t)i * 16u, xg + (row_base + t) * x_ld);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+
   // pass 1: sum
   float s = 0.f;
   for (int t = t0, i = threadIdx.x; t < t_valid; t += tstep, i += kGnThreads) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(xg + (row_base + t) * x_ld));
-    if (CACHED) cache[i] = q;
+    const uint4 q = CACHED ? cache[i]
+                           : __ldg(reinterpret_cast<const uint4*>(xg + (row_base + t) * x_ld));
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -81,7 +96,7 @@ gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __r
     be[e] = __ldg(beta + g * cg + cv * 8 + e) - mean * gm;
   }
 
-  // pass 3: normalise + SiLU, write; slots t >= t_valid stay zero
+  // pass 3: normalise + SiLU, write; slots t >= t_valid are written as zero
   for (int t = t0, i = threadIdx.x; t < tp; t += tstep, i += kGnThreads) {
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (t < t_valid) {
@@ -115,7 +130,8 @@ extern "C" int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void
                                  int32_t groups, float eps, int32_t apply_silu) {
   using namespace lm2a;
   LM2A_REQUIRE(x && y && gamma && beta, "gn_silu: null pointer");
-  LM2A_REQUIRE(rows > 0 && tp > 0 && t_valid > 0 && t_valid <= tp, "gn_silu: bad geometry");
+  LM2A_REQUIRE(rows > 0 && rows <= 65535 && tp > 0 && t_valid > 0 && t_valid <= tp,
+               "gn_silu: bad geometry");
   LM2A_REQUIRE(groups > 0 && c % groups == 0, "gn_silu: c=%d not divisible by groups=%d", c,
                groups);
   const int cg = c / groups;

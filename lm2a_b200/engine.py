@@ -132,9 +132,14 @@ def pack_block(blk, heads, dev, film_col):
         # fuse(cat(Om Wo_m^T + bo_m, Ot Wo_t^T + bo_t)) = [Om Ot] [Wf1 Wo_m, Wf2 Wo_t]^T + b
         wof = torch.cat([wf[:, :e] @ wo[0], wf[:, e:] @ wo[1]], dim=1)
         bof = wf[:, :e] @ bo[0] + wf[:, e:] @ bo[1] + bf
+        # all-zero conditions: V rows of stream s are the constant bv'_s, softmax is uniform, so
+        # the block's attention output is the constant c (used by the uncond shortcut)
+        c_unc = wf[:, :e] @ (wo[0] @ bkv[0][e:] + bo[0]) + wf[:, e:] @ (wo[1] @ bkv[1][e:] + bo[1]) + bf
         if has_skip:
             wof = torch.cat([wof, wskip], dim=1)
             bof = bof + bskip
+            p.wsk, p.bsk_c = _finish(wskip, bskip + c_unc, dev)
+        p.c_uncond = c_unc.to(dev, torch.float32).contiguous()
         p.wof, p.bof = _finish(wof, bof, dev)
     return p
 
@@ -192,8 +197,15 @@ class UNetPlan:
     frames held in `nslots` K/V cache slots. `copies` rows share each input clip
     (CFG: copies=2, rows = 2B, row k*B+b reads clip b)."""
 
-    def __init__(self, pm, rows, t, lk, nslots, copies, use_cond, dev):
+    def __init__(self, pm, rows, t, lk, nslots, copies, use_cond, dev, uniform_t=False,
+                 uncond_rows=0):
         self.pm, self.rows, self.t, self.lk, self.nslots = pm, rows, t, lk, nslots
+        # uniform_t: every clip-row is at the same timestep (sampling) -> one FiLM table row
+        self.uniform_t = uniform_t
+        self.t_rows = 1 if uniform_t else rows
+        # leading rows with all-zero conditions whose attention blocks take the constant shortcut
+        self.uncond_rows = uncond_rows if use_cond else 0
+        assert 0 <= self.uncond_rows < rows
         self.copies, self.use_cond, self.dev = copies, use_cond, dev
         assert rows % copies == 0
         self.batch = rows // copies
@@ -206,8 +218,8 @@ class UNetPlan:
         self.t_in = torch.zeros(rows, dtype=torch.int64, device=dev)
         self.eps = torch.zeros(rows, pm.in_dim, t, dtype=torch.float32, device=dev)
         self.kv_slot = torch.zeros(rows, dtype=torch.int32, device=dev)
-        self.silu_temb = torch.zeros(rows, pm.time_dim, dtype=torch.float32, device=dev)
-        self.film = torch.zeros(rows, pm.film_cols, dtype=torch.float32, device=dev)
+        self.silu_temb = torch.zeros(self.t_rows, pm.time_dim, dtype=torch.float32, device=dev)
+        self.film = torch.zeros(self.t_rows, pm.film_cols, dtype=torch.float32, device=dev)
 
         # scratch slabs shared by all blocks (sized for the largest level)
         cmax = 0
@@ -246,32 +258,59 @@ class UNetPlan:
         (valid slots x real output channels x K, no padding counted)."""
         ntaps = {TAPS_K1: 1, TAPS_K3: 3, TAPS_K4S2: 4}
         k_total = k.pop("k_real", None) or sum(ntaps[s.taps] * s.cin for s in segs)
-        meta = {"kind": "conv_gemm", "flops": 2 * self.rows * t_valid * n_valid * k_total,
+        meta = {"kind": "conv_gemm", "flops": 2 * (m // tp) * t_valid * n_valid * k_total,
                 "m": m, "n": n_valid, "k": k_total}
         self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
                   meta=meta)
 
     def _resblock(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv):
-        """xin/out: (tensor, ld, channel offset) views of slabs at level `lvl`."""
-        g, rows = self.geo, self.rows
-        m, tp, tv = g.M[lvl], g.Tp[lvl], g.T[lvl]
+        """xin/out: (tensor, ld, channel offset) views of slabs at level `lvl`. With the uncond
+        shortcut, attention blocks run the full pipeline on the cond rows only; the leading
+        `uncond_rows` rows get `skip(x) + const` (their attention output is Q-independent)."""
+        u = self.uncond_rows if (p.attn and self.use_cond) else 0
+        if u > 0:
+            self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, u)
+        self._resblock_rows(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv, u,
+                            self.rows - u)
+
+    def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, u):
+        """Rows whose conditions are all-zero (sample.py:155-157): every key of a stream is the
+        same vector, softmax is exactly uniform, the attention output is the constant
+        fuse(out_proj(v_row)) and replaces h (unet1d_ultimate.py:152-159) -> out = skip(x) + c."""
+        g = self.geo
+        tp, tv = g.Tp[lvl], g.T[lvl]
+        m = u * tp
+        if p.has_skip:
+            self._conv([Seg(xin, xin_ld, p.cin, TAPS_K1, m, xin_off)], p.wsk, p.bsk_c, p.cout, m,
+                       tp, tv, out, out_ld, out_chan_off=out_off)
+        else:
+            self._add(ops.bias_add, xin, xin_ld, xin_off, out, out_ld, out_off, p.c_uncond, m, tp,
+                      tv, p.cout, meta={"kind": "bias_add", "flops": 0})
+
+    def _resblock_rows(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv, r0, nr):
+        g = self.geo
+        tp, tv = g.Tp[lvl], g.T[lvl]
+        m = nr * tp
+        xo = r0 * tp * xin_ld + xin_off      # element offsets of the row range inside the slabs
+        oo = r0 * tp * out_ld + out_off
         cin, cout = p.cin, p.cout
         norm = self._view(self._norm, m, cin)
         h1 = self._view(self._h1, m, cout)
         norm2 = self._view(self._norm2, m, cout)
         gm, bt, groups, eps = p.gn1
-        self._add(ops.gn_silu, xin, xin_ld, norm, cin, gm, bt, rows, tp, tv, cin, groups, eps,
-                  True, xin_off, 0)
+        self._add(ops.gn_silu, xin, xin_ld, norm, cin, gm, bt, nr, tp, tv, cin, groups, eps,
+                  True, xo, 0)
         self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
-                   film=self.film, film_col=p.film_col, film_shift_off=cout)
+                   film=self.film, film_col=p.film_col, film_shift_off=cout,
+                   film_bcast=self.uniform_t, film_row=r0)
         gm, bt, groups, eps = p.gn2
-        self._add(ops.gn_silu, h1, cout, norm2, cout, gm, bt, rows, tp, tv, cout, groups, eps,
+        self._add(ops.gn_silu, h1, cout, norm2, cout, gm, bt, nr, tp, tv, cout, groups, eps,
                   True, 0, 0)
-        skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xin_off)] if p.has_skip else []
-        res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xin_off)
+        skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xo)] if p.has_skip else []
+        res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xo)
         if not (p.attn and self.use_cond):
             self._conv([Seg(norm2, cout, cout, TAPS_K3, m)] + skip_seg, p.w2s, p.b2s, cout, m,
-                       tp, tv, out, out_ld, out_chan_off=out_off, **res)
+                       tp, tv, out, out_ld, out_chan_off=oo, **res)
             return
         e = p.e
         h2 = self._view(self._h2, m, cout)
@@ -281,10 +320,11 @@ class UNetPlan:
         self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.w2, p.b2, cout, m, tp, tv, h2, cout)
         self._conv([Seg(h2, cout, cout, TAPS_K1, m)], p.wq, p.bq, 2 * e, m, tp, tv, q, 2 * e)
         self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e),
-                  ops._ptr(kv_t), ops._ptr(kv_t, e), 2 * e, self.kv_slot, rows, tp, tv, self.lk,
-                  e, p.heads, meta={"kind": "cross_attn", "flops": 2 * 4 * rows * tv * self.lk * e})
+                  ops._ptr(kv_t), ops._ptr(kv_t, e), 2 * e, ops._ptr(self.kv_slot, r0), nr, tp, tv,
+                  self.lk, e, p.heads,
+                  meta={"kind": "cross_attn", "flops": 2 * 4 * nr * tv * self.lk * e})
         self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
-                   out, out_ld, out_chan_off=out_off, **res)
+                   out, out_ld, out_chan_off=oo, **res)
 
     # -- plan construction ----------------------------------------------------------------
     def _build(self):
@@ -303,10 +343,10 @@ class UNetPlan:
                         self.lk, self.lk, dst, 2 * p.e),)))
 
         # timestep embedding + all FiLM tables, once per step
-        self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, rows,
+        self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,
                   pm.time_dim)
-        self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, rows, pm.time_dim,
-                  pm.film_cols)
+        self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, self.t_rows,
+                  pm.time_dim, pm.film_cols)
         # x -> bf16 slab (CFG row duplication happens here), in_proj
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
                   self.t, g.Tp[0], pm.in_pad)
@@ -394,21 +434,30 @@ class UNetPlan:
         """Algorithmic FLOPs of one forward over all rows (K/V hoisted, out_proj.fuse folded)."""
         return sum(meta["flops"] for _, _, meta in self.ops)
 
-    def profile(self, iters=5):
-        """Per-launch device time (CUDA events on the current stream), for bench.py's roofline
-        line and profiles/: returns [(kind, meta, seconds)] in launch order."""
-        stream = torch.cuda.current_stream(self.dev)
+    def profile(self, iters=10):
+        """Per-launch device time for bench.py's roofline line and profiles/. Each launch is
+        captured `iters` times back to back in a CUDA Graph and the replay is timed with CUDA
+        events on the launching stream, so short kernels are not measured at the Python launch
+        rate. Repeats of one launch re-read the same operands (L2-warm; the slabs of the big
+        layers exceed what stays resident next to the weights). Returns [(kind, meta, seconds)]
+        in launch order."""
         out = []
         for fn, args, meta in self.ops:
-            fn(*args)  # warm
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-            evs[0].record(stream)
-            for i in range(iters):
-                fn(*args)
-                evs[i + 1].record(stream)
+            fn(*args)  # warm (first-launch attribute setup must not happen under capture)
             torch.cuda.synchronize(self.dev)
-            ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(iters))
-            out.append((meta["kind"], meta, ts[len(ts) // 2] * 1e-3))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters):
+                    fn(*args)
+            g.replay()
+            stream = torch.cuda.current_stream(self.dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize(self.dev)
+            out.append((meta["kind"], meta, e0.elapsed_time(e1) * 1e-3 / iters))
+            del g
         return out
 
 
@@ -421,10 +470,11 @@ class UNetEngine:
         self.plans = {}
         self._cond_key = None
 
-    def plan(self, rows, t, lk, nslots, copies=1, use_cond=True):
-        key = (rows, t, lk, nslots, copies, use_cond)
+    def plan(self, rows, t, lk, nslots, copies=1, use_cond=True, uniform_t=False, uncond_rows=0):
+        key = (rows, t, lk, nslots, copies, use_cond, uniform_t, uncond_rows)
         if key not in self.plans:
-            self.plans[key] = UNetPlan(self.pm, rows, t, lk, nslots, copies, use_cond, self.dev)
+            self.plans[key] = UNetPlan(self.pm, rows, t, lk, nslots, copies, use_cond, self.dev,
+                                       uniform_t, uncond_rows)
         return self.plans[key]
 
     def forward(self, x, t, motion_f=None, text_f=None):

@@ -32,6 +32,8 @@ class GaussianDiffusion:
                                   self.betas / (1.0 - self.alpha_bars).sqrt(),
                                   self.betas.sqrt(), torch.zeros_like(betas)], dim=1).contiguous()
         self._samplers = {}
+        # classifier-free guidance: skip the Q-independent attention branch of the uncond rows
+        self.uncond_shortcut = True
 
     # ---- forward process (training side; trivial torch, kept for API parity) ----------
     def q_sample(self, x0, t, noise=None):
@@ -101,10 +103,12 @@ class GaussianDiffusion:
         return x_prev, x0_pred
 
     # ---- batched classifier-free-guided sampling (sample.py:131-225, any B) -----------
-    def sampler(self, batch, t_len, lk, guided=True):
-        key = (batch, t_len, lk, bool(guided))
+    def sampler(self, batch, t_len, lk, guided=True, uncond_shortcut=None):
+        if uncond_shortcut is None:
+            uncond_shortcut = self.uncond_shortcut
+        key = (batch, t_len, lk, bool(guided), bool(uncond_shortcut))
         if key not in self._samplers:
-            self._samplers[key] = CfgSampler(self, batch, t_len, lk, guided)
+            self._samplers[key] = CfgSampler(self, batch, t_len, lk, guided, uncond_shortcut)
         return self._samplers[key]
 
     @torch.no_grad()
@@ -125,14 +129,17 @@ class GaussianDiffusion:
 class CfgSampler:
     """State + CUDA Graph of the per-step launch sequence for a fixed (B, T, Lk)."""
 
-    def __init__(self, diffusion, batch, t_len, lk, guided):
+    def __init__(self, diffusion, batch, t_len, lk, guided, uncond_shortcut=True):
         self.d = diffusion
         self.batch, self.t_len, self.lk, self.guided = batch, t_len, lk, guided
         eng = diffusion.model.engine()
         self.dev = eng.dev
         rows = 2 * batch if guided else batch
         nslots = batch + 1 if guided else batch
-        self.plan = eng.plan(rows, t_len, lk, nslots, 2 if guided else 1, True)
+        # uncond rows [0, B) attend to all-zero conditions: their attention blocks reduce to
+        # skip(x) + const (exact in real arithmetic; executed FLOPs drop accordingly)
+        self.plan = eng.plan(rows, t_len, lk, nslots, 2 if guided else 1, True, uniform_t=True,
+                             uncond_rows=batch if (guided and uncond_shortcut) else 0)
         self.noise = torch.zeros(batch, eng.pm.in_dim, t_len, dtype=torch.float32, device=self.dev)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.gw = 1.0

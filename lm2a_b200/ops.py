@@ -46,7 +46,8 @@ class Seg:
 
 
 def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan_off=0,
-                   film=None, film_col=0, film_shift_off=0, residual=None, res_ld=0,
+                   film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
+                   residual=None, res_ld=0,
                    res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object."""
@@ -65,8 +66,8 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
     d.t_valid = t_valid
     d.bias = bias.data_ptr()
     if film is not None:
-        d.film = film.data_ptr() + film_col * 4
-        d.film_ld = film.shape[1]
+        d.film = film.data_ptr() + (film_col + (0 if film_bcast else film_row * film.shape[1])) * 4
+        d.film_ld = 0 if film_bcast else film.shape[1]  # 0: one table row for all clip-rows
         d.film_shift_off = film_shift_off
     if residual is not None:
         d.residual = residual.data_ptr() + res_chan_off * 2
@@ -93,7 +94,8 @@ def gn_silu(x, x_ld, y, y_ld, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-
 def cross_attn(q, q_ld, o, o_ld, k_m, v_m, k_t, v_t, kv_ld, kv_slot, rows, tp, t_valid, lk, e,
                heads):
     _lib.check(_lib.load().lm2a_cross_attn_bf16(
-        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, v_m, k_t, v_t, kv_ld, _ptr(kv_slot), rows,
+        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, v_m, k_t, v_t, kv_ld,
+        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), rows,
         tp, t_valid, lk, e, heads), "lm2a_cross_attn_bf16")
 
 
@@ -128,3 +130,9 @@ def cfg_posterior(x, eps, noise, sched, t_dev, ticket, batch, elems_per_clip, gu
         _stream(), _ptr(x), _ptr(eps), _ptr(noise), _ptr(sched), _ptr(t_dev), t_dev.numel(),
         _ptr(ticket), batch, elems_per_clip, float(guidance), 1 if guided else 0,
         1 if advance else 0, _ptr(eps_out)), "lm2a_cfg_posterior")
+
+
+def bias_add(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c):
+    _lib.check(_lib.load().lm2a_bias_add_bf16(_stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld,
+                                              _ptr(bias), slots, tp, t_valid, c),
+               "lm2a_bias_add_bf16")

@@ -176,7 +176,8 @@ def test_conv_rejects_bad_arguments(ops):
 
 
 @pytest.mark.parametrize("r,t,tp,c,groups", [(2, 37, 40, 64, 8), (3, 129, 130, 2048, 8),
-                                             (4, 516, 520, 256, 8), (2, 2064, 2080, 512, 8)])
+                                             (4, 516, 520, 256, 8), (2, 516, 520, 512, 8),
+                                             (1, 2064, 2080, 256, 8), (2, 2064, 2080, 512, 8)])
 def test_gn_silu(ops, r, t, tp, c, groups):
     x = rnd(r, c, t, seed=20) * 1.7 + 0.3
     gamma = 1 + 0.1 * rnd(c, seed=21)

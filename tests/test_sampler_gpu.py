@@ -172,3 +172,39 @@ def test_sample_from_npz_file_contract(tmp_path, golden_dir):
     assert np.isfinite(r["mel"]).all()
     with pytest.raises(RuntimeError, match="no CPU"):
         sample.sample_from_npz(str(npz), str(ckpt), str(tmp_path / "out"), device="cpu")
+
+
+def test_uncond_shortcut_equals_full_path():
+    """CFG uncond rows have all-zero conditions -> uniform softmax -> constant attention output.
+    The shortcut plan (skip(x) + const on those rows) must match the full computation."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    cfg, sd, net = _b64()
+    steps, bsz, t_len = 20, 3, 132
+    g = torch.Generator().manual_seed(31)
+    x0 = torch.randn(bsz, 80, t_len, generator=g).cuda()
+    mf = torch.randn(bsz, t_len, 128, generator=g).cuda()
+    tf = torch.randn(bsz, t_len, 128, generator=g).cuda()
+    noises = torch.randn(3, bsz, 80, t_len, generator=g).cuda()
+    diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    outs = []
+    for shortcut in (True, False):
+        s = diff.sampler(bsz, t_len, t_len, guided=True, uncond_shortcut=shortcut)
+        assert s.plan.uncond_rows == (bsz if shortcut else 0)
+        s.gw = 2.1
+        s.set_conditions(mf, tf)
+        s.plan.x_in.copy_(x0)
+        s.plan.t_in.fill_(steps - 1)
+        for i in range(3):
+            s.noise.copy_(noises[i])
+            s._step(False)
+        outs.append((s.plan.eps.clone(), s.plan.x_in.clone()))
+    assert outs[0][0].shape[0] == 2 * bsz
+    # two different bf16 evaluation orders of the same function: each is within ~1e-2 of fp32
+    assert _rel(outs[0][0][:bsz], outs[1][0][:bsz]) < 1.5e-2   # uncond eps rows
+    assert _rel(outs[0][0][bsz:], outs[1][0][bsz:]) < 1.5e-2   # cond rows (after 2 shared steps)
+    assert _rel(outs[0][1], outs[1][1]) < 2e-3
+    # executed work drops: 9 of 15 blocks lose their h-branch on the uncond rows
+    full = diff.sampler(bsz, t_len, t_len, True, False).plan.flops()
+    short = diff.sampler(bsz, t_len, t_len, True, True).plan.flops()
+    assert short < 0.72 * full

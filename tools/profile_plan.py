@@ -25,7 +25,7 @@ g = torch.Generator().manual_seed(0)
 s.set_conditions(torch.randn(B, T, 128, generator=g).to(dev), torch.randn(B, T, 128, generator=g).to(dev))
 s.plan.x_in.normal_()
 s.plan.t_in.fill_(500)
-prof = s.plan.profile(iters=7)
+prof = s.plan.profile(iters=10)
 print("idx,kind,m,n,k,gflop,us,tflops")
 tot = {}
 for i, (kind, meta, sec) in enumerate(prof):
