@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 1
+#define LM2A_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -94,16 +94,24 @@ int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                       int32_t rows, int32_t tp, int32_t t_valid, int32_t c,
                       int32_t groups, float eps, int32_t apply_silu);
 
-/* ---- cross-attention core ------------------------------------------------ */
+/* ---- cross-attention core (tcgen05 + TMEM) -------------------------------- */
 /* q,o: bf16 slabs [R*tp, ld]; stream s, head h live at channel s*e + h*dh.
- * q is pre-scaled by log2(e)/sqrt(dh). k_s/v_s: bf16 [slots, lk, kv_ld]
- * (first e channels used). kv_slot[r] selects the cache slot of clip-row r. */
+ * q is pre-scaled by log2(e)/sqrt(dh). k_s: bf16 [slots*lk, k_ld] (first e
+ * channels used); vt_s: bf16 V^T [slots*e, vt_ld] (first lk keys of each row
+ * used, vt_ld >= lk, multiple of 8). kv_slot[r] selects the cache slot of
+ * clip-row r. dh = e/heads must be 32, 64 or 128.                           */
 int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
                          int32_t o_ld, const void* k_motion,
-                         const void* v_motion, const void* k_text,
-                         const void* v_text, int32_t kv_ld,
-                         const int32_t* kv_slot, int32_t rows, int32_t tp,
-                         int32_t t_valid, int32_t lk, int32_t e, int32_t heads);
+                         const void* vt_motion, const void* k_text,
+                         const void* vt_text, int32_t k_ld, int32_t vt_ld,
+                         const int32_t* kv_slot, int32_t slots, int32_t rows,
+                         int32_t tp, int32_t t_valid, int32_t lk, int32_t e,
+                         int32_t heads);
+/* per-clip V cache transpose: src [slots*lk, src_ld] (c channels) ->
+ * dst [slots*c, dst_ld] (lk keys); c multiple of 32.                        */
+int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src_ld,
+                           void* dst, int32_t dst_ld, int32_t slots,
+                           int32_t lk, int32_t c);
 
 /* ---- timestep embedding + FiLM tables ----------------------------------- */
 /* silu_temb[r,:] = SiLU(SiLU(W sinus(t[r]) + b))  (the SiLU that opens every

@@ -25,6 +25,7 @@ class ConvDesc(ctypes.Structure):
                 ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32)]
 
 
+ABI_VERSION = 2
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -40,8 +41,11 @@ SIGNATURES = {
                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_float, c_int32]),
     "lm2a_cross_attn_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
-                                       c_int32, c_int32, c_int32, c_int32, c_int32]),
+                                       c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_int32]),
+    "lm2a_transpose_kv_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                         c_int32, c_int32]),
     "lm2a_time_mlp": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                 c_int32]),
     "lm2a_film": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
@@ -76,7 +80,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.lm2a_abi_version() != 1:
+    if lib.lm2a_abi_version() != ABI_VERSION:
         raise RuntimeError("liblm2a_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -1,0 +1,424 @@
+// Cross-attention core softmax(q k^T) v on the 5th-gen tensor cores (tcgen05 + TMEM),
+// both condition streams (motion, lyrics) of CrossAttentionFusion in one launch
+// (reference models/cross_attention.py:50-61, i.e. the bmm / softmax / bmm inside
+// nn.MultiheadAttention). K and V^T are per-clip caches built once per clip; q arrives
+// pre-scaled by log2(e)/sqrt(d_h) so the softmax is a bare exp2. The [Tq, Lk] probability
+// matrix never leaves the SM (the reference materialises it, head-averages it and throws
+// it away).
+//
+// One CTA = 128 queries of one (clip-row, stream, head); keys are walked in tiles of 64.
+//   warp 4     TMA producer: Q tile once, then a 3-stage ring of (K tile, V^T tile)
+//   warp 5     tcgen05.mma issuer (one thread): S_j = Q K_j^T into a double-buffered TMEM
+//              tile, O += P_j V_j with P_j read from shared memory; S_{j+1} is issued
+//              before P_j V_j so the tensor pipe works while the softmax warps run
+//   warps 0-3  softmax: one query row per thread (TMEM lane), tcgen05.ld of S, running
+//              max with lazy rescaling (O in TMEM is only corrected when the row max grows
+//              by more than 2^8), exp2, row sum, P -> bf16 -> 128B-swizzled shared tile;
+//              finally O / l -> bf16 slab
+// TMEM: S[0] cols 0-63, S[1] cols 64-127, O cols 128-(128+dh); 256 columns per CTA, two
+// CTAs per SM for dh <= 64.
+#include "../../include/lm2a_b200.h"
+#include "common.cuh"
+
+namespace lm2a {
+namespace {
+
+constexpr int kBQ = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 3;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 256;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int DH>
+struct AttnSmem {
+  static constexpr int kPanels = DH > 64 ? DH / 64 : 1;  // 64-channel panels of Q / K tiles
+  static constexpr int kPanelW = DH > 64 ? 64 : DH;
+  static constexpr int kQPanelBytes = kBQ * kPanelW * 2;
+  static constexpr int kKPanelBytes = kBK * kPanelW * 2;
+  static constexpr int kQBytes = kBQ * DH * 2;
+  static constexpr int kKBytes = kBK * DH * 2;
+  static constexpr int kVBytes = DH * kBK * 2;
+  static constexpr int kPBytes = kBQ * kBK * 2;
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kPOff = kQBytes;
+  static constexpr int kKVOff = kPOff + 2 * kPBytes;
+  static constexpr int kBarOff = kKVOff + kStages * kStageBytes;
+  static constexpr int kNeeded = kBarOff + 256 + 1024;
+  // dh = 32 would fit three CTAs per SM by shared memory but only two by TMEM columns:
+  // ask for enough that the third is never scheduled (it would spin in tcgen05.alloc)
+  static constexpr int kBytes = kNeeded < 80 * 1024 && DH <= 64 ? 80 * 1024 : kNeeded;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, bool sw64) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sw64 ? 512 : 1024) >> 4) << 32;  // 8 rows x swizzle span
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(sw64 ? 4 : 2) << 61;              // SWIZZLE_64B / SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kThreads, (DH > 64 ? 1 : 2))
+cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                     const __grid_constant__ CUtensorMap tmKm,
+                     const __grid_constant__ CUtensorMap tmKt,
+                     const __grid_constant__ CUtensorMap tmVm,
+                     const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ o,
+                     int o_ld, const int* __restrict__ kv_slot, int tp, int t_valid, int lk,
+                     int e, int heads) {
+  using L = AttnSmem<DH>;
+  constexpr bool kSw64 = (DH == 32);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_base = smem_base;
+  auto p_tile = [&](int b) { return smem_base + L::kPOff + b * L::kPBytes; };
+  auto k_tile = [&](int s) { return smem_base + L::kKVOff + s * L::kStageBytes; };
+  auto v_tile = [&](int s) { return smem_base + L::kKVOff + s * L::kStageBytes + L::kKBytes; };
+  const uint32_t bar_base = smem_base + L::kBarOff;
+  // barrier slots (8 B each)
+  const uint32_t q_full = bar_base;
+  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + kStages + s); };
+  auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * kStages + b); };
+  auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * kStages + b); };
+  auto pv_done = [&](int b) { return bar_base + 8u * (5 + 2 * kStages + b); };
+  const uint32_t o_full = bar_base + 8u * (7 + 2 * kStages);
+  const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * kStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.z;
+  const int stream = blockIdx.y / heads;
+  const int h = blockIdx.y % heads;
+  const int q0 = blockIdx.x * kBQ;
+  const int ntiles = (lk + kBK - 1) / kBK;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(stream ? &tmKt : &tmKm);
+    tma_prefetch_desc(stream ? &tmVt : &tmVm);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(s_full(b), 1);
+      mbar_init(p_full(b), 128);
+      mbar_init(pv_done(b), 1);
+    }
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int slot = kv_slot[r];
+      const CUtensorMap* km = stream ? &tmKt : &tmKm;
+      const CUtensorMap* vm = stream ? &tmVt : &tmVm;
+      mbar_expect_tx(q_full, L::kQBytes);
+#pragma unroll
+      for (int p = 0; p < L::kPanels; ++p)
+        tma_load_2d(q_base + p * L::kQPanelBytes, &tmQ, stream * e + h * DH + p * 64,
+                    r * tp + q0, q_full);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kStages;
+        const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+        mbar_wait(kv_empty(st), ph ^ 1u);
+        mbar_expect_tx(kv_full(st), L::kStageBytes);
+#pragma unroll
+        for (int p = 0; p < L::kPanels; ++p)
+          tma_load_2d(k_tile(st) + p * L::kKPanelBytes, km, h * DH + p * 64,
+                      slot * lk + j * kBK, kv_full(st));
+        tma_load_2d(v_tile(st), vm, j * kBK, slot * e + h * DH, kv_full(st));
+      }
+    }
+  } else if (warp == 5) {
+    // --------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, DH);
+      auto issue_pv = [&](int jj) {
+        const int b = jj & 1, st = jj % kStages;
+        mbar_wait(p_full(b), (uint32_t)(jj >> 1) & 1u);
+        tc_fence_after_sync();
+        const int keys = min(kBK, lk - jj * kBK);
+        const int ksteps = (keys + 15) >> 4;
+        const uint64_t adesc = umma_desc_kmajor(p_tile(b), false);
+        const uint64_t bdesc = umma_desc_kmajor(v_tile(st), false);
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ss(tmem_o, adesc + 2u * k, bdesc + 2u * k, idesc_pv,
+                       (jj | k) != 0 ? 1u : 0u);
+        umma_commit(kv_empty(st));
+        umma_commit(pv_done(b));
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kStages, b = j & 1;
+        mbar_wait(kv_full(st), (uint32_t)(j / kStages) & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) {
+          const int panel = (k * 16) / L::kPanelW, kk = k % (L::kPanelW / 16);
+          const uint64_t adesc =
+              umma_desc_kmajor(q_base + panel * L::kQPanelBytes + kk * 32, kSw64);
+          const uint64_t bdesc =
+              umma_desc_kmajor(k_tile(st) + panel * L::kKPanelBytes + kk * 32, kSw64);
+          umma_bf16_ss(tmem_base + b * kBK, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(b));
+        if (j >= 1) issue_pv(j - 1);
+      }
+      issue_pv(ntiles - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax
+    const int row = warp * 32 + lane;  // TMEM lane == query row of the tile
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float m_used = -INFINITY, l_run = 0.f;
+    const uint32_t p_row = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int b = j & 1;
+      mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after_sync();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
+      tmem_ld_32x32(tmem_base + lane_off + b * kBK + 32, v1);
+      tmem_ld_wait();
+      float s[64];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        s[c] = __uint_as_float(v0[c]);
+        s[32 + c] = __uint_as_float(v1[c]);
+      }
+      const int keys = lk - j * kBK;
+      if (keys < kBK) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= keys) s[c] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
+
+      // lazy rescale: keep the stale max while the new one is within 2^8 of it
+      const bool grow = mx > m_used + kRescaleThreshold;
+      float corr = 1.0f;
+      if (grow) {
+        corr = ex2_approx(m_used - mx);  // first tile: exp2(-inf) = 0
+        m_used = mx;
+        l_run *= corr;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_o + lane_off + c0, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
+          tmem_st_32x32(tmem_o + lane_off + c0, ov);
+        }
+        tmem_st_wait();
+      }
+
+      float sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 2) {
+        const float p0 = ex2_approx(s[c] - m_used);
+        const float p1 = ex2_approx(s[c + 1] - m_used);
+        sum += p0 + p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run += sum;
+
+      // P tile slot b is free once P_{j-2} V_{j-2} has completed
+      if (j >= 2) mbar_wait(pv_done(b), (uint32_t)((j >> 1) - 1) & 1u);
+      const uint32_t pb = p_tile(b) + p_row;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = pb + (((uint32_t)c ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
+                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(p_full(b));
+    }
+
+    // ---- finalise: O / l -> bf16 slab
+    mbar_wait(o_full, 0);
+    tc_fence_after_sync();
+    const float inv = 1.0f / l_run;
+    const int t = q0 + row;
+    __nv_bfloat16* op = o + ((size_t)r * tp + t) * o_ld + stream * e + h * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_off + c0, ov);
+      tmem_ld_wait();
+      if (t < t_valid) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(ov[c + 0]) * inv, __uint_as_float(ov[c + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(ov[c + 2]) * inv, __uint_as_float(ov[c + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(ov[c + 4]) * inv, __uint_as_float(ov[c + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(ov[c + 6]) * inv, __uint_as_float(ov[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c0 + c) = q;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+int encode_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+               uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer, bool sw64) {
+  EncodeTiledFn fn = get_encode_fn();
+  LM2A_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult res = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LM2A_REQUIRE(res == CUDA_SUCCESS,
+               "cross_attn: cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu "
+               "pitch=%llu box=%ux%u",
+               (int)res, base, (unsigned long long)inner, (unsigned long long)outer,
+               (unsigned long long)pitch_elems, box_inner, box_outer);
+  return 0;
+}
+
+template <int DH>
+int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, const void* k_m,
+                const void* vt_m, const void* k_t, const void* vt_t, int k_ld, int vt_ld,
+                const int32_t* kv_slot, int slots, int rows, int tp, int t_valid, int lk, int e,
+                int heads) {
+  using L = AttnSmem<DH>;
+  constexpr bool sw64 = (DH == 32);
+  auto kern = cross_attn_tc_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    LM2A_CUDA_OK(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+    configured = true;
+  }
+  CUtensorMap tq, tkm, tkt, tvm, tvt;
+  if (encode_map(&tq, q, (uint64_t)2 * e, (uint64_t)rows * tp, (uint64_t)q_ld, L::kPanelW, kBQ,
+                 sw64))
+    return 1;
+  if (encode_map(&tkm, k_m, (uint64_t)e, (uint64_t)slots * lk, (uint64_t)k_ld, L::kPanelW, kBK,
+                 sw64) ||
+      encode_map(&tkt, k_t, (uint64_t)e, (uint64_t)slots * lk, (uint64_t)k_ld, L::kPanelW, kBK,
+                 sw64))
+    return 1;
+  if (encode_map(&tvm, vt_m, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK, DH,
+                 false) ||
+      encode_map(&tvt, vt_t, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK, DH,
+                 false))
+    return 1;
+  dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
+  kern<<<grid, kThreads, L::kBytes, st>>>(tq, tkm, tkt, tvm, tvt,
+                                          reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
+                                          t_valid, lk, e, heads);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+}  // namespace lm2a
+
+extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                                    int32_t o_ld, const void* k_motion, const void* vt_motion,
+                                    const void* k_text, const void* vt_text, int32_t k_ld,
+                                    int32_t vt_ld, const int32_t* kv_slot, int32_t slots,
+                                    int32_t rows, int32_t tp, int32_t t_valid, int32_t lk,
+                                    int32_t e, int32_t heads) {
+  using namespace lm2a;
+  LM2A_REQUIRE(q && o && k_motion && vt_motion && k_text && vt_text && kv_slot,
+               "cross_attn: null pointer");
+  LM2A_REQUIRE(rows > 0 && rows <= 65535 && slots > 0 && tp > 0 && t_valid > 0 &&
+                   t_valid <= tp && lk > 0,
+               "cross_attn: bad geometry");
+  LM2A_REQUIRE(heads > 0 && e % heads == 0, "cross_attn: e=%d not divisible by heads=%d", e,
+               heads);
+  LM2A_REQUIRE(q_ld % 8 == 0 && o_ld % 8 == 0 && k_ld % 8 == 0 && vt_ld % 8 == 0 &&
+                   q_ld >= 2 * e && o_ld >= 2 * e && k_ld >= e && vt_ld >= lk,
+               "cross_attn: bad pitches (q_ld=%d o_ld=%d k_ld=%d vt_ld=%d e=%d lk=%d)", q_ld,
+               o_ld, k_ld, vt_ld, e, lk);
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(o) |
+                 reinterpret_cast<uintptr_t>(k_motion) | reinterpret_cast<uintptr_t>(vt_motion) |
+                 reinterpret_cast<uintptr_t>(k_text) | reinterpret_cast<uintptr_t>(vt_text)) &
+                15) == 0,
+               "cross_attn: tensors must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int dh = e / heads;
+  switch (dh) {
+    case 32:
+      return launch_attn<32>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
+                             vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
+    case 64:
+      return launch_attn<64>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
+                             vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
+    case 128:
+      return launch_attn<128>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
+                              vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
+    default:
+      LM2A_REQUIRE(false, "cross_attn: head dim %d unsupported (32, 64 or 128)", dh);
+  }
+  return 0;
+}

@@ -13,6 +13,15 @@ namespace lm2a {
 // ---------------------------------------------------------------- host side
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int num_sms();
+
+// cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn();
 
 #define LM2A_REQUIRE(cond, ...)        \
   do {                                 \

@@ -282,26 +282,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
-            cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess) {
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-  }
-  return fn;
-}
-
 // 2-D bf16 map: inner = channels (box 64 -> 128 B, SWIZZLE_128B), outer = slots / rows.
 int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
               uint64_t pitch_elems, uint32_t box_outer) {
@@ -320,17 +300,6 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
                (int)res, base, (unsigned long long)inner, (unsigned long long)outer,
                (unsigned long long)pitch_elems);
   return 0;
-}
-
-int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
 }
 
 template <int BLOCK_N, int STAGES>

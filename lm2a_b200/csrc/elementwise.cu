@@ -117,6 +117,28 @@ bias_add_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
   *reinterpret_cast<uint4*>(y + (size_t)slot * y_ld + cv * 8) = o;
 }
 
+// V cache transpose, once per clip: src bf16 [slots * lk, src_ld] (c channels used) ->
+// dst bf16 [slots * c, dst_ld] (lk keys used). The tcgen05 attention kernel wants V^T with
+// keys contiguous (K-major B operand of the P V product).
+__global__ void __launch_bounds__(256)
+transpose_kv_kernel(const __nv_bfloat16* __restrict__ src, int src_ld,
+                    __nv_bfloat16* __restrict__ dst, int dst_ld, int lk, int c) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int slot = blockIdx.z;
+  const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int key = k0 + i;
+    tile[i][tx] = (key < lk) ? src[((size_t)slot * lk + key) * src_ld + c0 + tx]
+                             : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int key = k0 + tx;
+    if (key < lk) dst[((size_t)slot * c + c0 + i) * dst_ld + key] = tile[tx][i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // SinusoidalPosEmb -> Linear -> SiLU (reference models/embedding.py:19-43) and the
 // SiLU that opens every FiLM net (unet1d_ultimate.py:50-53). One CTA per row;
@@ -268,6 +290,23 @@ extern "C" int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t
   const int blocks = (int)((total + 255) / 256);
   ingest_seq_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(slab), total, t, c, tp, ld);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src_ld, void* dst,
+                                      int32_t dst_ld, int32_t slots, int32_t lk, int32_t c) {
+  using namespace lm2a;
+  LM2A_REQUIRE(src && dst, "transpose_kv: null pointer");
+  LM2A_REQUIRE(slots > 0 && slots <= 65535 && lk > 0 && c > 0 && c % 32 == 0 && src_ld >= c &&
+                   dst_ld >= lk,
+               "transpose_kv: bad geometry (slots=%d lk=%d c=%d src_ld=%d dst_ld=%d)", slots, lk,
+               c, src_ld, dst_ld);
+  dim3 grid((lk + 31) / 32, c / 32, slots);
+  transpose_kv_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_ld, reinterpret_cast<__nv_bfloat16*>(dst),
+      dst_ld, lk, c);
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -91,12 +91,17 @@ def gn_silu(x, x_ld, y, y_ld, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-
         rows, tp, t_valid, c, groups, eps, 1 if silu else 0), "lm2a_gn_silu_bf16")
 
 
-def cross_attn(q, q_ld, o, o_ld, k_m, v_m, k_t, v_t, kv_ld, kv_slot, rows, tp, t_valid, lk, e,
-               heads):
+def cross_attn(q, q_ld, o, o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, kv_slot, slots, rows, tp,
+               t_valid, lk, e, heads):
     _lib.check(_lib.load().lm2a_cross_attn_bf16(
-        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, v_m, k_t, v_t, kv_ld,
-        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), rows,
+        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld,
+        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows,
         tp, t_valid, lk, e, heads), "lm2a_cross_attn_bf16")
+
+
+def transpose_kv(src, src_ld, src_off, dst, dst_ld, slots, lk, c):
+    _lib.check(_lib.load().lm2a_transpose_kv_bf16(_stream(), _ptr(src, src_off), src_ld, _ptr(dst),
+                                                  dst_ld, slots, lk, c), "lm2a_transpose_kv_bf16")
 
 
 def time_mlp(t, w, b, out, rows, dim):

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by liblm2a_b200.so"
     assert declared == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
-    assert _lib.load().lm2a_abi_version() == 1
+    assert _lib.load().lm2a_abi_version() == _lib.ABI_VERSION
 
 
 def test_conv_desc_struct_matches_header_layout():
