@@ -235,13 +235,17 @@ class UNetPlan:
         self.x_slab = z(g.M[0], pm.in_pad)
         self.cat = [z(g.M[lvl], 2 * pm.dims[lvl]) for lvl in range(n_down)]
 
-        # K/V caches: per attention block [nslots*lk, 2E] per stream (K | V)
-        self.kv = []
+        # K/V caches per attention block and stream: [nslots*lk, 2E] (K | V) written by the
+        # projection GEMM, plus V^T [nslots*E, lk_pad] (keys contiguous: the K-major B operand
+        # of the tcgen05 P.V product)
+        self.kv, self.vt = [], []
+        self.lk_pad = _pad_to(lk, 8) if use_cond else 0
         if use_cond:
             self.cond_m = z(nslots * lk, pm.cond_dim)
             self.cond_t = z(nslots * lk, pm.cond_dim)
             for b in pm.attn_blocks:
                 self.kv.append((z(nslots * lk, 2 * b.e), z(nslots * lk, 2 * b.e)))
+                self.vt.append((z(nslots * b.e, self.lk_pad), z(nslots * b.e, self.lk_pad)))
         self.ops = []
         self.kv_ops = []
         self._build()
@@ -316,12 +320,12 @@ class UNetPlan:
         h2 = self._view(self._h2, m, cout)
         q = self._view(self._q, m, 2 * e)
         o = self._view(self._o, m, 2 * e)
-        kv_m, kv_t = kv
+        (kv_m, kv_t), (vt_m, vt_t) = kv
         self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.w2, p.b2, cout, m, tp, tv, h2, cout)
         self._conv([Seg(h2, cout, cout, TAPS_K1, m)], p.wq, p.bq, 2 * e, m, tp, tv, q, 2 * e)
-        self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e),
-                  ops._ptr(kv_t), ops._ptr(kv_t, e), 2 * e, ops._ptr(self.kv_slot, r0), nr, tp, tv,
-                  self.lk, e, p.heads,
+        self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
+                  ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad, ops._ptr(self.kv_slot, r0),
+                  self.nslots, nr, tp, tv, self.lk, e, p.heads,
                   meta={"kind": "cross_attn", "flops": 2 * 4 * nr * tv * self.lk * e})
         self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
                    out, out_ld, out_chan_off=oo, **res)
@@ -330,17 +334,19 @@ class UNetPlan:
     def _build(self):
         pm, g, rows = self.pm, self.geo, self.rows
         n_down = len(pm.dims)
-        kv_iter = iter(self.kv) if self.use_cond else iter(())
+        kv_iter = iter(zip(self.kv, self.vt)) if self.use_cond else iter(())
         next_kv = lambda p: next(kv_iter) if (p.attn and self.use_cond) else None  # noqa: E731
 
         if self.use_cond:
-            for p, (kv_m, kv_t) in zip(pm.attn_blocks, self.kv):
+            for p, (kv_m, kv_t), (vt_m, vt_t) in zip(pm.attn_blocks, self.kv, self.vt):
                 n = self.nslots * self.lk
-                for cond, w, b, dst in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m),
-                                        (self.cond_t, p.wkv_t, p.bkv_t, kv_t)):
+                for cond, w, b, dst, vt in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m, vt_m),
+                                            (self.cond_t, p.wkv_t, p.bkv_t, kv_t, vt_t)):
                     self.kv_ops.append((ops.conv1d, (ops.make_conv_desc(
                         [Seg(cond, pm.cond_dim, pm.cond_dim, TAPS_K1, n)], w, b, 2 * p.e, n,
                         self.lk, self.lk, dst, 2 * p.e),)))
+                    self.kv_ops.append((ops.transpose_kv, (dst, 2 * p.e, p.e, vt, self.lk_pad,
+                                                           self.nslots, self.lk, p.e)))
 
         # timestep embedding + all FiLM tables, once per step
         self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,

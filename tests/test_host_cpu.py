@@ -73,7 +73,7 @@ def test_geometry_and_plan():
     plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
     kinds = [m["kind"] for _, _, m in plan.ops]
     assert kinds.count("conv_gemm") == 56 and kinds.count("gn_silu") == 31
-    assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 18
+    assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
     # K/V hoisted + out_proj.fuse folded: production net = 28.23 GFLOP per row-step at T=516
     big = PackedModel(UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8), torch.device("cpu"))
     gf = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu")).flops() / 2 / 1e9

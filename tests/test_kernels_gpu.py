@@ -191,20 +191,34 @@ def test_gn_silu(ops, r, t, tp, c, groups):
     assert pads_are_zero(y, r, tp, t)
 
 
-@pytest.mark.parametrize("e,heads,t,lk", [(256, 8, 100, 77), (512, 8, 258, 516), (1024, 8, 64, 516),
-                                          (128, 4, 33, 64)])
-def test_cross_attention_core(ops, e, heads, t, lk):
+@pytest.mark.parametrize("e,heads,t,lk,qgain", [
+    (256, 8, 100, 77, 1.0), (512, 8, 258, 516, 1.0), (1024, 8, 64, 516, 1.0), (128, 4, 33, 64, 1.0),
+    (256, 8, 516, 516, 1.0),     # production level 0: dh = 32, five query tiles, ragged key tail
+    (1024, 8, 129, 516, 1.0),    # production level 2: dh = 128, two query tiles
+    (512, 8, 130, 2064, 1.0),    # long-clip K/V
+    (256, 8, 200, 300, 6.0), (1024, 8, 70, 200, 6.0),  # peaked softmax: running max grows, O is rescaled
+])
+def test_cross_attention_core(ops, e, heads, t, lk, qgain):
     r, slots, tp = 3, 2, t + 2
     dh = e // heads
-    q = rnd(r, 2 * e, t, seed=30)
+    q = rnd(r, 2 * e, t, seed=30) * qgain
     kv_m = rnd(slots * lk, 2 * e, seed=31).to(BF16)
     kv_t = rnd(slots * lk, 2 * e, seed=32).to(BF16)
     kv_slot = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
     scale = 1.0 / math.sqrt(dh)
     qs = to_slab(q * (scale * 1.4426950408889634), tp)
     o = torch.zeros(r * tp, 2 * e, dtype=BF16, device="cuda")
-    ops.cross_attn(qs, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(kv_m, e), ops._ptr(kv_t),
-                   ops._ptr(kv_t, e), 2 * e, kv_slot, r, tp, t, lk, e, heads)
+    lk_pad = (lk + 7) // 8 * 8
+    vts = []
+    for kv in (kv_m, kv_t):
+        vt = torch.zeros(slots * e, lk_pad, dtype=BF16, device="cuda")
+        ops.transpose_kv(kv, 2 * e, e, vt, lk_pad, slots, lk, e)
+        torch.cuda.synchronize()
+        want = kv.view(slots, lk, 2 * e)[:, :, e:].permute(0, 2, 1).reshape(slots * e, lk)
+        assert torch.equal(vt[:, :lk], want) and bool((vt[:, lk:] == 0).all())
+        vts.append(vt)
+    ops.cross_attn(qs, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vts[0]), ops._ptr(kv_t),
+                   ops._ptr(vts[1]), 2 * e, lk_pad, kv_slot, slots, r, tp, t, lk, e, heads)
     torch.cuda.synchronize()
     got = from_slab(o, r, tp, t, 2 * e)
     for s, kv in enumerate((kv_m, kv_t)):
