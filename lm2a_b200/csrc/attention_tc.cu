@@ -215,9 +215,18 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const uint32_t p_row = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
 
+    // warps whose 32 query rows are all past t_valid only keep the barrier protocol going
+    // (their P rows stay garbage: MMA rows are independent and those O rows are never stored)
+    const bool warp_valid = q0 + warp * 32 < t_valid;
+
     for (int j = 0; j < ntiles; ++j) {
       const int b = j & 1;
       mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
+      if (!warp_valid) {
+        // s_full(j) implies p_full(j-2) has completed, so this arrival lands in tile j's phase
+        mbar_arrive(p_full(b));
+        continue;
+      }
       tc_fence_after_sync();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
@@ -235,9 +244,15 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         for (int c = 0; c < 64; ++c)
           if (c >= keys) s[c] = -INFINITY;
       }
-      float mx = s[0];
+      float mxa[4] = {s[0], s[1], s[2], s[3]};  // four independent chains
 #pragma unroll
-      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
+      for (int c = 4; c < 64; c += 4) {
+        mxa[0] = fmaxf(mxa[0], s[c]);
+        mxa[1] = fmaxf(mxa[1], s[c + 1]);
+        mxa[2] = fmaxf(mxa[2], s[c + 2]);
+        mxa[3] = fmaxf(mxa[3], s[c + 3]);
+      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
 
       // lazy rescale: keep the stale max while the new one is within 2^8 of it
       const bool grow = mx > m_used + kRescaleThreshold;
@@ -262,16 +277,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_st_wait();
       }
 
-      float sum = 0.f;
+      float suma[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
         const float p0 = ex2_approx(s[c] - m_used);
         const float p1 = ex2_approx(s[c + 1] - m_used);
-        sum += p0 + p1;
+        suma[(c >> 1) & 3] += p0 + p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
-      l_run += sum;
+      l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
 
       // P tile slot b is free once P_{j-2} V_{j-2} has completed
       if (j >= 2) mbar_wait(pv_done(b), (uint32_t)((j >> 1) - 1) & 1u);
@@ -295,7 +310,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const int t = q0 + row;
     __nv_bfloat16* op = o + ((size_t)r * tp + t) * o_ld + stream * e + h * DH;
 #pragma unroll
-    for (int c0 = 0; c0 < DH; c0 += 32) {
+    for (int c0 = 0; c0 < (warp_valid ? DH : 0); c0 += 32) {
       uint32_t ov[32];
       tmem_ld_32x32(tmem_o + lane_off + c0, ov);
       tmem_ld_wait();
