@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 2
+#define LM2A_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -83,6 +83,18 @@ typedef struct lm2a_conv_desc {
   void* out;              /* bf16 slab [m, out_ld] or fp32 [R, n_valid, t_valid] */
   int32_t out_ld;
   int32_t block_n;        /* 0 = auto, else 128 or 256                        */
+  /* Optional partial GroupNorm statistics of the OUTPUT (bf16 slab mode only),
+   * consumed by lm2a_gn_apply_bf16. float2 {sum, sum of squares} at
+   *   stats[((r*stats_sub + c/stats_gran) * stats_ns) + slice]
+   * for clip-row r (relative to this launch), output channel c (relative to
+   * `out`), slice = ceil(t_first/32) of the 32-slot warp segment that starts at
+   * slot t_first of the clip. Every slice is written by exactly one warp
+   * (plain store): allocate zeroed, never clear. stats_ns >= tp/32 + 2.       */
+  void* stats;
+  int32_t stats_sub;      /* row pitch of the stats buffer in sub-blocks      */
+  int32_t stats_ns;       /* slices per (row, sub-block)                      */
+  int32_t stats_gran;     /* channels per sub-block: 8, 16 or 32              */
+  int32_t _pad2;
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);
@@ -93,6 +105,17 @@ int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                       int32_t y_ld, const float* gamma, const float* beta,
                       int32_t rows, int32_t tp, int32_t t_valid, int32_t c,
                       int32_t groups, float eps, int32_t apply_silu);
+
+/* GroupNorm + SiLU as one streaming pass over a slab whose partial sums were
+ * produced by the kernel that wrote it (lm2a_conv_desc.stats / lm2a_bias_add_bf16):
+ * adds the slices in a fixed order (fp64), y = SiLU((x - mean) * rstd * gamma + beta).
+ * c/8 must divide 256 or be a multiple of it; (c/groups) % stats_gran == 0.   */
+int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                       int32_t y_ld, const void* stats, int32_t stats_sub,
+                       int32_t stats_ns, int32_t stats_gran, const float* gamma,
+                       const float* beta, int32_t rows, int32_t tp,
+                       int32_t t_valid, int32_t c, int32_t groups, float eps,
+                       int32_t apply_silu);
 
 /* ---- cross-attention core (tcgen05 + TMEM) -------------------------------- */
 /* q,o: bf16 slabs [R*tp, ld]; stream s, head h live at channel s*e + h*dh.
@@ -140,10 +163,13 @@ int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
 
 /* y[slot,:c] = x[slot,:c] + bias[:c] for slots with t < t_valid, zero otherwise
  * (identity-skip ResBlock of an all-zero-condition row: its attention output is
- * a constant vector — the classifier-free-guidance uncond shortcut).         */
+ * a constant vector — the classifier-free-guidance uncond shortcut). `stats`
+ * (optional) receives the partial GroupNorm sums of y, layout as in
+ * lm2a_conv_desc.                                                            */
 int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                        int32_t y_ld, const float* bias, int64_t slots,
-                       int32_t tp, int32_t t_valid, int32_t c);
+                       int32_t tp, int32_t t_valid, int32_t c, void* stats,
+                       int32_t stats_sub, int32_t stats_ns, int32_t stats_gran);
 
 /* ---- CFG blend + clamps + DDPM posterior update -------------------------- */
 /* x [B,c,T] fp32 updated in place. eps: fp32 [2B,c,T] (uncond rows first)

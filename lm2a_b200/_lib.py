@@ -22,10 +22,12 @@ class ConvDesc(ctypes.Structure):
                 ("m", c_int64), ("tp", c_int32), ("t_valid", c_int32), ("bias", c_void_p),
                 ("film", c_void_p), ("film_ld", c_int32), ("film_shift_off", c_int32),
                 ("residual", c_void_p), ("res_ld", c_int32), ("out_mode", c_int32),
-                ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32)]
+                ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32),
+                ("stats", c_void_p), ("stats_sub", c_int32), ("stats_ns", c_int32),
+                ("stats_gran", c_int32), ("_pad2", c_int32)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -57,7 +59,11 @@ SIGNATURES = {
     "lm2a_upsample2x_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, c_int32]),
     "lm2a_bias_add_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
-                                     c_int64, c_int32, c_int32, c_int32]),
+                                     c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                     c_int32, c_int32]),
+    "lm2a_gn_apply_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                     c_int32, c_int32, c_int32, c_int32, c_float, c_int32]),
     "lm2a_cfg_posterior": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_int32, c_int64, c_float, c_int32,
                                      c_int32, c_void_p]),

@@ -15,8 +15,9 @@
 //              out-of-bounds zero fill are the conv padding) and one BLOCK_Nx64 W box
 //   warp 1     tcgen05.mma issuer (single thread), accumulators in TMEM,
 //              double-buffered so tile i+1's MMAs overlap tile i's epilogue
-//   warps 2-5  epilogue: tcgen05.ld -> bias/FiLM/residual -> bf16 slab (or the
-//              final fp32 [R, C, T] eps tensor)
+//   warps 2-9  epilogue: tcgen05.ld -> bias/FiLM/residual (+ partial GroupNorm sums of the
+//              output) -> bf16 slab (or the final fp32 [R, C, T] eps tensor); warp w reads
+//              TMEM lane quadrant w % 4 and the column half (w - 2) / 4
 #include "../../include/lm2a_b200.h"
 #include "common.cuh"
 
@@ -27,7 +28,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes half of the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct ConvArgs {
   int seg_cblk[2];   // cin / 64 per segment
@@ -45,6 +47,10 @@ struct ConvArgs {
   void* out;
   int out_ld;
   int out_mode;
+  float2* stats;     // partial GroupNorm sums of the output (or null), see lm2a_conv_desc
+  int stats_sub;     // sub-blocks per clip-row in the stats buffer (= its row pitch)
+  int stats_ns;      // slices per (clip-row, sub-block)
+  int stats_gran;    // channels per sub-block: 8, 16 or 32
 };
 
 template <int BLOCK_N, int STAGES>
@@ -87,7 +93,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 32 * kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -178,22 +184,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   } else {
     // ----------------------------------------------------------------- epilogue
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const long long m = (long long)(tile / p.n_tiles) * kBlockM + row;
+      const int m_tile0 = (tile / p.n_tiles) * kBlockM;
+      const long long m = (long long)m_tile0 + row;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const bool in_range = m < p.m;
-      const int r = in_range ? (int)(m / p.tp) : 0;
-      const int t = in_range ? (int)(m - (long long)r * p.tp) : 0;
+      const int r = in_range ? (int)((int)m / p.tp) : 0;
+      const int t = in_range ? (int)m - r * p.tp : 0;
       const bool valid = in_range && t < p.t_valid;
+      // clip-rows touched by this warp's 32 slots (GroupNorm partial sums are per clip-row)
+      const int m_first = m_tile0 + quad * 32;
+      const int m_last = m_first + 31 < (int)p.m - 1 ? m_first + 31 : (int)p.m - 1;
+      const int r_lo = m_first / p.tp;
+      const int r_hi = m_first < (int)p.m ? m_last / p.tp : r_lo - 1;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
         const int n = n0 + c0;
         if (n >= p.n_valid) break;  // warp-uniform
         uint32_t v[32];
@@ -233,6 +246,51 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               const float2 a = unpack_bf16x2(w[e]);
               f[j * 8 + e * 2 + 0] += a.x;
               f[j * 8 + e * 2 + 1] += a.y;
+            }
+          }
+        }
+        if (p.stats != nullptr) {
+          // Partial sum / sum of squares of this warp's 32 slots x 32 channels, per clip-row
+          // and per `gran`-channel sub-block, written (not accumulated) to a slot that only
+          // this warp owns: the consumer (gn_apply) adds the slices in a fixed order, so the
+          // statistics are deterministic and need no zeroing between steps.
+          float q1[4], q2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = valid ? f[q * 8 + j] : 0.f;
+              a += v;
+              b = fmaf(v, v, b);
+            }
+            q1[q] = a;
+            q2[q] = b;
+          }
+          const int nsub = 32 / p.stats_gran;  // sub-blocks inside this 32-channel chunk
+          if (nsub == 1) {
+            q1[0] = (q1[0] + q1[1]) + (q1[2] + q1[3]);
+            q2[0] = (q2[0] + q2[1]) + (q2[2] + q2[3]);
+          } else if (nsub == 2) {
+            q1[0] += q1[1];
+            q2[0] += q2[1];
+            q1[1] = q1[2] + q1[3];
+            q2[1] = q2[2] + q2[3];
+          }
+          const int sub0 = (n >> 3) / (p.stats_gran >> 3);
+          for (int rr = r_lo; rr <= r_hi; ++rr) {
+            const bool mine = in_range && r == rr;
+            const int t_first = m_first - rr * p.tp;
+            const int slice = t_first > 0 ? (t_first + 31) >> 5 : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (q < nsub) {
+                const float a = warp_sum(mine ? q1[q] : 0.f);
+                const float b = warp_sum(mine ? q2[q] : 0.f);
+                if (lane == 0)
+                  p.stats[((size_t)rr * p.stats_sub + sub0 + q) * p.stats_ns + slice] =
+                      make_float2(a, b);
+              }
             }
           }
         }
@@ -431,6 +489,18 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   a.out = d->out;
   a.out_ld = d->out_ld;
   a.out_mode = d->out_mode;
+  a.stats = reinterpret_cast<float2*>(d->stats);
+  a.stats_sub = d->stats_sub;
+  a.stats_ns = d->stats_ns;
+  a.stats_gran = d->stats_gran;
+  if (d->stats != nullptr) {
+    LM2A_REQUIRE(d->out_mode == LM2A_OUT_BF16_SLAB, "conv1d: stats need a bf16 slab output");
+    LM2A_REQUIRE((d->stats_gran == 8 || d->stats_gran == 16 || d->stats_gran == 32) &&
+                     d->stats_sub > 0 && d->stats_ns >= d->tp / 32 + 2 &&
+                     (reinterpret_cast<uintptr_t>(d->stats) & 7) == 0,
+                 "conv1d: bad stats layout (gran=%d sub=%d ns=%d, need ns >= tp/32+2 = %d)",
+                 d->stats_gran, d->stats_sub, d->stats_ns, d->tp / 32 + 2);
+  }
   if (d->out_mode == LM2A_OUT_BF16_SLAB) {
     LM2A_REQUIRE(d->out_ld % 8 == 0 && d->out_ld >= d->n_valid && d->n_valid % 32 == 0,
                  "conv1d: bf16 slab output needs ld %% 8 == 0 and n_valid %% 32 == 0 (ld=%d n=%d)",

@@ -94,27 +94,154 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* 
 // y[slot, :] = x[slot, :] + bias for valid slots (zero for the pad slots): the
 // identity-skip ResBlock of an all-zero-condition row, whose attention output is a
 // constant vector (reference unet1d_ultimate.py:152-159 with cross_attention.py:38-67).
+// One CTA = one 32-slot segment (the same segmentation as the conv epilogue), so it can emit
+// the same partial GroupNorm statistics of y for lm2a_gn_apply_bf16.
 __global__ void __launch_bounds__(256)
 bias_add_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
-                int y_ld, const float* __restrict__ bias, long long total_vec, int tp,
-                int t_valid, int c) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_vec) return;
+                int y_ld, const float* __restrict__ bias, long long slots, int tp, int t_valid,
+                int c, float2* __restrict__ stats, int stats_sub, int stats_ns, int stats_gran) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m_first = (long long)blockIdx.x * 32;
   const int vpr = c >> 3;
-  const int cv = (int)(i % vpr);
-  const long long slot = i / vpr;
-  const int t = (int)(slot % tp);
-  uint4 o = make_uint4(0u, 0u, 0u, 0u);
-  if (t < t_valid) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (size_t)slot * x_ld + cv * 8));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cv * 8 + 4));
-    const float2 f0 = unpack_bf16x2(a.x), f1 = unpack_bf16x2(a.y);
-    const float2 f2 = unpack_bf16x2(a.z), f3 = unpack_bf16x2(a.w);
-    o = make_uint4(pack_bf16x2(f0.x + b0.x, f0.y + b0.y), pack_bf16x2(f1.x + b0.z, f1.y + b0.w),
-                   pack_bf16x2(f2.x + b1.x, f2.y + b1.y), pack_bf16x2(f3.x + b1.z, f3.y + b1.w));
+  const int lanes_per_sub = stats != nullptr ? stats_gran >> 3 : 1;
+  for (int cvb = warp * 32; cvb < vpr; cvb += 256) {
+    const int cv = cvb + lane;
+    const bool active = cv < vpr;
+    float bv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bv[e] = active ? __ldg(bias + cv * 8 + e) : 0.f;
+    float a = 0.f, b = 0.f;
+    int r_cur = (int)(m_first / tp);
+    auto flush = [&](int rr) {
+      if (stats == nullptr) return;
+      float sa = a, sb = b;
+      for (int o = 1; o < lanes_per_sub; o <<= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      }
+      if (active && (cv % lanes_per_sub) == 0) {
+        const long long t_first = m_first - (long long)rr * tp;
+        const int slice = t_first > 0 ? (int)((t_first + 31) >> 5) : 0;
+        stats[((size_t)rr * stats_sub + (size_t)(cv / lanes_per_sub)) * stats_ns + slice] =
+            make_float2(sa, sb);
+      }
+    };
+    for (int sidx = 0; sidx < 32; ++sidx) {
+      const long long m = m_first + sidx;
+      if (m >= slots) break;
+      const int r = (int)(m / tp);
+      const int t = (int)(m - (long long)r * tp);
+      if (r != r_cur) {
+        flush(r_cur);
+        a = b = 0.f;
+        r_cur = r;
+      }
+      if (!active) continue;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (t < t_valid) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * x_ld + cv * 8));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(w[e]);
+          const float v0 = f.x + bv[2 * e], v1 = f.y + bv[2 * e + 1];
+          a += v0 + v1;
+          b = fmaf(v0, v0, fmaf(v1, v1, b));
+          ow[e] = pack_bf16x2(v0, v1);
+        }
+        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)m * y_ld + cv * 8) = o;
+    }
+    flush(r_cur);
   }
-  *reinterpret_cast<uint4*>(y + (size_t)slot * y_ld + cv * 8) = o;
+}
+
+// Same contract for tp >= 32 (a 32-slot segment then touches at most two clip-rows): all 256
+// threads stream the segment in parallel (thread = one 8-channel vector column, every
+// `tstep`-th slot); the partial sums are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256)
+bias_add_par_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+                    int y_ld, const float* __restrict__ bias, int slots, int tp, int t_valid,
+                    int c, float2* __restrict__ stats, int stats_sub, int stats_ns,
+                    int stats_gran) {
+  __shared__ float4 red[256];
+  const int m_first = blockIdx.x * 32;
+  const int vpr = c >> 3;
+  const int lanes = vpr < 256 ? vpr : 256;   // host guarantees 256 % lanes == 0
+  const int tstep = 256 / lanes;
+  const int cvl = threadIdx.x % lanes, ts = threadIdx.x / lanes;
+  const int r_lo = m_first / tp;
+  const int lanes_per_sub = stats != nullptr ? stats_gran >> 3 : 1;
+  for (int cv = cvl; cv < vpr; cv += 256) {
+    float bv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) bv[e] = __ldg(bias + cv * 8 + e);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // {sum, sumsq} of clip r_lo, of clip r_lo + 1
+    for (int sidx = ts; sidx < 32; sidx += tstep) {
+      const int m = m_first + sidx;
+      if (m >= slots) break;
+      const int r = m / tp;
+      const int t = m - r * tp;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (t < t_valid) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * x_ld + cv * 8));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t ow[4];
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(w[e]);
+          const float v0 = f.x + bv[2 * e], v1 = f.y + bv[2 * e + 1];
+          a += v0 + v1;
+          b = fmaf(v0, v0, fmaf(v1, v1, b));
+          ow[e] = pack_bf16x2(v0, v1);
+        }
+        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        if (r == r_lo) {
+          acc.x += a;
+          acc.y += b;
+        } else {
+          acc.z += a;
+          acc.w += b;
+        }
+      }
+      *reinterpret_cast<uint4*>(y + (size_t)m * y_ld + cv * 8) = o;
+    }
+    if (stats != nullptr) {
+      __syncthreads();
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      if (ts == 0) {
+        float4 tot = red[cvl];
+        for (int k = 1; k < tstep; ++k) {
+          const float4 v = red[k * lanes + cvl];
+          tot.x += v.x;
+          tot.y += v.y;
+          tot.z += v.z;
+          tot.w += v.w;
+        }
+        // lanes_per_sub (1, 2 or 4) adjacent vector columns form one sub-block
+        for (int o = 1; o < lanes_per_sub; o <<= 1) {
+          tot.x += __shfl_xor_sync(0xffffffffu, tot.x, o);
+          tot.y += __shfl_xor_sync(0xffffffffu, tot.y, o);
+          tot.z += __shfl_xor_sync(0xffffffffu, tot.z, o);
+          tot.w += __shfl_xor_sync(0xffffffffu, tot.w, o);
+        }
+        if ((cv % lanes_per_sub) == 0) {
+          const int m_last = m_first + 31 < slots - 1 ? m_first + 31 : slots - 1;
+          const int r_hi = m_last / tp;
+          const int t0 = m_first - r_lo * tp;
+          stats[((size_t)r_lo * stats_sub + cv / lanes_per_sub) * stats_ns +
+                (t0 > 0 ? (t0 + 31) >> 5 : 0)] = make_float2(tot.x, tot.y);
+          if (r_hi > r_lo)
+            stats[((size_t)r_hi * stats_sub + cv / lanes_per_sub) * stats_ns] =
+                make_float2(tot.z, tot.w);
+        }
+      }
+    }
+  }
 }
 
 // V cache transpose, once per clip: src bf16 [slots * lk, src_ld] (c channels used) ->
@@ -332,7 +459,8 @@ extern "C" int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, v
 
 extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                                   int32_t y_ld, const float* bias, int64_t slots, int32_t tp,
-                                  int32_t t_valid, int32_t c) {
+                                  int32_t t_valid, int32_t c, void* stats, int32_t stats_sub,
+                                  int32_t stats_ns, int32_t stats_gran) {
   using namespace lm2a;
   LM2A_REQUIRE(x && y && bias, "bias_add: null pointer");
   LM2A_REQUIRE(slots > 0 && tp > 0 && t_valid > 0 && t_valid <= tp && slots % tp == 0 &&
@@ -341,11 +469,27 @@ extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, voi
   LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                  reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
                "bias_add: tensors must be 16-byte aligned");
-  const long long total_vec = (long long)slots * (c / 8);
-  const int blocks = (int)((total_vec + 255) / 256);
-  bias_add_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
-      bias, total_vec, tp, t_valid, c);
+  if (stats != nullptr) {
+    LM2A_REQUIRE((stats_gran == 8 || stats_gran == 16 || stats_gran == 32) &&
+                     c % stats_gran == 0 && stats_sub >= c / stats_gran &&
+                     stats_ns >= tp / 32 + 2 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+                 "bias_add: bad stats layout (gran=%d sub=%d ns=%d)", stats_gran, stats_sub,
+                 stats_ns);
+  }
+  const long long blocks = (slots + 31) / 32;
+  const int vpr = c / 8;
+  LM2A_REQUIRE(slots < (1ll << 31) - 64, "bias_add: too many slots");
+  if (tp >= 32 && vpr % 32 == 0 && (vpr >= 256 ? vpr % 256 == 0 : 256 % vpr == 0)) {
+    bias_add_par_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
+        y_ld, bias, (int)slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub,
+        stats_ns, stats_gran);
+  } else {
+    bias_add_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
+        y_ld, bias, slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub, stats_ns,
+        stats_gran);
+  }
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

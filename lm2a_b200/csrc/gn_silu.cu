@@ -121,8 +121,157 @@ gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __r
   }
 }
 
+// ---------------------------------------------------------------------------
+// GroupNorm + SiLU as a pure streaming pass: the per-(row, group) sums were already
+// produced by the epilogue of the kernel that wrote x (lm2a_conv1d_bf16 / lm2a_bias_add_bf16
+// `stats`), so this kernel only adds the partial slices (fixed order, fp64), derives
+// mean / rstd and applies y = SiLU(x * a_c + b_c). One CTA = a few consecutive slots of one
+// clip-row, all channels; every thread owns one 8-channel vector column (4 slots of it).
+constexpr int kApplyVec = 4;  // 16-byte vectors per thread and pass
+
+__device__ __forceinline__ float silu_tanh(float v) {
+  // v * sigmoid(v) with sigmoid(v) = 0.5 + 0.5 tanh(v / 2): one MUFU op instead of two
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return v * fmaf(0.5f, t, 0.5f);
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
+                int y_ld, const float2* __restrict__ stats, int stats_sub, int stats_ns,
+                int stats_gran, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int tp, int t_valid, int c, int groups, float eps, int apply_silu) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int r = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = c / groups;
+  // thread -> (vector column, slot) mapping; the first pass's loads are issued before the
+  // statistics are reduced so their latency overlaps
+  const int vpr = c >> 3;
+  const int lanes = vpr < kGnThreads ? vpr : kGnThreads;
+  const int passes = (vpr + kGnThreads - 1) / kGnThreads;
+  const int tstep = kGnThreads / lanes;
+  const int cvl = threadIdx.x % lanes, tl = threadIdx.x / lanes;
+  const int t_begin = blockIdx.x * (kApplyVec * tstep);
+  const size_t row_base = (size_t)r * tp;
+  uint4 q[kApplyVec];
+#pragma unroll
+  for (int k = 0; k < kApplyVec; ++k) {
+    const int t = t_begin + tl + k * tstep;
+    q[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (t < t_valid)
+      q[k] = __ldg(reinterpret_cast<const uint4*>(x + (row_base + t) * x_ld + cvl * 8));
+  }
+  const int sub_per_group = cg / stats_gran;
+  const int per_group = sub_per_group * stats_ns;
+  const double inv_n = 1.0 / ((double)cg * (double)t_valid);
+  for (int g = warp; g < groups; g += kGnThreads / 32) {
+    const float2* sp = stats + ((size_t)r * stats_sub + (size_t)g * sub_per_group) * stats_ns;
+    double a = 0.0, b = 0.0;
+    for (int i = lane; i < per_group; i += 32) {
+      const float2 v = __ldg(sp + i);
+      a += (double)v.x;
+      b += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) {
+      const double mean = a * inv_n;
+      double var = b * inv_n - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+
+  for (int pass = 0; pass < passes; ++pass) {
+    const int cv = pass * kGnThreads + cvl;
+    if (pass > 0) {
+#pragma unroll
+      for (int k = 0; k < kApplyVec; ++k) {
+        const int t = t_begin + tl + k * tstep;
+        if (t < t_valid)
+          q[k] = __ldg(reinterpret_cast<const uint4*>(x + (row_base + t) * x_ld + cv * 8));
+      }
+    }
+    const int g = (cv * 8) / cg;
+    const float mean = s_mean[g], rstd = s_rstd[g];
+    float ga[8], be[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gm = __ldg(gamma + cv * 8 + e) * rstd;
+      ga[e] = gm;
+      be[e] = __ldg(beta + cv * 8 + e) - mean * gm;
+    }
+#pragma unroll
+    for (int k = 0; k < kApplyVec; ++k) {
+      const int t = t_begin + tl + k * tstep;
+      if (t >= tp) break;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (t < t_valid) {
+        const uint32_t w[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = unpack_bf16x2(w[e]);
+          float v0 = fmaf(a.x, ga[2 * e], be[2 * e]);
+          float v1 = fmaf(a.y, ga[2 * e + 1], be[2 * e + 1]);
+          if (apply_silu) {
+            v0 = silu_tanh(v0);
+            v1 = silu_tanh(v1);
+          }
+          ow[e] = pack_bf16x2(v0, v1);
+        }
+        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      *reinterpret_cast<uint4*>(y + (row_base + t) * y_ld + cv * 8) = o;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace lm2a
+
+extern "C" int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
+                                  int32_t y_ld, const void* stats, int32_t stats_sub,
+                                  int32_t stats_ns, int32_t stats_gran, const float* gamma,
+                                  const float* beta, int32_t rows, int32_t tp, int32_t t_valid,
+                                  int32_t c, int32_t groups, float eps, int32_t apply_silu) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && y && stats && gamma && beta, "gn_apply: null pointer");
+  LM2A_REQUIRE(rows > 0 && rows <= 65535 && tp > 0 && t_valid > 0 && t_valid <= tp,
+               "gn_apply: bad geometry");
+  LM2A_REQUIRE(groups > 0 && groups <= 64 && c % groups == 0,
+               "gn_apply: c=%d not divisible by groups=%d (<= 64)", c, groups);
+  const int cg = c / groups;
+  const int vpr = c / 8;
+  LM2A_REQUIRE(c % 8 == 0 && (kGnThreads % vpr == 0 || vpr % kGnThreads == 0),
+               "gn_apply: c/8 (%d) must divide or be a multiple of %d", vpr, kGnThreads);
+  LM2A_REQUIRE((stats_gran == 8 || stats_gran == 16 || stats_gran == 32) &&
+                   cg % stats_gran == 0 && stats_sub >= c / stats_gran &&
+                   stats_ns >= tp / 32 + 2,
+               "gn_apply: stats layout (gran=%d sub=%d ns=%d) does not fit c=%d groups=%d tp=%d",
+               stats_gran, stats_sub, stats_ns, c, groups, tp);
+  LM2A_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+               "gn_apply: ld must be a multiple of 8 and >= c");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+               "gn_apply: slabs must be 16-byte aligned");
+  const int lanes = vpr < kGnThreads ? vpr : kGnThreads;
+  const int slots_per_cta = kApplyVec * (kGnThreads / lanes);
+  dim3 grid((tp + slots_per_cta - 1) / slots_per_cta, rows);
+  gn_apply_kernel<<<grid, kGnThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
+      reinterpret_cast<const float2*>(stats), stats_sub, stats_ns, stats_gran, gamma, beta, tp,
+      t_valid, c, groups, eps, apply_silu);
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 
 extern "C" int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                                  int32_t y_ld, const float* gamma, const float* beta,

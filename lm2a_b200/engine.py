@@ -79,6 +79,17 @@ class PackedBlock:
     pass
 
 
+def _stats_gran(c, groups):
+    """Channel granularity of the partial GroupNorm sums of a slab whose consumer normalises
+    `c` channels in `groups` groups (8, 16 or 32 channels per sub-block)."""
+    cg = c // groups
+    for g in (32, 16, 8):
+        if cg % g == 0:
+            return g
+    raise RuntimeError(f"GroupNorm over {c} channels in {groups} groups: channels per group "
+                       "must be a multiple of 8 on the sm_100a path")
+
+
 def _check_channels(c, what):
     if c % 64 != 0:
         raise RuntimeError(f"{what}={c}: the sm_100a path needs channel counts that are "
@@ -267,31 +278,37 @@ class UNetPlan:
         self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
                   meta=meta)
 
-    def _resblock(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv):
-        """xin/out: (tensor, ld, channel offset) views of slabs at level `lvl`. With the uncond
+    def _stats(self, rows, lvl, c, groups):
+        return ops.Stats(rows, self.geo.Tp[lvl], c, _stats_gran(c, groups), self.dev)
+
+    def _resblock(self, p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st, kv):
+        """xin/out: (tensor, ld, channel offset, Stats) views of slabs at level `lvl`; the block
+        consumes the partial GroupNorm sums of xin and produces those of out. With the uncond
         shortcut, attention blocks run the full pipeline on the cond rows only; the leading
         `uncond_rows` rows get `skip(x) + const` (their attention output is Q-independent)."""
         u = self.uncond_rows if (p.attn and self.use_cond) else 0
         if u > 0:
-            self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, u)
-        self._resblock_rows(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv, u,
-                            self.rows - u)
+            self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u)
+        self._resblock_rows(p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st, kv,
+                            u, self.rows - u)
 
-    def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, u):
+    def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u):
         """Rows whose conditions are all-zero (sample.py:155-157): every key of a stream is the
         same vector, softmax is exactly uniform, the attention output is the constant
         fuse(out_proj(v_row)) and replaces h (unet1d_ultimate.py:152-159) -> out = skip(x) + c."""
         g = self.geo
         tp, tv = g.Tp[lvl], g.T[lvl]
         m = u * tp
+        st = out_st.view(0, out_off)
         if p.has_skip:
             self._conv([Seg(xin, xin_ld, p.cin, TAPS_K1, m, xin_off)], p.wsk, p.bsk_c, p.cout, m,
-                       tp, tv, out, out_ld, out_chan_off=out_off)
+                       tp, tv, out, out_ld, out_chan_off=out_off, stats=st)
         else:
             self._add(ops.bias_add, xin, xin_ld, xin_off, out, out_ld, out_off, p.c_uncond, m, tp,
-                      tv, p.cout, meta={"kind": "bias_add", "flops": 0})
+                      tv, p.cout, st, meta={"kind": "bias_add", "flops": 0})
 
-    def _resblock_rows(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, kv, r0, nr):
+    def _resblock_rows(self, p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st,
+                       kv, r0, nr):
         g = self.geo
         tp, tv = g.Tp[lvl], g.T[lvl]
         m = nr * tp
@@ -302,19 +319,21 @@ class UNetPlan:
         h1 = self._view(self._h1, m, cout)
         norm2 = self._view(self._norm2, m, cout)
         gm, bt, groups, eps = p.gn1
-        self._add(ops.gn_silu, xin, xin_ld, norm, cin, gm, bt, nr, tp, tv, cin, groups, eps,
-                  True, xo, 0)
+        self._add(ops.gn_apply, xin, xin_ld, norm, cin, xin_st.view(r0, xin_off), gm, bt, nr, tp,
+                  tv, cin, groups, eps, True, xo, 0, meta={"kind": "gn_apply", "flops": 0})
+        gm, bt, groups, eps = p.gn2
+        h1_st = self._stats(nr, lvl, cout, groups)
         self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
                    film=self.film, film_col=p.film_col, film_shift_off=cout,
-                   film_bcast=self.uniform_t, film_row=r0)
-        gm, bt, groups, eps = p.gn2
-        self._add(ops.gn_silu, h1, cout, norm2, cout, gm, bt, nr, tp, tv, cout, groups, eps,
-                  True, 0, 0)
+                   film_bcast=self.uniform_t, film_row=r0, stats=h1_st)
+        self._add(ops.gn_apply, h1, cout, norm2, cout, h1_st, gm, bt, nr, tp, tv, cout, groups,
+                  eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
         skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xo)] if p.has_skip else []
         res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xo)
+        ost = out_st.view(r0, out_off)
         if not (p.attn and self.use_cond):
             self._conv([Seg(norm2, cout, cout, TAPS_K3, m)] + skip_seg, p.w2s, p.b2s, cout, m,
-                       tp, tv, out, out_ld, out_chan_off=oo, **res)
+                       tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
             return
         e = p.e
         h2 = self._view(self._h2, m, cout)
@@ -328,7 +347,7 @@ class UNetPlan:
                   self.nslots, nr, tp, tv, self.lk, e, p.heads,
                   meta={"kind": "cross_attn", "flops": 2 * 4 * nr * tv * self.lk * e})
         self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
-                   out, out_ld, out_chan_off=oo, **res)
+                   out, out_ld, out_chan_off=oo, stats=ost, **res)
 
     # -- plan construction ----------------------------------------------------------------
     def _build(self):
@@ -356,10 +375,22 @@ class UNetPlan:
         # x -> bf16 slab (CFG row duplication happens here), in_proj
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
                   self.t, g.Tp[0], pm.in_pad)
+        groups_of = lambda blk_gn: blk_gn[2]  # noqa: E731
         cur = self._view(self._pp[0], g.M[0], pm.base)
+        first = pm.downs[0][0][0]
+        cur_st = self._stats(rows, 0, pm.base, groups_of(first.gn1))
         self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
-                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim)
+                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim, stats=cur_st)
         cur_c, pp = pm.base, 1
+
+        # the concat slab of level l is normalised as a whole by the first up block of that
+        # level; its two halves are written by different kernels into one Stats buffer
+        up_first = {n_down - 1 - i: blocks[0] for i, (_, _, blocks) in enumerate(pm.ups)}
+        self.cat_st = [self._stats(rows, lvl, 2 * pm.dims[lvl], groups_of(up_first[lvl].gn1))
+                       for lvl in range(n_down)]
+
+        def consumer_stats(lvl, c, nxt_block):
+            return self._stats(rows, lvl, c, groups_of(nxt_block.gn1))
 
         # down path: the last block of each stage writes straight into the second half of
         # the level's concat slab (= the skip connection), the stride-2 conv reads it there
@@ -369,25 +400,31 @@ class UNetPlan:
             for bi, p in enumerate(blocks):
                 last = bi == len(blocks) - 1
                 if last:
-                    out, out_ld, out_off = self.cat[lvl], 2 * dim, dim
+                    out, out_ld, out_off, out_st = self.cat[lvl], 2 * dim, dim, self.cat_st[lvl]
                 else:
                     out = self._view(self._pp[pp], g.M[lvl], p.cout)
                     out_ld, out_off = p.cout, 0
+                    out_st = consumer_stats(lvl, p.cout, blocks[bi + 1])
                     pp ^= 1
-                self._resblock(p, lvl, cur, cur_ld, cur_off, out, out_ld, out_off, next_kv(p))
-                cur, cur_ld, cur_off, cur_c = out, out_ld, out_off, p.cout
+                self._resblock(p, lvl, cur, cur_ld, cur_off, cur_st, out, out_ld, out_off, out_st,
+                               next_kv(p))
+                cur, cur_ld, cur_off, cur_c, cur_st = out, out_ld, out_off, p.cout, out_st
             nxt = self._view(self._pp[pp], g.M[lvl + 1], dim)
             pp ^= 1
+            nxt_block = pm.downs[lvl + 1][0][0] if lvl + 1 < n_down else pm.mid[0]
+            nxt_st = self._stats(rows, lvl + 1, dim, groups_of(nxt_block.gn1))
             self._conv([Seg(cur, cur_ld, dim, TAPS_K4S2, g.M[lvl], cur_off)], wd, bd, dim,
-                       g.M[lvl + 1], g.Tp[lvl + 1], g.T[lvl + 1], nxt, dim)
-            cur, cur_c = nxt, dim
+                       g.M[lvl + 1], g.Tp[lvl + 1], g.T[lvl + 1], nxt, dim, stats=nxt_st)
+            cur, cur_c, cur_st = nxt, dim, nxt_st
 
         lvl = n_down
-        for p in pm.mid:
+        for i, p in enumerate(pm.mid):
             out = self._view(self._pp[pp], g.M[lvl], p.cout)
             pp ^= 1
-            self._resblock(p, lvl, cur, cur_c, 0, out, p.cout, 0, next_kv(p))
-            cur, cur_c = out, p.cout
+            # (the last mid block feeds the up-conv, which has no GroupNorm: stats unused there)
+            out_st = self._stats(rows, lvl, p.cout, groups_of(pm.mid[min(i + 1, len(pm.mid) - 1)].gn1))
+            self._resblock(p, lvl, cur, cur_c, 0, cur_st, out, p.cout, 0, out_st, next_kv(p))
+            cur, cur_c, cur_st = out, p.cout, out_st
 
         # up path: interp x2 -> conv k3 into the first half of the concat slab (slots past
         # 2*T_{l+1} stay zero = F.pad), then the ResBlocks read the concat slab directly
@@ -400,19 +437,26 @@ class UNetPlan:
             self._add(ops.upsample2x, cur, cur_c, xup, cur_c, rows, g.Tp[lvl + 1], g.T[lvl + 1],
                       g.Tp[lvl], cur_c)
             self._conv([Seg(xup, cur_c, cur_c, TAPS_K3, g.M[lvl])], wu, bu, dim, g.M[lvl],
-                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim)
-            cur, cur_ld, cur_c = self.cat[lvl], 2 * dim, 2 * dim
-            for p in blocks:
+                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim, stats=self.cat_st[lvl].view(0, 0))
+            cur, cur_ld, cur_c, cur_st = self.cat[lvl], 2 * dim, 2 * dim, self.cat_st[lvl]
+            for bi, p in enumerate(blocks):
                 out = self._view(self._pp[pp], g.M[lvl], p.cout)
                 pp ^= 1
-                self._resblock(p, lvl, cur, cur_ld, 0, out, p.cout, 0, next_kv(p))
-                cur, cur_ld, cur_c = out, p.cout, p.cout
+                if bi + 1 < len(blocks):
+                    out_groups = groups_of(blocks[bi + 1].gn1)
+                elif i + 1 < len(pm.ups):
+                    out_groups = groups_of(p.gn2)  # feeds the next up-conv: no GroupNorm reads it
+                else:
+                    out_groups = pm.gn_out[2]
+                out_st = self._stats(rows, lvl, p.cout, out_groups)
+                self._resblock(p, lvl, cur, cur_ld, 0, cur_st, out, p.cout, 0, out_st, next_kv(p))
+                cur, cur_ld, cur_c, cur_st = out, p.cout, p.cout, out_st
 
         # out_proj: GN + SiLU + 1x1 conv, written as fp32 [rows, in_dim, T]
         gm, bt, groups, eps = pm.gn_out
         norm = self._view(self._norm, g.M[0], cur_c)
-        self._add(ops.gn_silu, cur, cur_c, norm, cur_c, gm, bt, rows, g.Tp[0], g.T[0], cur_c,
-                  groups, eps, True, 0, 0)
+        self._add(ops.gn_apply, cur, cur_c, norm, cur_c, cur_st, gm, bt, rows, g.Tp[0], g.T[0],
+                  cur_c, groups, eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
         self._conv([Seg(norm, cur_c, cur_c, TAPS_K1, g.M[0])], pm.w_out, pm.b_out, pm.in_dim,
                    g.M[0], g.Tp[0], g.T[0], self.eps, 0, out_mode=OUT_F32_NCT, block_n=128)
 

@@ -37,6 +37,28 @@ def reset_launch_count():
     _lib.load().lm2a_reset_launch_count()
 
 
+class Stats:
+    """Partial GroupNorm statistics of a slab [rows, tp, c]: float2 [rows, c/gran, ns] written by
+    the producing kernel's epilogue, read by gn_apply. `view(row0, chan0)` addresses a
+    row / channel sub-range (a launch over part of the rows, or one half of a concat slab)."""
+
+    def __init__(self, rows, tp, c, gran, dev, buf=None, row0=0, chan0=0):
+        self.rows, self.tp, self.c, self.gran = rows, tp, c, gran
+        self.sub = c // gran
+        self.ns = tp // 32 + 2
+        self.buf = buf if buf is not None else torch.zeros(rows * self.sub * self.ns, 2,
+                                                           dtype=torch.float32, device=dev)
+        self.row0, self.chan0 = row0, chan0
+
+    def view(self, row0=0, chan0=0):
+        return Stats(self.rows, self.tp, self.c, self.gran, None, self.buf, self.row0 + row0,
+                     self.chan0 + chan0)
+
+    def ptr(self):
+        off = (self.row0 * self.sub + self.chan0 // self.gran) * self.ns
+        return self.buf.data_ptr() + off * 8
+
+
 class Seg:
     """One K segment of the implicit GEMM: a bf16 slab view (tensor + channel offset)."""
 
@@ -48,7 +70,7 @@ class Seg:
 def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan_off=0,
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
-                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0):
+                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object."""
     d = ConvDesc()
@@ -76,7 +98,10 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
     d.out = out.data_ptr() + out_chan_off * out.element_size()
     d.out_ld = out_ld
     d.block_n = block_n
-    d._keep = (segs, w, bias, film, residual, out)
+    if stats is not None:  # Stats view: partial GroupNorm sums of the output
+        d.stats = stats.ptr()
+        d.stats_sub, d.stats_ns, d.stats_gran = stats.sub, stats.ns, stats.gran
+    d._keep = (segs, w, bias, film, residual, out, stats)
     return d
 
 
@@ -137,7 +162,17 @@ def cfg_posterior(x, eps, noise, sched, t_dev, ticket, batch, elems_per_clip, gu
         1 if advance else 0, _ptr(eps_out)), "lm2a_cfg_posterior")
 
 
-def bias_add(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c):
-    _lib.check(_lib.load().lm2a_bias_add_bf16(_stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld,
-                                              _ptr(bias), slots, tp, t_valid, c),
-               "lm2a_bias_add_bf16")
+def bias_add(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c, stats=None):
+    _lib.check(_lib.load().lm2a_bias_add_bf16(
+        _stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld, _ptr(bias), slots, tp, t_valid, c,
+        ctypes.c_void_p(stats.ptr()) if stats is not None else None,
+        stats.sub if stats is not None else 0, stats.ns if stats is not None else 0,
+        stats.gran if stats is not None else 0), "lm2a_bias_add_bf16")
+
+
+def gn_apply(x, x_ld, y, y_ld, stats, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-5,
+             silu=True, x_chan_off=0, y_chan_off=0):
+    _lib.check(_lib.load().lm2a_gn_apply_bf16(
+        _stream(), _ptr(x, x_chan_off), x_ld, _ptr(y, y_chan_off), y_ld,
+        ctypes.c_void_p(stats.ptr()), stats.sub, stats.ns, stats.gran, _ptr(gamma), _ptr(beta),
+        rows, tp, t_valid, c, groups, eps, 1 if silu else 0), "lm2a_gn_apply_bf16")

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "lm2a_b200.h")).read()
     code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(lm2a_[a-z0-9_]+)\s*\(", code))
-    assert len(declared) >= 14
+    assert len(declared) >= 16
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by liblm2a_b200.so"
@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_conv_desc_struct_matches_header_layout():
     from lm2a_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSeg) == 32
-    assert ctypes.sizeof(_lib.ConvDesc) == 152
+    assert ctypes.sizeof(_lib.ConvDesc) == 176
     assert _lib.ConvDesc.out.offset == 136 and _lib.ConvDesc.m.offset == 80
 
 
@@ -72,7 +72,7 @@ def test_geometry_and_plan():
     pm = PackedModel(net, torch.device("cpu"))
     plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
     kinds = [m["kind"] for _, _, m in plan.ops]
-    assert kinds.count("conv_gemm") == 56 and kinds.count("gn_silu") == 31
+    assert kinds.count("conv_gemm") == 56 and kinds.count("gn_apply") == 31
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
     # K/V hoisted + out_proj.fuse folded: production net = 28.23 GFLOP per row-step at T=516
     big = PackedModel(UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8), torch.device("cpu"))

@@ -191,6 +191,73 @@ def test_gn_silu(ops, r, t, tp, c, groups):
     assert pads_are_zero(y, r, tp, t)
 
 
+@pytest.mark.parametrize("r,t,tp,cin,cout,groups,r0", [
+    (3, 37, 40, 64, 64, 8, 0),        # tiny: 8 channels per group, several clips per warp segment
+    (5, 129, 130, 128, 256, 8, 2),    # row sub-range (cond rows of a CFG batch), clip straddles
+    (4, 516, 520, 256, 256, 8, 0),    # production level 0
+    (6, 64, 65, 1024, 2048, 8, 3),    # 256 channels per group, 65-slot clips
+])
+def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0):
+    """conv epilogue emits partial GroupNorm sums; gn_apply consumes them: together they must
+    equal F.group_norm + SiLU of the conv output (unet1d_ultimate.py:136-147)."""
+    nr = r - r0
+    x = rnd(r, cin, t, seed=50)
+    w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=51)
+    b = rnd(cout, scale=0.3, seed=52)
+    gamma = 1 + 0.1 * rnd(cout, seed=53)
+    beta = 0.1 * rnd(cout, seed=54)
+    xs = to_slab(x, tp)
+    h = torch.zeros(r * tp, cout, dtype=BF16, device="cuda")
+    cg = cout // groups
+    gran = 32 if cg % 32 == 0 else (16 if cg % 16 == 0 else 8)
+    st = ops.Stats(r, tp, cout, gran, "cuda")
+    # launch over rows [r0, r): slabs and stats addressed through row-offset views
+    d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, nr * tp, chan_off=r0 * tp * cin)],
+                           pack_w(w), pad_bias(b, (cout + 127) // 128 * 128), cout, nr * tp, tp, t,
+                           h, cout, out_chan_off=r0 * tp * cout, stats=st.view(r0, 0))
+    ops.conv1d(d)
+    y = torch.full((r * tp, cout), 3.0, dtype=BF16, device="cuda")
+    ops.gn_apply(h, cout, y, cout, st.view(r0, 0), gamma, beta, nr, tp, t, cout, groups,
+                 x_chan_off=r0 * tp * cout, y_chan_off=r0 * tp * cout)
+    torch.cuda.synchronize()
+    hf = from_slab(h, r, tp, t, cout)[r0:]
+    ref = F.silu(F.group_norm(hf, groups, gamma, beta, 1e-5))
+    assert_close(from_slab(y, r, tp, t, cout)[r0:], ref, 6e-3, "conv stats -> gn_apply")
+    assert pads_are_zero(y[r0 * tp:], nr, tp, t)
+    # the statistics themselves: sum over slices == per-(row, group) sums of the conv output
+    sums = st.buf.view(r, cout // gran, st.ns, 2).sum(2)[r0:].view(nr, groups, -1, 2).sum(2)
+    ref1 = hf.reshape(nr, groups, -1).sum(-1)
+    ref2 = (hf.reshape(nr, groups, -1) ** 2).sum(-1)
+    assert torch.allclose(sums[..., 0], ref1, rtol=2e-2, atol=0.5)
+    assert torch.allclose(sums[..., 1], ref2, rtol=2e-2)
+    # determinism: a second run writes bit-identical statistics
+    before = st.buf.clone()
+    ops.conv1d(d)
+    torch.cuda.synchronize()
+    assert torch.equal(before, st.buf)
+
+
+@pytest.mark.parametrize("r,t,tp,c,groups,gran", [(3, 129, 130, 512, 8, 32), (33, 64, 65, 1024, 8, 32),
+                                                  (5, 9, 10, 64, 8, 8), (4, 516, 520, 256, 8, 32)])
+def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
+    x = rnd(r, c, t, seed=60)
+    bias = rnd(c, scale=0.5, seed=61)
+    gamma = 1 + 0.1 * rnd(c, seed=62)
+    beta = 0.1 * rnd(c, seed=63)
+    xs = to_slab(x, tp)
+    y = torch.full((r * tp, c), 2.0, dtype=BF16, device="cuda")
+    st = ops.Stats(r, tp, c, gran, "cuda")
+    ops.bias_add(xs, c, 0, y, c, 0, bias, r * tp, tp, t, c, st)
+    z = torch.zeros_like(y)
+    ops.gn_apply(y, c, z, c, st, gamma, beta, r, tp, t, c, groups)
+    torch.cuda.synchronize()
+    yf = from_slab(y, r, tp, t, c)
+    assert_close(yf, bf(x) + bias[None, :, None], 4e-3, "bias_add")
+    assert pads_are_zero(y, r, tp, t)
+    ref = F.silu(F.group_norm(yf, groups, gamma, beta, 1e-5))
+    assert_close(from_slab(z, r, tp, t, c), ref, 6e-3, "bias_add stats -> gn_apply")
+
+
 @pytest.mark.parametrize("e,heads,t,lk,qgain", [
     (256, 8, 100, 77, 1.0), (512, 8, 258, 516, 1.0), (1024, 8, 64, 516, 1.0), (128, 4, 33, 64, 1.0),
     (256, 8, 516, 516, 1.0),     # production level 0: dh = 32, five query tiles, ragged key tail
