@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/lm2a_b200.h"
 #include "common.cuh"
@@ -33,6 +34,15 @@ EncodeTiledFn get_encode_fn() {
     }
   }
   return fn;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LM2A_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int num_sms() {

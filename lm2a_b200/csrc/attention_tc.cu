@@ -7,7 +7,8 @@
 // it away).
 //
 // One CTA = 128 queries of one (clip-row, stream, head); keys are walked in tiles of 64.
-//   warp 4     TMA producer: Q tile once, then a 3-stage ring of (K tile, V^T tile)
+//   warp 4     TMA producer: Q tile once + a ring of K tiles and a ring of V^T tiles (separate
+//              rings: a K slot is free as soon as S_j is done, a V slot only after P_j V_j)
 //   warp 5     tcgen05.mma issuer (one thread): S_j = Q K_j^T into a double-buffered TMEM
 //              tile, O += P_j V_j with P_j read from shared memory; S_{j+1} is issued
 //              before P_j V_j so the tensor pipe works while the softmax warps run
@@ -25,8 +26,7 @@ namespace {
 
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
-constexpr int kStages = 3;
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;  // 4 softmax warps, TMA producer, MMA issuer
 constexpr uint32_t kTmemCols = 256;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -40,14 +40,19 @@ struct AttnSmem {
   static constexpr int kKBytes = kBK * DH * 2;
   static constexpr int kVBytes = DH * kBK * 2;
   static constexpr int kPBytes = kBQ * kBK * 2;
-  static constexpr int kStageBytes = kKBytes + kVBytes;
+  // dh = 128: two K + two V stages and one P tile keep a CTA at 112 KB so that two fit an SM
+  static constexpr int kKStages = DH > 64 ? 2 : 3;
+  static constexpr int kVStages = DH > 64 ? 2 : 3;
+  static constexpr int kPBufs = DH > 64 ? 1 : 2;
   static constexpr int kPOff = kQBytes;
-  static constexpr int kKVOff = kPOff + 2 * kPBytes;
-  static constexpr int kBarOff = kKVOff + kStages * kStageBytes;
-  static constexpr int kNeeded = kBarOff + 256 + 1024;
+  static constexpr int kKOff = kPOff + kPBufs * kPBytes;
+  static constexpr int kVOff = kKOff + kKStages * kKBytes;
+  static constexpr int kBarOff = kVOff + kVStages * kVBytes;
+  static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 1;
+  static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
   // dh = 32 would fit three CTAs per SM by shared memory but only two by TMEM columns:
   // ask for enough that the third is never scheduled (it would spin in tcgen05.alloc)
-  static constexpr int kBytes = kNeeded < 80 * 1024 && DH <= 64 ? 80 * 1024 : kNeeded;
+  static constexpr int kBytes = kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, bool sw64) {
@@ -83,7 +88,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int DH>
-__global__ void __launch_bounds__(kThreads, (DH > 64 ? 1 : 2))
+__global__ void __launch_bounds__(kThreads, 2)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmKm,
                      const __grid_constant__ CUtensorMap tmKt,
@@ -93,22 +98,25 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                      int e, int heads) {
   using L = AttnSmem<DH>;
   constexpr bool kSw64 = (DH == 32);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int KS = L::kKStages, VS = L::kVStages, PB = L::kPBufs;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t q_base = smem_base;
   auto p_tile = [&](int b) { return smem_base + L::kPOff + b * L::kPBytes; };
-  auto k_tile = [&](int s) { return smem_base + L::kKVOff + s * L::kStageBytes; };
-  auto v_tile = [&](int s) { return smem_base + L::kKVOff + s * L::kStageBytes + L::kKBytes; };
+  auto k_tile = [&](int s) { return smem_base + L::kKOff + s * L::kKBytes; };
+  auto v_tile = [&](int s) { return smem_base + L::kVOff + s * L::kVBytes; };
   const uint32_t bar_base = smem_base + L::kBarOff;
   // barrier slots (8 B each)
   const uint32_t q_full = bar_base;
-  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + kStages + s); };
-  auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * kStages + b); };
-  auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * kStages + b); };
-  auto pv_done = [&](int b) { return bar_base + 8u * (5 + 2 * kStages + b); };
-  const uint32_t o_full = bar_base + 8u * (7 + 2 * kStages);
-  const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * kStages);
+  auto k_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar_base + 8u * (1 + KS + s); };
+  auto v_full = [&](int s) { return bar_base + 8u * (1 + 2 * KS + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (1 + 2 * KS + VS + s); };
+  auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * KS + 2 * VS + b); };
+  auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + b); };
+  auto pv_done = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + PB + b); };
+  const uint32_t o_full = bar_base + 8u * (3 + 2 * KS + 2 * VS + 2 * PB);
+  const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.z;
@@ -116,19 +124,30 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   const int h = blockIdx.y % heads;
   const int q0 = blockIdx.x * kBQ;
   const int ntiles = (lk + kBK - 1) / kBK;
+  // softmax warps whose 32 query rows are all past t_valid do nothing at all (their P rows
+  // stay garbage: MMA rows are independent and those O rows are never stored)
+  const int valid_warps = min(4, (t_valid - q0 + 31) >> 5);
 
   if (warp == 4 && lane == 0) {
+    if ((smem_base & 1023u) != 0) {
+      printf("lm2a: attention shared memory base not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(stream ? &tmKt : &tmKm);
     tma_prefetch_desc(stream ? &tmVt : &tmVm);
     mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(s_full(b), 1);
-      mbar_init(p_full(b), 128);
+    for (int s = 0; s < VS; ++s) {
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) mbar_init(s_full(b), 1);
+    for (int b = 0; b < PB; ++b) {
+      mbar_init(p_full(b), 32 * valid_warps);
       mbar_init(pv_done(b), 1);
     }
     mbar_init(o_full, 1);
@@ -143,29 +162,40 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // everything above overlapped the previous kernel's tail; from here on we touch its output
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 4) {
     // ------------------------------------------------------------- TMA producer
+    // Q, then K_{j+1} before V_j: a K slot frees when S_{j+1-KS} is done, a V slot when
+    // P_{j-VS} V_{j-VS} is done, which happen in this order
     if (lane == 0) {
       const int slot = kv_slot[r];
       const CUtensorMap* km = stream ? &tmKt : &tmKm;
       const CUtensorMap* vm = stream ? &tmVt : &tmVm;
+      auto load_k = [&](int j) {
+        const int st = j % KS;
+        mbar_wait(k_empty(st), ((uint32_t)(j / KS) & 1u) ^ 1u);
+        mbar_expect_tx(k_full(st), L::kKBytes);
+#pragma unroll
+        for (int p = 0; p < L::kPanels; ++p)
+          tma_load_2d(k_tile(st) + p * L::kKPanelBytes, km, h * DH + p * 64,
+                      slot * lk + j * kBK, k_full(st));
+      };
       mbar_expect_tx(q_full, L::kQBytes);
 #pragma unroll
       for (int p = 0; p < L::kPanels; ++p)
         tma_load_2d(q_base + p * L::kQPanelBytes, &tmQ, stream * e + h * DH + p * 64,
                     r * tp + q0, q_full);
+      load_k(0);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kStages;
-        const uint32_t ph = (uint32_t)(j / kStages) & 1u;
-        mbar_wait(kv_empty(st), ph ^ 1u);
-        mbar_expect_tx(kv_full(st), L::kStageBytes);
-#pragma unroll
-        for (int p = 0; p < L::kPanels; ++p)
-          tma_load_2d(k_tile(st) + p * L::kKPanelBytes, km, h * DH + p * 64,
-                      slot * lk + j * kBK, kv_full(st));
-        tma_load_2d(v_tile(st), vm, j * kBK, slot * e + h * DH, kv_full(st));
+        if (j + 1 < ntiles) load_k(j + 1);
+        const int st = j % VS;
+        mbar_wait(v_empty(st), ((uint32_t)(j / VS) & 1u) ^ 1u);
+        mbar_expect_tx(v_full(st), L::kVBytes);
+        tma_load_2d(v_tile(st), vm, j * kBK, slot * e + h * DH, v_full(st));
       }
     }
   } else if (warp == 5) {
@@ -174,23 +204,24 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, DH);
       auto issue_pv = [&](int jj) {
-        const int b = jj & 1, st = jj % kStages;
-        mbar_wait(p_full(b), (uint32_t)(jj >> 1) & 1u);
+        const int pb = jj % PB, st = jj % VS;
+        mbar_wait(v_full(st), (uint32_t)(jj / VS) & 1u);
+        mbar_wait(p_full(pb), (uint32_t)(jj / PB) & 1u);
         tc_fence_after_sync();
         const int keys = min(kBK, lk - jj * kBK);
         const int ksteps = (keys + 15) >> 4;
-        const uint64_t adesc = umma_desc_kmajor(p_tile(b), false);
+        const uint64_t adesc = umma_desc_kmajor(p_tile(pb), false);
         const uint64_t bdesc = umma_desc_kmajor(v_tile(st), false);
         for (int k = 0; k < ksteps; ++k)
           umma_bf16_ss(tmem_o, adesc + 2u * k, bdesc + 2u * k, idesc_pv,
                        (jj | k) != 0 ? 1u : 0u);
-        umma_commit(kv_empty(st));
-        umma_commit(pv_done(b));
+        umma_commit(v_empty(st));
+        umma_commit(pv_done(pb));
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kStages, b = j & 1;
-        mbar_wait(kv_full(st), (uint32_t)(j / kStages) & 1u);
+        const int st = j % KS, b = j & 1;
+        mbar_wait(k_full(st), (uint32_t)(j / KS) & 1u);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -201,13 +232,14 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
               umma_desc_kmajor(k_tile(st) + panel * L::kKPanelBytes + kk * 32, kSw64);
           umma_bf16_ss(tmem_base + b * kBK, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
         }
+        umma_commit(k_empty(st));
         umma_commit(s_full(b));
         if (j >= 1) issue_pv(j - 1);
       }
       issue_pv(ntiles - 1);
       umma_commit(o_full);
     }
-  } else {
+  } else if (warp < valid_warps) {
     // ------------------------------------------------------------------ softmax
     const int row = warp * 32 + lane;  // TMEM lane == query row of the tile
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
@@ -215,18 +247,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const uint32_t p_row = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
 
-    // warps whose 32 query rows are all past t_valid only keep the barrier protocol going
-    // (their P rows stay garbage: MMA rows are independent and those O rows are never stored)
-    const bool warp_valid = q0 + warp * 32 < t_valid;
-
     for (int j = 0; j < ntiles; ++j) {
-      const int b = j & 1;
+      const int b = j & 1, pb = j % PB;
       mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
-      if (!warp_valid) {
-        // s_full(j) implies p_full(j-2) has completed, so this arrival lands in tile j's phase
-        mbar_arrive(p_full(b));
-        continue;
-      }
       tc_fence_after_sync();
       uint32_t v0[32], v1[32];
       tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
@@ -263,7 +286,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         l_run *= corr;
       }
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        mbar_wait(pv_done((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+        mbar_wait(pv_done((j - 1) % PB), (uint32_t)((j - 1) / PB) & 1u);
         tc_fence_after_sync();
 #pragma unroll
         for (int c0 = 0; c0 < DH; c0 += 32) {
@@ -277,30 +300,29 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_st_wait();
       }
 
+      // the P tile slot is free once P_{j-PB} V_{j-PB} has completed
+      if (j >= PB) mbar_wait(pv_done(pb), (uint32_t)(j / PB - 1) & 1u);
+      const uint32_t pbase = p_tile(pb) + p_row;
       float suma[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float p0 = ex2_approx(s[c] - m_used);
-        const float p1 = ex2_approx(s[c + 1] - m_used);
-        suma[(c >> 1) & 3] += p0 + p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
-      }
-      l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
-
-      // P tile slot b is free once P_{j-2} V_{j-2} has completed
-      if (j >= 2) mbar_wait(pv_done(b), (uint32_t)((j >> 1) - 1) & 1u);
-      const uint32_t pb = p_tile(b) + p_row;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const uint32_t addr = pb + (((uint32_t)c ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * c]),
-                     "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = ex2_approx(s[c * 8 + 2 * i] - m_used);
+          const float p1 = ex2_approx(s[c * 8 + 2 * i + 1] - m_used);
+          suma[i] += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        const uint32_t addr = pbase + (((uint32_t)c ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]),
+                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
       }
+      l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(p_full(b));
+      mbar_arrive(p_full(pb));
     }
 
     // ---- finalise: O / l -> bf16 slab
@@ -310,7 +332,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const int t = q0 + row;
     __nv_bfloat16* op = o + ((size_t)r * tp + t) * o_ld + stream * e + h * DH;
 #pragma unroll
-    for (int c0 = 0; c0 < (warp_valid ? DH : 0); c0 += 32) {
+    for (int c0 = 0; c0 < DH; c0 += 32) {
       uint32_t ov[32];
       tmem_ld_32x32(tmem_o + lane_off + c0, ov);
       tmem_ld_wait();
@@ -386,9 +408,9 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
                  false))
     return 1;
   dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
-  kern<<<grid, kThreads, L::kBytes, st>>>(tq, tkm, tkt, tvm, tvt,
+  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, st, tq, tkm, tkt, tvm, tvt,
                                           reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
-                                          t_valid, lk, e, heads);
+                                          t_valid, lk, e, heads));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -23,6 +23,30 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_fn();
 
+// Every kernel of the library is launched with programmatic dependent launch (PDL): its
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the
+// previous kernel in the stream; it calls pdl_wait() before touching global memory.
+// LM2A_PDL=0 in the environment turns the attribute off (plain stream order).
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define LM2A_REQUIRE(cond, ...)        \
   do {                                 \
     if (!(cond)) {                     \
@@ -43,6 +67,16 @@ EncodeTiledFn get_encode_fn();
 
 // -------------------------------------------------------------- device side
 #ifdef __CUDACC__
+
+// PDL: block until the preceding kernel in the stream has completed and its writes are
+// visible (no-op when launched without the attribute); then let the next kernel's CTAs be
+// scheduled as soon as resources free up.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

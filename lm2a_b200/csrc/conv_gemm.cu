@@ -106,6 +106,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // everything above overlapped the previous kernel's tail; from here on we touch its output
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
@@ -373,7 +376,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   }
   const int tiles = args.m_tiles * args.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, L::kBytes, stream>>>(a0, a1, b, args);
+  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, stream, a0, a1, b, args));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -14,6 +14,8 @@ namespace {
 __global__ void __launch_bounds__(256)
 ingest_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, int batch,
                 int copies, int c, int T, int tp, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float tile[32][129];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
@@ -39,6 +41,8 @@ ingest_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, i
 __global__ void __launch_bounds__(256)
 ingest_seq_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, long long total,
                   int T, int c, int tp, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cc = (int)(i % ld);
@@ -57,6 +61,8 @@ ingest_seq_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab,
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
                   int y_ld, long long total_vec, int tp_in, int t_in, int tp_out, int c) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total_vec) return;
   const int vpr = c >> 3;
@@ -100,6 +106,8 @@ __global__ void __launch_bounds__(256)
 bias_add_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
                 int y_ld, const float* __restrict__ bias, long long slots, int tp, int t_valid,
                 int c, float2* __restrict__ stats, int stats_sub, int stats_ns, int stats_gran) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_first = (long long)blockIdx.x * 32;
   const int vpr = c >> 3;
@@ -166,6 +174,8 @@ bias_add_par_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
                     int y_ld, const float* __restrict__ bias, int slots, int tp, int t_valid,
                     int c, float2* __restrict__ stats, int stats_sub, int stats_ns,
                     int stats_gran) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float4 red[256];
   const int m_first = blockIdx.x * 32;
   const int vpr = c >> 3;
@@ -250,6 +260,8 @@ bias_add_par_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
 __global__ void __launch_bounds__(256)
 transpose_kv_kernel(const __nv_bfloat16* __restrict__ src, int src_ld,
                     __nv_bfloat16* __restrict__ dst, int dst_ld, int lk, int c) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __nv_bfloat16 tile[32][34];
   const int slot = blockIdx.z;
   const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -273,6 +285,8 @@ transpose_kv_kernel(const __nv_bfloat16* __restrict__ src, int src_ld,
 __global__ void __launch_bounds__(256)
 time_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w,
                 const float* __restrict__ b, float* __restrict__ out, int dim) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float emb[];
   const int r = blockIdx.x;
   const int half = dim / 2;
@@ -305,6 +319,8 @@ template <int KPL>  // dim / 32
 __global__ void __launch_bounds__(256)
 film_kernel(const float* __restrict__ s, const float* __restrict__ w,
             const float* __restrict__ b, float* __restrict__ film, int rows, int cols) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + warp;
   if (j >= cols) return;
@@ -335,6 +351,8 @@ cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
                      int64_t* __restrict__ t_dev, int n_t, unsigned int* __restrict__ ticket,
                      long long total_vec, long long clip_vec, int batch, float gw, int guided,
                      int advance, float* __restrict__ eps_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long uncond_to_cond = (long long)batch * clip_vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
@@ -401,8 +419,8 @@ extern "C" int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t b
                    tp >= t,
                "ingest_x: bad geometry (c=%d ld=%d t=%d tp=%d; c, ld <= 128)", c, ld, t, tp);
   dim3 grid((tp + 31) / 32, batch);
-  ingest_x_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(slab), batch, copies, c, t, tp, ld);
+  LM2A_CUDA_OK(launch_kernel(ingest_x_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
+      x, reinterpret_cast<__nv_bfloat16*>(slab), batch, copies, c, t, tp, ld));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -415,8 +433,8 @@ extern "C" int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t
   LM2A_REQUIRE(rows > 0 && t > 0 && tp >= t && c > 0 && ld >= c, "ingest_seq: bad geometry");
   const long long total = (long long)rows * tp * ld;
   const int blocks = (int)((total + 255) / 256);
-  ingest_seq_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<__nv_bfloat16*>(slab), total, t, c, tp, ld);
+  LM2A_CUDA_OK(launch_kernel(ingest_seq_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
+      x, reinterpret_cast<__nv_bfloat16*>(slab), total, t, c, tp, ld));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -431,9 +449,9 @@ extern "C" int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src
                "transpose_kv: bad geometry (slots=%d lk=%d c=%d src_ld=%d dst_ld=%d)", slots, lk,
                c, src_ld, dst_ld);
   dim3 grid((lk + 31) / 32, c / 32, slots);
-  transpose_kv_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LM2A_CUDA_OK(launch_kernel(transpose_kv_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(src), src_ld, reinterpret_cast<__nv_bfloat16*>(dst),
-      dst_ld, lk, c);
+      dst_ld, lk, c));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -449,9 +467,9 @@ extern "C" int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, v
                "upsample2x: bad geometry");
   const long long total_vec = (long long)rows * tp_out * (c / 8);
   const int blocks = (int)((total_vec + 255) / 256);
-  upsample2x_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LM2A_CUDA_OK(launch_kernel(upsample2x_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
-      total_vec, tp_in, t_in, tp_out, c);
+      total_vec, tp_in, t_in, tp_out, c));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -480,15 +498,15 @@ extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, voi
   const int vpr = c / 8;
   LM2A_REQUIRE(slots < (1ll << 31) - 64, "bias_add: too many slots");
   if (tp >= 32 && vpr % 32 == 0 && (vpr >= 256 ? vpr % 256 == 0 : 256 % vpr == 0)) {
-    bias_add_par_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    LM2A_CUDA_OK(launch_kernel(bias_add_par_kernel, dim3((unsigned)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
         reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
         y_ld, bias, (int)slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub,
-        stats_ns, stats_gran);
+        stats_ns, stats_gran));
   } else {
-    bias_add_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    LM2A_CUDA_OK(launch_kernel(bias_add_kernel, dim3((unsigned)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
         reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
         y_ld, bias, slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub, stats_ns,
-        stats_gran);
+        stats_gran));
   }
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -500,9 +518,8 @@ extern "C" int lm2a_time_mlp(void* stream, const int64_t* t, const float* w, con
   using namespace lm2a;
   LM2A_REQUIRE(t && w && b && silu_temb, "time_mlp: null pointer");
   LM2A_REQUIRE(rows > 0 && dim >= 4 && dim % 2 == 0 && dim <= 4096, "time_mlp: bad dim %d", dim);
-  time_mlp_kernel<<<dim3(rows, (dim + 7) / 8), 256, dim * sizeof(float),
-                    reinterpret_cast<cudaStream_t>(stream)>>>(
-      t, w, b, silu_temb, dim);
+  LM2A_CUDA_OK(launch_kernel(time_mlp_kernel, dim3(dim3(rows, (dim + 7) / 8)), dim3(256), dim * sizeof(float), reinterpret_cast<cudaStream_t>(stream), 
+      t, w, b, silu_temb, dim));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -516,9 +533,9 @@ extern "C" int lm2a_film(void* stream, const float* silu_temb, const float* w, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = (cols + 7) / 8;
   switch (dim) {
-    case 128: film_kernel<4><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
-    case 256: film_kernel<8><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
-    case 512: film_kernel<16><<<blocks, 256, 0, st>>>(silu_temb, w, b, film, rows, cols); break;
+    case 128: LM2A_CUDA_OK(launch_kernel(film_kernel<4>, dim3(blocks), dim3(256), 0, st, silu_temb, w, b, film, rows, cols)); break;
+    case 256: LM2A_CUDA_OK(launch_kernel(film_kernel<8>, dim3(blocks), dim3(256), 0, st, silu_temb, w, b, film, rows, cols)); break;
+    case 512: LM2A_CUDA_OK(launch_kernel(film_kernel<16>, dim3(blocks), dim3(256), 0, st, silu_temb, w, b, film, rows, cols)); break;
     default:
       LM2A_REQUIRE(false, "film: time_emb_dim %d unsupported (128, 256 or 512)", dim);
   }
@@ -546,9 +563,9 @@ extern "C" int lm2a_cfg_posterior(void* stream, float* x, const float* eps, cons
   const long long total_vec = clip_vec * batch;
   long long blocks = (total_vec + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cfg_posterior_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LM2A_CUDA_OK(launch_kernel(cfg_posterior_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, eps, noise, sched, t_dev, n_t, ticket, total_vec, clip_vec, batch, guidance, guided,
-      advance, eps_out);
+      advance, eps_out));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

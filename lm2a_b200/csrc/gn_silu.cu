@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(kGnThreads)
 gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
                int y_ld, const float* __restrict__ gamma, const float* __restrict__ beta,
                int tp, int t_valid, int cg, float eps, int apply_silu) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ uint4 cache[];
   __shared__ float red[kGnThreads / 32];
   const int g = blockIdx.x, r = blockIdx.y;
@@ -141,6 +143,8 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
                 int y_ld, const float2* __restrict__ stats, int stats_sub, int stats_ns,
                 int stats_gran, const float* __restrict__ gamma, const float* __restrict__ beta,
                 int tp, int t_valid, int c, int groups, float eps, int apply_silu) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float s_mean[64], s_rstd[64];
   const int r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -264,10 +268,10 @@ extern "C" int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, voi
   const int lanes = vpr < kGnThreads ? vpr : kGnThreads;
   const int slots_per_cta = kApplyVec * (kGnThreads / lanes);
   dim3 grid((tp + slots_per_cta - 1) / slots_per_cta, rows);
-  gn_apply_kernel<<<grid, kGnThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  LM2A_CUDA_OK(launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
       reinterpret_cast<const float2*>(stats), stats_sub, stats_ns, stats_gran, gamma, beta, tp,
-      t_valid, c, groups, eps, apply_silu);
+      t_valid, c, groups, eps, apply_silu));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -303,11 +307,11 @@ extern "C" int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void
                                         200 * 1024));
       configured = true;
     }
-    gn_silu_kernel<true><<<grid, kGnThreads, cache_bytes, st>>>(
-        xp, x_ld, yp, y_ld, gamma, beta, tp, t_valid, cg, eps, apply_silu);
+    LM2A_CUDA_OK(launch_kernel(gn_silu_kernel<true>, dim3(grid), dim3(kGnThreads), cache_bytes, st, 
+        xp, x_ld, yp, y_ld, gamma, beta, tp, t_valid, cg, eps, apply_silu));
   } else {
-    gn_silu_kernel<false><<<grid, kGnThreads, 0, st>>>(xp, x_ld, yp, y_ld, gamma, beta, tp,
-                                                       t_valid, cg, eps, apply_silu);
+    LM2A_CUDA_OK(launch_kernel(gn_silu_kernel<false>, dim3(grid), dim3(kGnThreads), 0, st, xp, x_ld, yp, y_ld, gamma, beta, tp,
+                                                       t_valid, cg, eps, apply_silu));
   }
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
