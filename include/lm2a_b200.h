@@ -94,7 +94,8 @@ typedef struct lm2a_conv_desc {
   int32_t stats_sub;      /* row pitch of the stats buffer in sub-blocks      */
   int32_t stats_ns;       /* slices per (row, sub-block)                      */
   int32_t stats_gran;     /* channels per sub-block: 8, 16 or 32              */
-  int32_t _pad2;
+  int32_t cta_group;      /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA
+                             pair (cluster of 2, cta_group::2 UMMA) per 256 rows */
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);

@@ -24,7 +24,7 @@ class ConvDesc(ctypes.Structure):
                 ("residual", c_void_p), ("res_ld", c_int32), ("out_mode", c_int32),
                 ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32),
                 ("stats", c_void_p), ("stats_sub", c_int32), ("stats_ns", c_int32),
-                ("stats_gran", c_int32), ("_pad2", c_int32)]
+                ("stats_gran", c_int32), ("cta_group", c_int32)]
 
 
 ABI_VERSION = 3

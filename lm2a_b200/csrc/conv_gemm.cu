@@ -19,6 +19,8 @@
 //              output) -> bf16 slab (or the final fp32 [R, C, T] eps tensor); warp w reads
 //              TMEM lane quadrant w % 4 and the column half (w - 2) / 4
 #include "../../include/lm2a_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lm2a {
@@ -53,20 +55,23 @@ struct ConvArgs {
   int stats_gran;    // channels per sub-block: 8, 16 or 32
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CG>
 struct SmemLayout {
-  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBTileBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits B along N
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
 };
 
-template <int BLOCK_N, int STAGES>
+// CG = 1: one CTA per 128 x BLOCK_N tile. CG = 2: a CTA pair (cluster of 2) per 256 x BLOCK_N
+// tile with cta_group::2 UMMA: each CTA stages its own 128 rows of A and half of the W rows,
+// so the operand bytes an SM pulls from L2 per MMA cycle drop from 96 to 64 (BLOCK_N = 256).
+template <int BLOCK_N, int STAGES, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::kBarOffset;
@@ -82,6 +87,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;       // tile-walking unit
+  const int num_units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -93,16 +101,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 32 * kEpiWarps);
+      mbar_init(tempty_bar(s), 32 * kEpiWarps * CG);  // pair: the leader collects both CTAs
     }
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BLOCK_N);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, 2 * BLOCK_N);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, 2 * BLOCK_N);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -114,9 +127,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * kBlockM;
-        const int n0 = (tile % p.n_tiles) * BLOCK_N;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        const int m0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
+        const int n0 = (tile % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
         int kb = 0;
 #pragma unroll 1
         for (int seg = 0; seg < 2; ++seg) {
@@ -139,10 +152,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll 1
             for (int cb = 0; cb < cblk; ++cb, ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              mbar_expect_tx(full_bar(stage), L::kStageBytes);
-              tma_load_2d(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift,
-                          full_bar(stage));
-              tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
+              if (CG == 2) {
+                // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
+                const uint32_t fb = mapa_shared(full_bar(stage), 0);
+                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+                tma_load_2d_cg2(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift, fb);
+                tma_load_2d_cg2(b_tile(stage), &tmB, kb * kBlockK, n0, fb);
+              } else {
+                mbar_expect_tx(full_bar(stage), L::kStageBytes);
+                tma_load_2d(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift,
+                            full_bar(stage));
+                tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
+              }
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1u;
@@ -153,11 +174,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       }
     }
   } else if (warp == 1) {
-    // --------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+    // ------------------------------------------- MMA issuer (pair: the leader CTA only)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -170,16 +191,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
-            umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2)
+              umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));
+        if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
         acc ^= 1u;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -190,8 +215,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile0 = (tile / p.n_tiles) * kBlockM;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
+      const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
       const long long m = (long long)m_tile0 + row;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
       const bool in_range = m < p.m;
@@ -328,17 +353,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         }
       }
       tc_fence_before_sync();
-      mbar_arrive(tempty_bar(acc));
+      if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      else mbar_arrive(tempty_bar(acc));
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, 2 * BLOCK_N);
+    else tmem_dealloc(tmem_base, 2 * BLOCK_N);
   }
 }
 
@@ -363,11 +390,11 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int CG>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
            const CUtensorMap& b, const ConvArgs& args) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
-  auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, CG>;
+  auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CG>;
   static bool configured = false;
   if (!configured) {
     LM2A_CUDA_OK(
@@ -375,11 +402,42 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
     configured = true;
   }
   const int tiles = args.m_tiles * args.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, stream, a0, a1, b, args));
-  LM2A_CUDA_OK(cudaGetLastError());
+  const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
+  const int grid = (tiles < units ? tiles : units) * CG;
+  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kThreads), L::kBytes, stream,
+                                     (unsigned)CG, a0, a1, b, args));
   count_launch();
   return 0;
+}
+
+// Tile shape choice by a wave model. Per 64-deep K block a CTA needs max(MMA cycles, operand
+// bytes / ~64 B per clock an SM pulls from L2):
+//   1 CTA,  128 x 256: max(512, 48 KB / 64) = 768      1 CTA,  128 x 128: max(256, 512) = 512
+//   pair,   256 x 256: max(512, 32 KB / 64) = 512      pair,   256 x 128: max(256, 384) = 384
+struct TileChoice {
+  int block_n, cg;
+};
+TileChoice choose_tile(long long m, int n_pad) {
+  const long long sms = num_sms();
+  TileChoice best{128, 1};
+  long long best_cost = -1;
+  const int bns[2] = {256, 128};
+  for (int cg = 2; cg >= 1; --cg) {
+    for (int bi = 0; bi < 2; ++bi) {
+      const int bn = bns[bi];
+      if (n_pad % bn != 0) continue;
+      const long long tiles = ((m + 128 * cg - 1) / (128 * cg)) * (n_pad / bn);
+      const long long units = sms / cg;
+      const long long waves = (tiles + units - 1) / units;
+      const long long per_kb = cg == 2 ? (bn == 256 ? 512 : 384) : (bn == 256 ? 768 : 512);
+      const long long cost = waves * per_kb;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best = TileChoice{bn, cg};
+      }
+    }
+  }
+  return best;
 }
 
 }  // namespace
@@ -442,33 +500,43 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     }
     k_total += ntaps * g.cin;
   }
-  int block_n = d->block_n;
-  if (block_n == 0) {
-    block_n = 128;
-    if (d->n_pad % 256 == 0) {
-      // wave model: cost = waves x tile width; 128-wide tiles pay ~15 % for the higher
-      // shared-memory operand traffic per MMA. Narrow tiles win when 256-wide ones would
-      // leave most SMs idle (e.g. the cond-only half batch at the deepest level).
-      const long long m_tiles = (d->m + kBlockM - 1) / kBlockM;
-      const long long sms = num_sms();
-      const long long w256 = (m_tiles * (d->n_pad / 256) + sms - 1) / sms;
-      const long long w128 = (m_tiles * (d->n_pad / 128) + sms - 1) / sms;
-      block_n = (w128 * 128 * 115 < w256 * 256 * 100) ? 128 : 256;
+  int block_n = d->block_n, cg = d->cta_group;
+  if (cg == 0) {
+    // LM2A_CONV_CG=1|2 pins the auto choice (A/B measurements); unset = wave model
+    static const int forced = [] {
+      const char* e = getenv("LM2A_CONV_CG");
+      return (e != nullptr && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }();
+    if (forced != 0) {
+      cg = forced;
+      if (block_n == 0) block_n = d->n_pad % 256 == 0 ? 256 : 128;
+    }
+  }
+  if (block_n == 0 || cg == 0) {
+    const TileChoice c = choose_tile(d->m, d->n_pad);
+    if (block_n == 0 && cg == 0) {
+      block_n = c.block_n;
+      cg = c.cg;
+    } else if (block_n == 0) {
+      block_n = d->n_pad % 256 == 0 ? 256 : 128;
+    } else {
+      cg = c.cg;
     }
   }
   LM2A_REQUIRE((block_n == 128 || block_n == 256) && d->n_pad % block_n == 0,
                "conv1d: block_n=%d incompatible with n_pad=%d", block_n, d->n_pad);
+  LM2A_REQUIRE(cg == 1 || cg == 2, "conv1d: cta_group=%d (0 = auto, 1 or 2)", cg);
   LM2A_REQUIRE((reinterpret_cast<uintptr_t>(d->w) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0,
                "conv1d: w / out / bias must be 16-byte aligned");
   CUtensorMap tmB;
   if (encode_2d(&tmB, d->w, (uint64_t)k_total, (uint64_t)d->n_pad, (uint64_t)k_total,
-                (uint32_t)block_n))
+                (uint32_t)(block_n / cg)))
     return 1;
 
   a.num_kb = k_total / 64;
-  a.m_tiles = (int)((d->m + kBlockM - 1) / kBlockM);
+  a.m_tiles = (int)((d->m + kBlockM * cg - 1) / (kBlockM * cg));
   a.n_tiles = d->n_pad / block_n;
   a.m = d->m;
   a.tp = d->tp;
@@ -513,6 +581,10 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return launch<256, 4>(st, tmA[0], tmA[1], tmB, a);
-  return launch<128, 6>(st, tmA[0], tmA[1], tmB, a);
+  if (cg == 2) {
+    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, a);
+    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, a);
+  }
+  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, a);
+  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, a);
 }

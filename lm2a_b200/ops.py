@@ -70,7 +70,7 @@ class Seg:
 def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan_off=0,
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
-                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None):
+                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object."""
     d = ConvDesc()
@@ -98,6 +98,7 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
     d.out = out.data_ptr() + out_chan_off * out.element_size()
     d.out_ld = out_ld
     d.block_n = block_n
+    d.cta_group = cta_group
     if stats is not None:  # Stats view: partial GroupNorm sums of the output
         d.stats = stats.ptr()
         d.stats_sub, d.stats_ns, d.stats_gran = stats.sub, stats.ns, stats.gran

@@ -69,20 +69,22 @@ def assert_close(got, ref, rel=1e-2, what=""):
     assert err < rel, f"{what}: rel-L2 {err:.3e} max-abs {mx:.3e}"
 
 
+@pytest.mark.parametrize("cta_group", [1, 2, 0])  # one CTA per tile, CTA pair (cta_group::2), auto
 @pytest.mark.parametrize("r,t,tp,cin,cout,block_n", [
-    (2, 60, 64, 64, 128, 128),      # single M tile
+    (2, 60, 64, 64, 128, 128),      # single M tile (pair: the second CTA's rows are all padding)
     (3, 129, 130, 128, 256, 256),   # tiles span clip boundaries
     (5, 258, 260, 256, 512, 0),     # multi-tile persistent, auto block_n
     (64, 64, 65, 1024, 1024, 256),  # production mid level: K = 3072, all SMs busy
+    (40, 516, 520, 256, 256, 128),  # more tiles than SMs: several tiles per CTA / pair
 ])
-def test_conv_k3(ops, r, t, tp, cin, cout, block_n):
+def test_conv_k3(ops, r, t, tp, cin, cout, block_n, cta_group):
     x = rnd(r, cin, t, seed=1)
     w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=2)
     b = rnd(cout, scale=0.1, seed=3)
     xs = to_slab(x, tp)
     out = torch.full((r * tp, cout), 7.0, dtype=BF16, device="cuda")
     d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, r * tp)], pack_w(w), pad_bias(b, (cout + 127) // 128 * 128),
-                           cout, r * tp, tp, t, out, cout, block_n=block_n)
+                           cout, r * tp, tp, t, out, cout, block_n=block_n, cta_group=cta_group)
     ops.conv1d(d)
     torch.cuda.synchronize()
     ref = F.conv1d(bf(x), bf(w), b, padding=1)
@@ -113,8 +115,9 @@ def test_conv_k1_film_residual_and_strided_io(ops):
     assert bool((out[:, :cout] == 0).all()), "first half of the output slab must be untouched"
 
 
+@pytest.mark.parametrize("cta_group", [1, 2])
 @pytest.mark.parametrize("r,t_in,c", [(2, 64, 128), (3, 129, 256), (9, 516, 256)])
-def test_conv_k4s2(ops, r, t_in, c):
+def test_conv_k4s2(ops, r, t_in, c, cta_group):
     t_out = t_in // 2
     tp_out = t_out + 1
     tp_in = 2 * tp_out
@@ -125,7 +128,8 @@ def test_conv_k4s2(ops, r, t_in, c):
     xs = to_slab(x, tp_in, ld=2 * c, chan_off=c)
     out = torch.zeros(r * tp_out, c, dtype=BF16, device="cuda")
     d = ops.make_conv_desc([ops.Seg(xs, 2 * c, c, ops.TAPS_K4S2, r * tp_in, chan_off=c)], pack_w(w),
-                           pad_bias(b, (c + 127) // 128 * 128), c, r * tp_out, tp_out, t_out, out, c)
+                           pad_bias(b, (c + 127) // 128 * 128), c, r * tp_out, tp_out, t_out, out, c,
+                           cta_group=cta_group)
     ops.conv1d(d)
     torch.cuda.synchronize()
     ref = F.conv1d(bf(x), bf(w), b, stride=2, padding=1)
@@ -134,7 +138,8 @@ def test_conv_k4s2(ops, r, t_in, c):
     assert pads_are_zero(out, r, tp_out, t_out)
 
 
-def test_conv_two_segments_and_f32_nct(ops):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_conv_two_segments_and_f32_nct(ops, cta_group):
     """conv2 + fused 1x1 skip conv (second K segment), and the fp32 [R, C, T] eps epilogue."""
     r, t, tp, c1, c2, cout = 3, 77, 80, 128, 256, 128
     a = rnd(r, c1, t, seed=12)
@@ -146,7 +151,7 @@ def test_conv_two_segments_and_f32_nct(ops):
     out = torch.zeros(r * tp, cout, dtype=BF16, device="cuda")
     d = ops.make_conv_desc([ops.Seg(to_slab(a, tp), c1, c1, ops.TAPS_K3, r * tp),
                             ops.Seg(to_slab(x, tp), c2, c2, ops.TAPS_K1, r * tp)], wcat,
-                           pad_bias(b, 128), cout, r * tp, tp, t, out, cout)
+                           pad_bias(b, 128), cout, r * tp, tp, t, out, cout, cta_group=cta_group)
     ops.conv1d(d)
     ref = F.conv1d(bf(a), bf(w2), b, padding=1) + F.conv1d(bf(x), bf(ws))
     torch.cuda.synchronize()
@@ -158,7 +163,7 @@ def test_conv_two_segments_and_f32_nct(ops):
     eps = torch.zeros(r, n_valid, t, device="cuda")
     d = ops.make_conv_desc([ops.Seg(to_slab(a, tp), c1, c1, ops.TAPS_K1, r * tp)], pack_w(wo, 128),
                            pad_bias(bo, 128), n_valid, r * tp, tp, t, eps, 0,
-                           out_mode=ops.OUT_F32_NCT, block_n=128)
+                           out_mode=ops.OUT_F32_NCT, block_n=128, cta_group=cta_group)
     ops.conv1d(d)
     torch.cuda.synchronize()
     assert_close(eps, F.conv1d(bf(a), bf(wo), bo), 2e-3, "f32 nct epilogue")
@@ -197,7 +202,8 @@ def test_gn_silu(ops, r, t, tp, c, groups):
     (4, 516, 520, 256, 256, 8, 0),    # production level 0
     (6, 64, 65, 1024, 2048, 8, 3),    # 256 channels per group, 65-slot clips
 ])
-def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0, cta_group):
     """conv epilogue emits partial GroupNorm sums; gn_apply consumes them: together they must
     equal F.group_norm + SiLU of the conv output (unet1d_ultimate.py:136-147)."""
     nr = r - r0
@@ -214,7 +220,8 @@ def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0):
     # launch over rows [r0, r): slabs and stats addressed through row-offset views
     d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, nr * tp, chan_off=r0 * tp * cin)],
                            pack_w(w), pad_bias(b, (cout + 127) // 128 * 128), cout, nr * tp, tp, t,
-                           h, cout, out_chan_off=r0 * tp * cout, stats=st.view(r0, 0))
+                           h, cout, out_chan_off=r0 * tp * cout, stats=st.view(r0, 0),
+                           cta_group=cta_group)
     ops.conv1d(d)
     y = torch.full((r * tp, cout), 3.0, dtype=BF16, device="cuda")
     ops.gn_apply(h, cout, y, cout, st.view(r0, 0), gamma, beta, nr, tp, t, cout, groups,
