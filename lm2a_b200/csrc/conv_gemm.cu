@@ -59,8 +59,15 @@ template <int BLOCK_N, int STAGES, int CG>
 struct SmemLayout {
   static constexpr int kBTileBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits B along N
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
+  // epilogue: per warp a [32 rows][32 cols] bf16 staging tile (TMA store source, 64B swizzle)
+  // and a table of per-column (scale, offset) pairs for its BLOCK_N / 2 columns
+  static constexpr int kOutOffset = STAGES * kStageBytes;
+  static constexpr int kOutBytesPerWarp = 32 * 32 * 2;
+  static constexpr int kTabOffset = kOutOffset + kEpiWarps * kOutBytesPerWarp;
+  static constexpr int kTabBytesPerWarp = (BLOCK_N / 2) * 8;
+  static constexpr int kBarOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
   static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
+  static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
 
 // CG = 1: one CTA per 128 x BLOCK_N tile. CG = 2: a CTA pair (cluster of 2) per 256 x BLOCK_N
@@ -70,7 +77,8 @@ template <int BLOCK_N, int STAGES, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const ConvArgs p) {
+                 const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
   using L = SmemLayout<BLOCK_N, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -95,6 +103,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -214,6 +223,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
+    const uint32_t stg_base = smem_base + L::kOutOffset + (warp - 2) * L::kOutBytesPerWarp;
+    const uint32_t tab_base = smem_base + L::kTabOffset + (warp - 2) * L::kTabBytesPerWarp;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
@@ -229,6 +240,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int r_lo = m_first / p.tp;
       const int r_hi = m_first < (int)p.m ? m_last / p.tp : r_lo - 1;
 
+      // per-column (a, b) with out = acc * a + b: bias and the FiLM modulation
+      // (acc + bias) * (1 + scale) + shift folded; built while the MMAs of this tile still run.
+      // (per-row FiLM tables, film_ld != 0, are applied per lane further down)
+      const bool film_tab = p.film != nullptr && p.film_ld == 0;
+      const bool film_row = p.film != nullptr && p.film_ld != 0;
+      {
+        __syncwarp();  // previous tile's table reads are done
+        if (lane * 4 < BLOCK_N / 2) {
+          const int cl = lane * 4;                        // column inside this warp's half
+          const int n = n0 + half * (BLOCK_N / 2) + cl;
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4;
+          if (film_tab) {
+            s4 = __ldg(reinterpret_cast<const float4*>(p.film + n));
+            h4 = __ldg(reinterpret_cast<const float4*>(p.film + p.film_shift_off + n));
+          }
+          const float4 lo = make_float4(1.f + s4.x, fmaf(b4.x, 1.f + s4.x, h4.x), 1.f + s4.y,
+                                        fmaf(b4.y, 1.f + s4.y, h4.y));
+          const float4 hi = make_float4(1.f + s4.z, fmaf(b4.z, 1.f + s4.z, h4.z), 1.f + s4.w,
+                                        fmaf(b4.w, 1.f + s4.w, h4.w));
+          const uint32_t ta = tab_base + (uint32_t)cl * 8u;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(lo.x),
+                       "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(hi.x),
+                       "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+        }
+        __syncwarp();
+      }
+
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
@@ -239,17 +279,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (n >= p.n_valid) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
         float f[32];
+        const uint32_t tcol = tab_base + (uint32_t)(c0 - half * (BLOCK_N / 2)) * 8u;
+        float4 ab[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-          f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-          f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-          f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-          f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        for (int j = 0; j < 16; ++j)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(ab[j].x), "=f"(ab[j].y), "=f"(ab[j].z), "=f"(ab[j].w)
+                       : "r"(tcol + 16u * j));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          f[2 * j] = fmaf(__uint_as_float(v[2 * j]), ab[j].x, ab[j].y);
+          f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), ab[j].z, ab[j].w);
         }
-        if (p.film != nullptr) {
+        if (film_row) {
           const float* sc = p.film + (size_t)r * p.film_ld + n;
           const float* sh = sc + p.film_shift_off;
 #pragma unroll
@@ -323,22 +367,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
         if (p.out_mode == LM2A_OUT_BF16_SLAB) {
-          if (in_range) {
-            uint4* op = reinterpret_cast<uint4*>(
-                reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.out_ld + n);
+          // bf16 -> this warp's [32 slots][32 channels] staging tile (64B swizzle) -> one TMA
+          // store; rows past the slab and channels past n_valid are clipped by the tensor map,
+          // pad slots (t >= t_valid) are written as zeros to keep the conv padding intact
+          if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
+          __syncwarp();
+          const uint32_t srow = stg_base + (uint32_t)lane * 64u;
+          const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              if (valid) {
-                q.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-                q.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-                q.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-                q.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-              } else {
-                q = make_uint4(0u, 0u, 0u, 0u);  // keep the inter-clip zero slots zero
-              }
-              op[j] = q;
+          for (int j = 0; j < 4; ++j) {
+            uint32_t q0 = 0u, q1w = 0u, q2w = 0u, q3 = 0u;
+            if (valid) {
+              q0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+              q1w = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+              q2w = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+              q3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
             }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                             srow + (((uint32_t)j ^ sx) << 4)),
+                         "r"(q0), "r"(q1w), "r"(q2w), "r"(q3)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && m_first < (int)p.m) {
+            tma_store_2d(&tmOut, stg_base, n, m_first);
+            tma_store_commit();
           }
         } else {
           // fp32 [R, n_valid, t_valid]: lanes are consecutive t -> coalesced per channel
@@ -358,6 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       acc ^= 1u;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) tma_store_wait<0>();  // all boxes written before the grid completes
   }
 
   tc_fence_before_sync();
@@ -371,6 +426,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 
 // ------------------------------------------------------------------ host side
 // 2-D bf16 map: inner = channels (box 64 -> 128 B, SWIZZLE_128B), outer = slots / rows.
+// bf16 output slab as seen by the epilogue's TMA stores: [32 channels x 32 slots] boxes, 64B swizzle
+int encode_2d_out(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                  uint64_t pitch_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  LM2A_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult res = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LM2A_REQUIRE(res == CUDA_SUCCESS,
+               "cuTensorMapEncodeTiled (output) failed (%d): base=%p inner=%llu outer=%llu "
+               "pitch=%llu", (int)res, base, (unsigned long long)inner,
+               (unsigned long long)outer, (unsigned long long)pitch_elems);
+  return 0;
+}
+
 int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
               uint64_t pitch_elems, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
@@ -392,7 +466,7 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
 
 template <int BLOCK_N, int STAGES, int CG>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
-           const CUtensorMap& b, const ConvArgs& args) {
+           const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
   using L = SmemLayout<BLOCK_N, STAGES, CG>;
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CG>;
   static bool configured = false;
@@ -405,7 +479,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
   LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kThreads), L::kBytes, stream,
-                                     (unsigned)CG, a0, a1, b, args));
+                                     (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
 }
@@ -581,10 +655,14 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tmOut = tmB;  // unused in the fp32 output mode
+  if (d->out_mode == LM2A_OUT_BF16_SLAB &&
+      encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
+    return 1;
   if (cg == 2) {
-    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, a);
-    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, a);
+    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
+    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
   }
-  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, a);
-  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, a);
+  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
 }
