@@ -27,7 +27,7 @@ namespace {
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
 constexpr int kThreads = 192;  // 4 softmax warps, TMA producer, MMA issuer
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemColsS = 128;  // two 64-column S tiles
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int DH>
@@ -50,8 +50,8 @@ struct AttnSmem {
   static constexpr int kBarOff = kVOff + kVStages * kVBytes;
   static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 1;
   static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
-  // dh = 32 would fit three CTAs per SM by shared memory but only two by TMEM columns:
-  // ask for enough that the third is never scheduled (it would spin in tcgen05.alloc)
+  // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
+  // third is never scheduled
   static constexpr int kBytes = kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded;
 };
 
@@ -116,7 +116,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + b); };
   auto pv_done = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + PB + b); };
   const uint32_t o_full = bar_base + 8u * (3 + 2 * KS + 2 * VS + 2 * PB);
-  const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);
+  const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);  // S, then O (+4 B)
+  // TMEM: two allocations (S: 128 columns, O: DH columns) so that three dh = 32 CTAs fit an SM
+  constexpr uint32_t kTmemColsO = DH < 32 ? 32 : DH;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.z;
@@ -154,18 +156,19 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     mbar_fence_init();
   }
   if (warp == 5) {
-    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_alloc(tmem_slot, kTmemColsS);
+    tmem_alloc(tmem_slot + 4, kTmemColsO);
     tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  uint32_t tmem_base;
+  uint32_t tmem_base, tmem_o;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_o) : "r"(tmem_slot + 4));
   // everything above overlapped the previous kernel's tail; from here on we touch its output
   pdl_wait();
   pdl_launch_dependents();
-  const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 4) {
     // ------------------------------------------------------------- TMA producer
@@ -354,7 +357,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   __syncthreads();
   if (warp == 5) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(tmem_base, kTmemColsS);
+    tmem_dealloc(tmem_o, kTmemColsO);
   }
 }
 
