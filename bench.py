@@ -33,6 +33,20 @@ GW = 2.1
 METRIC = "cfg_sampling_mel_clips_per_sec"
 
 
+def measured_traffic(kind, launches):
+    """DRAM bytes per launch of kernel family `kind`, from the committed ncu capture of one eager
+    step of this workload (profiles/traffic_step.json <- tools/gpu/r20_profiles.sh); None when
+    the capture does not match the launch count of the current plan."""
+    p = os.path.join(ROOT, "profiles", "traffic_step.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f).get(kind)
+    if not d or d.get("launches") != launches:
+        return None
+    return (d["dram_read_bytes"] + d["dram_write_bytes"]) / launches
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -268,7 +282,11 @@ def run_b200(args):
             "finite": finite and e2e_finite,
             "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, "
                          f"{len(conv)} launches/step)", "achieved": achieved, "peak": tf_peak,
-                         "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                         "traffic": measured_traffic("conv_gemm", len(conv)),
+                         "traffic_note": "DRAM read+write bytes per conv launch (mean of the "
+                                         f"{len(conv)} launches of a step), ncu, profiles/traffic_step.json",
+                         "flops_per_launch": conv_flops / max(1, len(conv)),
                          "peak_source": src + " bf16_tflops_sustained",
                          "share_of_step": conv_s / sum(by_kind.values())},
             "kernel_ms": {k: v * 1e3 for k, v in sorted(by_kind.items())},

@@ -76,3 +76,46 @@ def test_forward_full_length_vs_oracle():
     eps = net(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
     err = _rel(eps, ref)
     assert err < TOL_BF16, f"eps rel-L2 {err:.3e}"
+
+
+def test_forward_long_clip_and_mixed_kv_length_vs_oracle():
+    """BASELINE config 5: long clip (4x mel frames: T = 2064) with a K/V length that differs from
+    T (Lk = 720: K/V length != T is legal in the reference, cross_attention.py:46-61) on the
+    default-width net (base 128: 16-channel GroupNorm groups, head dim 32/64/128), per-row t."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = orc.UNetConfig(80, 128, (1, 2, 4), 128, 256, 2, 3, 4)
+    sd = orc.random_state_dict(cfg, 11)
+    net = _model(cfg, sd)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(2, 80, 2064, generator=g)
+    mf = torch.randn(2, 720, 128, generator=g)
+    tf = torch.randn(2, 720, 128, generator=g)
+    t = torch.tensor([999, 3])
+    with torch.no_grad():
+        ref = orc.unet_forward(sd, cfg, x, t, mf, tf)
+    eps = net(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
+    assert torch.isfinite(eps).all()
+    err = _rel(eps, ref)
+    assert err < TOL_BF16, f"long clip eps rel-L2 {err:.3e}"
+
+
+def test_forward_is_batch_position_invariant_to_rounding():
+    """A clip's eps must not depend on which other clips share its batch (clips are independent;
+    multi-GPU sharding relies on it). GroupNorm partial sums are grouped by 32-slot segments of
+    the flattened batch, so the result may differ in the last fp32 bits of the statistics only."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = orc.UNetConfig(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    net = _model(cfg, orc.random_state_dict(cfg, 6))
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn(5, 80, 132, generator=g).cuda()
+    mf = torch.randn(5, 132, 128, generator=g).cuda()
+    tf = torch.randn(5, 132, 128, generator=g).cuda()
+    t = torch.tensor([10, 20, 30, 40, 49]).cuda()
+    full = net(x, t, mf, tf).clone()
+    sub = net(x[3:4].contiguous(), t[3:4].contiguous(), mf[3:4].contiguous(), tf[3:4].contiguous())
+    assert _rel(sub, full[3:4]) < 2e-3
+    perm = torch.tensor([4, 2, 0, 3, 1]).cuda()
+    shuf = net(x[perm].contiguous(), t[perm].contiguous(), mf[perm].contiguous(), tf[perm].contiguous())
+    assert _rel(shuf, full[perm]) < 2e-3
