@@ -7,17 +7,15 @@
 // it away).
 //
 // One CTA = 128 queries of one (clip-row, stream, head); keys are walked in tiles of 64.
-//   warp 8     TMA producer: Q tile once + a ring of K tiles and a ring of V^T tiles (separate
+//   warp 4     TMA producer: Q tile once + a ring of K tiles and a ring of V^T tiles (separate
 //              rings: a K slot is free as soon as S_j is done, a V slot only after P_j V_j)
-//   warp 9     tcgen05.mma issuer (one thread): S_j = Q K_j^T into a double-buffered TMEM
+//   warp 5     tcgen05.mma issuer (one thread): S_j = Q K_j^T into a double-buffered TMEM
 //              tile, O += P_j V_j with P_j read from shared memory; S_{j+1} is issued
 //              before P_j V_j so the tensor pipe works while the softmax warps run
-//   warps 0-7  softmax: warps w and w+4 share the 32 query rows of TMEM lane quadrant w%4 and
-//              take 32 of the 64 key columns each (four softmax warps per SM sub-partition
-//              with two CTAs per SM keep the MUFU pipe busy): tcgen05.ld of S, row max
-//              exchanged through shared memory, lazy rescaling (O in TMEM is only corrected
-//              when the row max grows by more than 2^8), exp2, partial row sums, P -> bf16 ->
-//              128B-swizzled shared tile; finally O / l -> bf16 slab
+//   warps 0-3  softmax: one query row per thread (TMEM lane), tcgen05.ld of S, running
+//              max with lazy rescaling (O in TMEM is only corrected when the row max grows
+//              by more than 2^8), exp2, row sum, P -> bf16 -> 128B-swizzled shared tile;
+//              finally O / l -> bf16 slab
 // TMEM: S[0] cols 0-63, S[1] cols 64-127, O cols 128-(128+dh); 256 columns per CTA, two
 // CTAs per SM for dh <= 64.
 #include "../../include/lm2a_b200.h"
@@ -28,8 +26,7 @@ namespace {
 
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 320;  // 8 softmax warps, TMA producer, MMA issuer
-constexpr int kWarpTma = 8, kWarpMma = 9;
+constexpr int kThreads = 192;  // 4 softmax warps, TMA producer, MMA issuer
 constexpr uint32_t kTmemColsS = 128;  // two 64-column S tiles
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -52,10 +49,7 @@ struct AttnSmem {
   static constexpr int kVOff = kKOff + kKStages * kKBytes;
   static constexpr int kBarOff = kVOff + kVStages * kVBytes;
   static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 1;
-  static constexpr int kXchOff = kBarOff + 8 * kNumBars + 8;  // row-max / row-sum exchange
-  static constexpr int kXchBytes = 2 * kBQ * 2;               // fp16 [2 column halves][128 rows]
-  static constexpr int kNeeded = kXchOff + kXchBytes;
-  static_assert(2 * (kNeeded + 1024) <= 228 * 1024, "two CTAs per SM must fit");
+  static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
   // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
   // third is never scheduled
   static constexpr int kBytes = kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded;
@@ -82,26 +76,6 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
         "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
-        "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      :
-      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
-        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
-        "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
@@ -143,7 +117,6 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   auto pv_done = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + PB + b); };
   const uint32_t o_full = bar_base + 8u * (3 + 2 * KS + 2 * VS + 2 * PB);
   const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);  // S, then O (+4 B)
-  const uint32_t xch_base = smem_base + L::kXchOff;
   // TMEM: two allocations (S: 128 columns, O: DH columns) so that three dh = 32 CTAs fit an SM
   constexpr uint32_t kTmemColsO = DH < 32 ? 32 : DH;
 
@@ -157,7 +130,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   // stay garbage: MMA rows are independent and those O rows are never stored)
   const int valid_warps = min(4, (t_valid - q0 + 31) >> 5);
 
-  if (warp == kWarpTma && lane == 0) {
+  if (warp == 4 && lane == 0) {
     if ((smem_base & 1023u) != 0) {
       printf("lm2a: attention shared memory base not 1024-byte aligned\n");
       __trap();
@@ -176,13 +149,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
     for (int b = 0; b < 2; ++b) mbar_init(s_full(b), 1);
     for (int b = 0; b < PB; ++b) {
-      mbar_init(p_full(b), 64 * valid_warps);
+      mbar_init(p_full(b), 32 * valid_warps);
       mbar_init(pv_done(b), 1);
     }
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
-  if (warp == kWarpMma) {
+  if (warp == 5) {
     tmem_alloc(tmem_slot, kTmemColsS);
     tmem_alloc(tmem_slot + 4, kTmemColsO);
     tmem_relinquish();
@@ -197,7 +170,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == kWarpTma) {
+  if (warp == 4) {
     // ------------------------------------------------------------- TMA producer
     // Q, then K_{j+1} before V_j: a K slot frees when S_{j+1-KS} is done, a V slot when
     // P_{j-VS} V_{j-VS} is done, which happen in this order
@@ -228,7 +201,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tma_load_2d(v_tile(st), vm, j * kBK, slot * e + h * DH, v_full(st));
       }
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == 5) {
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
@@ -269,64 +242,43 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       issue_pv(ntiles - 1);
       umma_commit(o_full);
     }
-  } else if ((warp & 3) < valid_warps) {
+  } else if (warp < valid_warps) {
     // ------------------------------------------------------------------ softmax
-    const int quad = warp & 3;   // TMEM lane quadrant = 32 query rows
-    const int ch = warp >> 2;    // which 32 of the tile's 64 key columns
-    const int row = quad * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int row = warp * 32 + lane;  // TMEM lane == query row of the tile
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     float m_used = -INFINITY, l_run = 0.f;
     const uint32_t p_row = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
-    const uint32_t xch_own = xch_base + (uint32_t)(ch * kBQ + row) * 2u;
-    const uint32_t xch_peer = xch_base + (uint32_t)((ch ^ 1) * kBQ + row) * 2u;
-    // named barriers of the warp pair (w, w + 4): 1 + quad = "both values written" (both warps
-    // sync); 5 + 2 * quad + c = "the peer of column-half c has read" (peer arrives, c syncs)
-    auto pair_sync = [&](int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); };
-    auto pair_arrive = [&](int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); };
 
     for (int j = 0; j < ntiles; ++j) {
       const int b = j & 1, pb = j % PB;
       mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
       tc_fence_after_sync();
-      uint32_t v0[32];
-      tmem_ld_32x32(tmem_base + lane_off + b * kBK + ch * 32, v0);
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
+      tmem_ld_32x32(tmem_base + lane_off + b * kBK + 32, v1);
       tmem_ld_wait();
-      float s[32];
+      float s[64];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) s[c] = __uint_as_float(v0[c]);
-      const int keys = lk - j * kBK - ch * 32;  // valid columns of this warp's half
-      if (keys < 32) {
+      for (int c = 0; c < 32; ++c) {
+        s[c] = __uint_as_float(v0[c]);
+        s[32 + c] = __uint_as_float(v1[c]);
+      }
+      const int keys = lk - j * kBK;
+      if (keys < kBK) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
+        for (int c = 0; c < 64; ++c)
           if (c >= keys) s[c] = -INFINITY;
       }
       float mxa[4] = {s[0], s[1], s[2], s[3]};  // four independent chains
 #pragma unroll
-      for (int c = 4; c < 32; c += 4) {
+      for (int c = 4; c < 64; c += 4) {
         mxa[0] = fmaxf(mxa[0], s[c]);
         mxa[1] = fmaxf(mxa[1], s[c + 1]);
         mxa[2] = fmaxf(mxa[2], s[c + 2]);
         mxa[3] = fmaxf(mxa[3], s[c + 3]);
       }
-      float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
-      // row max over both halves: both warps read the SAME two stored values (fp16, rounded
-      // up so that exp2(s - max) <= 1), hence take identical rescale decisions
-      {
-        if (j > 0) pair_sync(5 + 2 * quad + ch);  // the peer has consumed last tile's value
-        uint16_t hm;
-        asm("cvt.rp.f16.f32 %0, %1;" : "=h"(hm) : "f"(mx));
-        asm volatile("st.shared.b16 [%0], %1;" ::"r"(xch_own), "h"(hm) : "memory");
-        pair_sync(1 + quad);
-        uint16_t ha, hb;
-        asm volatile("ld.shared.b16 %0, [%1];" : "=h"(ha) : "r"(xch_own));
-        asm volatile("ld.shared.b16 %0, [%1];" : "=h"(hb) : "r"(xch_peer));
-        pair_arrive(5 + 2 * quad + (ch ^ 1));
-        float fa, fb;
-        asm("cvt.f32.f16 %0, %1;" : "=f"(fa) : "h"(ha));
-        asm("cvt.f32.f16 %0, %1;" : "=f"(fb) : "h"(hb));
-        mx = fmaxf(fa, fb);
-      }
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
 
       // lazy rescale: keep the stale max while the new one is within 2^8 of it
       const bool grow = mx > m_used + kRescaleThreshold;
@@ -337,26 +289,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         l_run *= corr;
       }
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
-        // each warp of the pair rescales its half of the O columns
         mbar_wait(pv_done((j - 1) % PB), (uint32_t)((j - 1) / PB) & 1u);
         tc_fence_after_sync();
-        if (DH == 32) {
-          uint32_t ov[16];
-          tmem_ld_32x16(tmem_o + lane_off + ch * 16, ov);
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_o + lane_off + c0, ov);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
-          tmem_st_32x16(tmem_o + lane_off + ch * 16, ov);
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < DH / 2; c0 += 32) {
-            uint32_t ov[32];
-            tmem_ld_32x32(tmem_o + lane_off + ch * (DH / 2) + c0, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
-            tmem_st_32x32(tmem_o + lane_off + ch * (DH / 2) + c0, ov);
-          }
+          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
+          tmem_st_32x32(tmem_o + lane_off + c0, ov);
         }
         tmem_st_wait();
       }
@@ -366,7 +308,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       const uint32_t pbase = p_tile(pb) + p_row;
       float suma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 8; ++c) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -375,7 +317,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
           suma[i] += p0 + p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        const uint32_t addr = pbase + (((uint32_t)(ch * 4 + c) ^ sw) << 4);
+        const uint32_t addr = pbase + (((uint32_t)c ^ sw) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]),
                      "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
@@ -386,53 +328,26 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       mbar_arrive(p_full(pb));
     }
 
-    // ---- finalise: row sum of both halves (fp32 through the P tile, which is idle now),
-    //      then O / l -> bf16 slab, each warp of the pair stores half of the d_h columns
+    // ---- finalise: O / l -> bf16 slab
     mbar_wait(o_full, 0);
     tc_fence_after_sync();
-    {
-      const uint32_t lx = p_tile(0) + (uint32_t)(ch * kBQ + row) * 4u;
-      const uint32_t lp = p_tile(0) + (uint32_t)((ch ^ 1) * kBQ + row) * 4u;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(lx), "f"(l_run) : "memory");
-      pair_sync(1 + quad);
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(lp));
-      l_run += other;
-    }
     const float inv = 1.0f / l_run;
     const int t = q0 + row;
-    __nv_bfloat16* op = o + ((size_t)r * tp + t) * o_ld + stream * e + h * DH + ch * (DH / 2);
-    if (DH == 32) {
-      uint32_t ov[16];
-      tmem_ld_32x16(tmem_o + lane_off + ch * 16, ov);
+    __nv_bfloat16* op = o + ((size_t)r * tp + t) * o_ld + stream * e + h * DH;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_off + c0, ov);
       tmem_ld_wait();
       if (t < t_valid) {
 #pragma unroll
-        for (int c = 0; c < 16; c += 8) {
+        for (int c = 0; c < 32; c += 8) {
           uint4 q;
           q.x = pack_bf16x2(__uint_as_float(ov[c + 0]) * inv, __uint_as_float(ov[c + 1]) * inv);
           q.y = pack_bf16x2(__uint_as_float(ov[c + 2]) * inv, __uint_as_float(ov[c + 3]) * inv);
           q.z = pack_bf16x2(__uint_as_float(ov[c + 4]) * inv, __uint_as_float(ov[c + 5]) * inv);
           q.w = pack_bf16x2(__uint_as_float(ov[c + 6]) * inv, __uint_as_float(ov[c + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c) = q;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int c0 = 0; c0 < DH / 2; c0 += 32) {
-        uint32_t ov[32];
-        tmem_ld_32x32(tmem_o + lane_off + ch * (DH / 2) + c0, ov);
-        tmem_ld_wait();
-        if (t < t_valid) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(ov[c + 0]) * inv, __uint_as_float(ov[c + 1]) * inv);
-            q.y = pack_bf16x2(__uint_as_float(ov[c + 2]) * inv, __uint_as_float(ov[c + 3]) * inv);
-            q.z = pack_bf16x2(__uint_as_float(ov[c + 4]) * inv, __uint_as_float(ov[c + 5]) * inv);
-            q.w = pack_bf16x2(__uint_as_float(ov[c + 6]) * inv, __uint_as_float(ov[c + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + c0 + c) = q;
-          }
+          *reinterpret_cast<uint4*>(op + c0 + c) = q;
         }
       }
     }
@@ -440,7 +355,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == kWarpMma) {
+  if (warp == 5) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemColsS);
     tmem_dealloc(tmem_o, kTmemColsO);
