@@ -259,6 +259,9 @@ class UNetPlan:
                 self.vt.append((z(nslots * b.e, self.lk_pad), z(nslots * b.e, self.lk_pad)))
         self.ops = []
         self.kv_ops = []
+        self.use_side_stream = True
+        self._side = None
+        self._side_op = self._side_pending = self._partial_rows = False
         self._build()
 
     # -- helpers -------------------------------------------------------------------------
@@ -266,7 +269,14 @@ class UNetPlan:
         return flat[: m * c].view(m, c)
 
     def _add(self, fn, *args, meta=None):
-        self.ops.append((fn, args, meta or {"kind": fn.__name__, "flops": 0}))
+        meta = meta or {"kind": fn.__name__, "flops": 0}
+        if self._side_op:
+            meta["side"] = True
+            self._side_pending = True
+        elif self._side_pending and not self._partial_rows:
+            meta["join"] = True   # first main op that reads rows written on the side stream
+            self._side_pending = False
+        self.ops.append((fn, args, meta))
 
     def _conv(self, segs, w, bias, n_valid, m, tp, t_valid, *a, **k):
         """Queues one implicit-GEMM launch; meta carries its ALGORITHMIC flops
@@ -288,9 +298,15 @@ class UNetPlan:
         `uncond_rows` rows get `skip(x) + const` (their attention output is Q-independent)."""
         u = self.uncond_rows if (p.attn and self.use_cond) else 0
         if u > 0:
+            # rows [0, u) only need skip(x) + const: one small launch, independent of the cond
+            # rows' pipeline below -> side stream; the block's own main ops touch rows >= u only
+            self._side_op = True
             self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u)
+            self._side_op = False
+            self._partial_rows = True
         self._resblock_rows(p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st, kv,
                             u, self.rows - u)
+        self._partial_rows = False
 
     def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u):
         """Rows whose conditions are all-zero (sample.py:155-157): every key of a stream is the
@@ -476,8 +492,32 @@ class UNetPlan:
         self.kv_slot.copy_(kv_slot.to(torch.int32))
 
     def run(self):
-        for fn, args, _ in self.ops:
+        """Launches the plan on torch's current stream. Ops tagged `side` (the uncond rows'
+        `skip(x) + const` kernels and the timestep / FiLM tables: small launches that nothing
+        on the main chain needs until the tagged `join` op) go to a second stream, forked from
+        and joined back into the current one — under CUDA Graph capture they become a parallel
+        branch, off the critical path of the cond rows' pipeline."""
+        if not self.use_side_stream:
+            for fn, args, _ in self.ops:
+                fn(*args)
+            return self.eps
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        side, pending = self._side, False
+        for fn, args, meta in self.ops:
+            if meta.get("side"):
+                side.wait_stream(main)  # fork after everything enqueued so far
+                with torch.cuda.stream(side):
+                    fn(*args)
+                pending = True
+                continue
+            if pending and meta.get("join"):
+                main.wait_stream(side)
+                pending = False
             fn(*args)
+        if pending:
+            main.wait_stream(side)
         return self.eps
 
     def flops(self):
