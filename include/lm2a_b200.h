@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 3
+#define LM2A_ABI_VERSION 4
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -96,9 +96,28 @@ typedef struct lm2a_conv_desc {
   int32_t stats_gran;     /* channels per sub-block: 8, 16 or 32              */
   int32_t cta_group;      /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA
                              pair (cluster of 2, cta_group::2 UMMA) per 256 rows */
+  /* Optional fused GroupNorm + SiLU of the output (unet1d_ultimate.py:146-147):
+   * gn_out = SiLU(GroupNorm(out)) is written as a second bf16 slab by the same
+   * launch. Every CTA keeps its tiles in TMEM, the partial sums go to `stats`
+   * (required, stats_gran = 32), all CTAs meet at a grid barrier, then the tiles
+   * are normalised straight out of TMEM. `out` may be NULL (raw output not
+   * needed). Needs (n_valid/gn_groups) % 32 == 0, tp >= 32, a uniform FiLM table
+   * (film_ld == 0) and lm2a_conv_gn_fusable(m, n_pad) != 0. gn_barrier: two
+   * zero-initialised uint32 owned by this launch site.                        */
+  const float* gn_gamma;  /* NULL = no fusion                                  */
+  const float* gn_beta;
+  void* gn_out;
+  void* gn_barrier;
+  int32_t gn_out_ld;
+  int32_t gn_groups;
+  float gn_eps;
+  int32_t _pad3;
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);
+/* 1 if an [m, n_pad] output can stay resident in the TMEM accumulators of one
+ * wave of CTAs (precondition of the fused GroupNorm), else 0.                 */
+int lm2a_conv_gn_fusable(int64_t m, int32_t n_pad);
 
 /* ---- GroupNorm + SiLU over a slab -------------------------------------- */
 /* x,y: bf16 slabs [R, tp, ld*]; stats over t < t_valid and c/groups channels */

@@ -24,10 +24,13 @@ class ConvDesc(ctypes.Structure):
                 ("residual", c_void_p), ("res_ld", c_int32), ("out_mode", c_int32),
                 ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32),
                 ("stats", c_void_p), ("stats_sub", c_int32), ("stats_ns", c_int32),
-                ("stats_gran", c_int32), ("cta_group", c_int32)]
+                ("stats_gran", c_int32), ("cta_group", c_int32),
+                ("gn_gamma", c_void_p), ("gn_beta", c_void_p), ("gn_out", c_void_p),
+                ("gn_barrier", c_void_p), ("gn_out_ld", c_int32), ("gn_groups", c_int32),
+                ("gn_eps", c_float), ("_pad3", c_int32)]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -39,6 +42,7 @@ SIGNATURES = {
     "lm2a_launch_count": (c_int64, []),
     "lm2a_reset_launch_count": (None, []),
     "lm2a_conv1d_bf16": (c_int32, [c_void_p, ctypes.POINTER(ConvDesc)]),
+    "lm2a_conv_gn_fusable": (c_int32, [c_int64, c_int32]),
     "lm2a_gn_silu_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_float, c_int32]),

@@ -363,6 +363,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 __device__ __forceinline__ float silu_accurate(float v) { return v / (1.0f + expf(-v)); }
 
+// v * sigmoid(v) with sigmoid(v) = 0.5 + 0.5 tanh(v / 2): one MUFU op instead of two
+__device__ __forceinline__ float silu_tanh(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
+  return v * fmaf(0.5f, t, 0.5f);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

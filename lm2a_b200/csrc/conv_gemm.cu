@@ -53,6 +53,14 @@ struct ConvArgs {
   int stats_sub;     // sub-blocks per clip-row in the stats buffer (= its row pitch)
   int stats_ns;      // slices per (clip-row, sub-block)
   int stats_gran;    // channels per sub-block: 8, 16 or 32
+  // fused GroupNorm + SiLU of the output (see lm2a_conv_desc.gn_*): the CTA keeps its tiles in
+  // TMEM, all CTAs meet at a grid barrier once the partial sums are written, then the tiles
+  // are normalised straight out of TMEM
+  const float* gn_gamma;
+  const float* gn_beta;
+  int gn_groups;
+  float gn_eps;
+  unsigned int* gn_barrier;  // {arrival count, generation}
 };
 
 template <int BLOCK_N, int STAGES, int CG>
@@ -64,7 +72,7 @@ struct SmemLayout {
   static constexpr int kOutOffset = STAGES * kStageBytes;
   static constexpr int kOutBytesPerWarp = 32 * 32 * 2;
   static constexpr int kTabOffset = kOutOffset + kEpiWarps * kOutBytesPerWarp;
-  static constexpr int kTabBytesPerWarp = (BLOCK_N / 2) * 8;
+  static constexpr int kTabBytesPerWarp = 2 * (BLOCK_N / 2) * 8;  // x2: one table per clip-row
   static constexpr int kBarOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
   static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
@@ -78,17 +86,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
+                 const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmOut2, const ConvArgs p) {
   using L = SmemLayout<BLOCK_N, STAGES, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + L::kBarOffset;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem ptr
+  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[4], tempty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 6);
+  // fused GroupNorm: every tile of this CTA keeps its own accumulator (512 / BLOCK_N of them)
+  const bool fuse_gn = p.gn_gamma != nullptr;
+  constexpr int kMaxAcc = 512 / BLOCK_N;
   auto a_tile = [&](int s) { return smem_base + s * L::kStageBytes; };
   auto b_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes; };
 
@@ -104,22 +116,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmOut2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
+    for (int s = 0; s < 4; ++s) mbar_init(tfull_bar(s), 1);
+    for (int s = 0; s < 2; ++s)
       mbar_init(tempty_bar(s), 32 * kEpiWarps * CG);  // pair: the leader collects both CTAs
-    }
     mbar_fence_init();
   }
+  const uint32_t tmem_cols = fuse_gn ? 512u : 2u * BLOCK_N;
   if (warp == 1) {
     if (CG == 2) {
-      tmem_alloc_cg2(tmem_slot, 2 * BLOCK_N);
+      tmem_alloc_cg2(tmem_slot, tmem_cols);
       tmem_relinquish_cg2();
     } else {
-      tmem_alloc(tmem_slot, 2 * BLOCK_N);
+      tmem_alloc(tmem_slot, tmem_cols);
       tmem_relinquish();
     }
   }
@@ -188,8 +201,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after_sync();
+        if (!fuse_gn) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after_sync();
+        }
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
 #pragma unroll 1
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -214,8 +229,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
         if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-        acc ^= 1u;
-        if (acc == 0) acc_phase ^= 1u;
+        if (fuse_gn) {
+          ++acc;  // one accumulator per tile, kept until the normalisation pass
+        } else {
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+        }
       }
     }
   } else {
@@ -225,8 +244,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int row = quad * 32 + lane;
     const uint32_t stg_base = smem_base + L::kOutOffset + (warp - 2) * L::kOutBytesPerWarp;
     const uint32_t tab_base = smem_base + L::kTabOffset + (warp - 2) * L::kTabBytesPerWarp;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    const bool film_tab = p.film != nullptr && p.film_ld == 0;
+    const bool film_row = p.film != nullptr && p.film_ld != 0;
+    constexpr int kHalfN = BLOCK_N / 2;  // columns handled by this warp
+
+    // One output tile. pass 0: out = acc * a + b (bias / FiLM folded per column) + residual,
+    // partial GroupNorm sums, raw output. pass 1 (fused GroupNorm only): the same accumulator
+    // again, now with the per-(clip-row, column) normalisation folded into the table, SiLU, and
+    // the normalised tile goes out through tmOut2.
+    auto run_tile = [&](int tile, uint32_t acc, uint32_t wait_parity, int pass) {
       const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
       const long long m = (long long)m_tile0 + row;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
@@ -243,44 +269,124 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       // per-column (a, b) with out = acc * a + b: bias and the FiLM modulation
       // (acc + bias) * (1 + scale) + shift folded; built while the MMAs of this tile still run.
       // (per-row FiLM tables, film_ld != 0, are applied per lane further down)
-      const bool film_tab = p.film != nullptr && p.film_ld == 0;
-      const bool film_row = p.film != nullptr && p.film_ld != 0;
       {
         __syncwarp();  // previous tile's table reads are done
-        if (lane * 4 < BLOCK_N / 2) {
-          const int cl = lane * 4;                        // column inside this warp's half
-          const int n = n0 + half * (BLOCK_N / 2) + cl;
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+        const int cl = lane * 4;                        // column inside this warp's half
+        const int ncol = n0 + half * kHalfN + cl;
+        if (cl < kHalfN) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ncol));
           float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4;
           if (film_tab) {
-            s4 = __ldg(reinterpret_cast<const float4*>(p.film + n));
-            h4 = __ldg(reinterpret_cast<const float4*>(p.film + p.film_shift_off + n));
+            s4 = __ldg(reinterpret_cast<const float4*>(p.film + ncol));
+            h4 = __ldg(reinterpret_cast<const float4*>(p.film + p.film_shift_off + ncol));
           }
-          const float4 lo = make_float4(1.f + s4.x, fmaf(b4.x, 1.f + s4.x, h4.x), 1.f + s4.y,
-                                        fmaf(b4.y, 1.f + s4.y, h4.y));
-          const float4 hi = make_float4(1.f + s4.z, fmaf(b4.z, 1.f + s4.z, h4.z), 1.f + s4.w,
-                                        fmaf(b4.w, 1.f + s4.w, h4.w));
-          const uint32_t ta = tab_base + (uint32_t)cl * 8u;
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(lo.x),
-                       "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(hi.x),
-                       "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          lo = make_float4(1.f + s4.x, fmaf(b4.x, 1.f + s4.x, h4.x), 1.f + s4.y,
+                           fmaf(b4.y, 1.f + s4.y, h4.y));
+          hi = make_float4(1.f + s4.z, fmaf(b4.z, 1.f + s4.z, h4.z), 1.f + s4.w,
+                           fmaf(b4.w, 1.f + s4.w, h4.w));
+        }
+        if (pass == 0) {
+          if (cl < kHalfN) {
+            const uint32_t ta = tab_base + (uint32_t)cl * 8u;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(lo.x),
+                         "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(hi.x),
+                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+          }
+        } else {
+          // GroupNorm folded in: y = (v - mean) * rstd * gamma + beta with v = acc * a + b
+          //   => A = a * rstd * gamma, B = (b - mean) * rstd * gamma + beta, one table per clip-row
+          const int cg = p.n_valid / p.gn_groups;          // channels per group (multiple of 32)
+          const int spg = cg >> 5;                         // 32-channel sub-blocks per group
+          const int cnt = spg * p.stats_ns;                // partial sums per (clip-row, group)
+          const int g_first = (n0 + half * kHalfN) / cg;
+          const int g_last = (n0 + half * kHalfN + kHalfN - 1) / cg;
+          const double inv_n = 1.0 / ((double)cg * (double)p.t_valid);
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), be4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cl < kHalfN && ncol < p.n_valid) {
+            g4 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + ncol));
+            be4 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + ncol));
+          }
+          const int my_g = ncol / cg;                      // 4 consecutive columns: one group
+          // all partial-sum loads of the (<= 2 clip-rows) x (<= 4 groups) of this warp are issued
+          // before any reduction, so their L2 latency is paid once
+          constexpr int kMaxG = kHalfN / 32;
+          float2 part[2][kMaxG];
+#pragma unroll
+          for (int ci = 0; ci < 2; ++ci) {
+            const int rr = ci == 0 ? r_lo : r_hi;
+            const bool live = r_hi >= r_lo && (ci == 0 || r_hi != r_lo);
+#pragma unroll
+            for (int gi = 0; gi < kMaxG; ++gi) {
+              part[ci][gi] = make_float2(0.f, 0.f);
+              const int g = g_first + gi;
+              if (live && g <= g_last && g < p.gn_groups) {
+                const float2* sp =
+                    p.stats + ((size_t)rr * p.stats_sub + (size_t)g * spg) * p.stats_ns;
+                for (int i = lane; i < cnt; i += 32) {
+                  const float2 v = __ldcg(sp + i);
+                  part[ci][gi].x += v.x;
+                  part[ci][gi].y += v.y;
+                }
+              }
+            }
+          }
+          for (int ci = 0; ci < 2; ++ci) {
+            float mean_c = 0.f, rstd_c = 0.f;
+#pragma unroll
+            for (int gi = 0; gi < kMaxG; ++gi) {
+              const int g = g_first + gi;
+              if (g > g_last) break;  // warp-uniform
+              double sa = (double)part[ci][gi].x, sb = (double)part[ci][gi].y;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+              }
+              const double mean = sa * inv_n;
+              double var = sb * inv_n - mean * mean;
+              var = var > 0.0 ? var : 0.0;
+              if (g == my_g) {
+                mean_c = (float)mean;
+                rstd_c = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+              }
+            }
+            if (cl < kHalfN) {
+              const float ga[4] = {g4.x * rstd_c, g4.y * rstd_c, g4.z * rstd_c, g4.w * rstd_c};
+              const float4 tlo = make_float4(lo.x * ga[0], fmaf(lo.y - mean_c, ga[0], be4.x),
+                                             lo.z * ga[1], fmaf(lo.w - mean_c, ga[1], be4.y));
+              const float4 thi = make_float4(hi.x * ga[2], fmaf(hi.y - mean_c, ga[2], be4.z),
+                                             hi.z * ga[3], fmaf(hi.w - mean_c, ga[3], be4.w));
+              const uint32_t ta = tab_base + (uint32_t)(ci * kHalfN + cl) * 8u;
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(tlo.x),
+                           "f"(tlo.y), "f"(tlo.z), "f"(tlo.w) : "memory");
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(thi.x),
+                           "f"(thi.y), "f"(thi.z), "f"(thi.w) : "memory");
+            }
+          }
         }
         __syncwarp();
       }
+      // pass 1: lanes of the second clip-row of this warp read the second table
+      const uint32_t tab_lane =
+          tab_base + ((pass == 1 && in_range && r != r_lo) ? (uint32_t)kHalfN * 8u : 0u);
 
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after_sync();
+      if (pass == 0) {
+        mbar_wait(tfull_bar(acc), wait_parity);
+        tc_fence_after_sync();
+      }
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
+      const CUtensorMap* tm_out = pass == 0 ? &tmOut : &tmOut2;
 
 #pragma unroll 1
-      for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
+      for (int c0 = half * kHalfN; c0 < (half + 1) * kHalfN; c0 += 32) {
         const int n = n0 + c0;
         if (n >= p.n_valid) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         float f[32];
-        const uint32_t tcol = tab_base + (uint32_t)(c0 - half * (BLOCK_N / 2)) * 8u;
+        const uint32_t tcol = tab_lane + (uint32_t)(c0 - half * kHalfN) * 8u;
         float4 ab[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -293,7 +399,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           f[2 * j] = fmaf(__uint_as_float(v[2 * j]), ab[j].x, ab[j].y);
           f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), ab[j].z, ab[j].w);
         }
-        if (film_row) {
+        if (pass == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = silu_tanh(f[j]);
+        }
+        if (film_row && pass == 0) {
           const float* sc = p.film + (size_t)r * p.film_ld + n;
           const float* sh = sc + p.film_shift_off;
 #pragma unroll
@@ -306,7 +416,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             f[j + 3] = fmaf(f[j + 3], 1.0f + s4.w, h4.w);
           }
         }
-        if (p.residual != nullptr && valid) {
+        if (pass == 0 && p.residual != nullptr && valid) {
           const uint4* rp =
               reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.res_ld + n);
 #pragma unroll
@@ -321,7 +431,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
           }
         }
-        if (p.stats != nullptr) {
+        if (pass == 0 && p.stats != nullptr) {
           // Partial sum / sum of squares of this warp's 32 slots x 32 channels, per clip-row
           // and per `gran`-channel sub-block, written (not accumulated) to a slot that only
           // this warp owns: the consumer (gn_apply) adds the slices in a fixed order, so the
@@ -369,30 +479,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (p.out_mode == LM2A_OUT_BF16_SLAB) {
           // bf16 -> this warp's [32 slots][32 channels] staging tile (64B swizzle) -> one TMA
           // store; rows past the slab and channels past n_valid are clipped by the tensor map,
-          // pad slots (t >= t_valid) are written as zeros to keep the conv padding intact
-          if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
-          __syncwarp();
-          const uint32_t srow = stg_base + (uint32_t)lane * 64u;
-          const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
+          // pad slots (t >= t_valid) are written as zeros to keep the conv padding intact.
+          // (fused GroupNorm with no raw output requested: pass 0 stores nothing)
+          if (pass == 1 || p.out != nullptr) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
+            __syncwarp();
+            const uint32_t srow = stg_base + (uint32_t)lane * 64u;
+            const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t q0 = 0u, q1w = 0u, q2w = 0u, q3 = 0u;
-            if (valid) {
-              q0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-              q1w = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-              q2w = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-              q3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+            for (int j = 0; j < 4; ++j) {
+              uint32_t q0 = 0u, q1w = 0u, q2w = 0u, q3 = 0u;
+              if (valid) {
+                q0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+                q1w = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+                q2w = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+                q3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               srow + (((uint32_t)j ^ sx) << 4)),
+                           "r"(q0), "r"(q1w), "r"(q2w), "r"(q3)
+                           : "memory");
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                             srow + (((uint32_t)j ^ sx) << 4)),
-                         "r"(q0), "r"(q1w), "r"(q2w), "r"(q3)
-                         : "memory");
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && m_first < (int)p.m) {
-            tma_store_2d(&tmOut, stg_base, n, m_first);
-            tma_store_commit();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && m_first < (int)p.m) {
+              tma_store_2d(tm_out, stg_base, n, m_first);
+              tma_store_commit();
+            }
           }
         } else {
           // fp32 [R, n_valid, t_valid]: lanes are consecutive t -> coalesced per channel
@@ -406,11 +519,50 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
       }
-      tc_fence_before_sync();
-      if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-      else mbar_arrive(tempty_bar(acc));
-      acc ^= 1u;
-      if (acc == 0) acc_phase ^= 1u;
+    };
+
+    if (!fuse_gn) {
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        run_tile(tile, acc, acc_phase, 0);
+        tc_fence_before_sync();
+        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+        else mbar_arrive(tempty_bar(acc));
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else {
+      // pass 0 over this CTA's tiles (their accumulators stay in TMEM), grid barrier once the
+      // partial GroupNorm sums of every CTA are in global memory, then the normalising pass
+      uint32_t ord = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) run_tile(tile, ord++, 0, 0);
+      __threadfence();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      if (warp == 2 && lane == 0) {
+        volatile unsigned int* cnt = p.gn_barrier;
+        volatile unsigned int* gen = p.gn_barrier + 1;
+        const unsigned int g0 = *gen;
+        __threadfence();
+        if (atomicAdd(p.gn_barrier, 1u) == gridDim.x - 1) {
+          *cnt = 0u;
+          __threadfence();
+          atomicAdd(p.gn_barrier + 1, 1u);
+        } else {
+          const uint64_t t0 = global_timer_ns();
+          unsigned int spins = 0;
+          while (*gen == g0) {
+            if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+              printf("lm2a: conv grid barrier timeout (block %d)\n", (int)blockIdx.x);
+              __trap();
+            }
+          }
+        }
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      tc_fence_after_sync();
+      ord = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) run_tile(tile, ord++, 0, 1);
     }
     if (lane == 0) tma_store_wait<0>();  // all boxes written before the grid completes
   }
@@ -419,8 +571,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    if (CG == 2) tmem_dealloc_cg2(tmem_base, 2 * BLOCK_N);
-    else tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -466,7 +618,8 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
 
 template <int BLOCK_N, int STAGES, int CG>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
-           const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
+           const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& o2,
+           const ConvArgs& args) {
   using L = SmemLayout<BLOCK_N, STAGES, CG>;
   auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CG>;
   static bool configured = false;
@@ -479,7 +632,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
   LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kThreads), L::kBytes, stream,
-                                     (unsigned)CG, a0, a1, b, o, args));
+                                     (unsigned)CG, a0, a1, b, o, o2, args));
   count_launch();
   return 0;
 }
@@ -491,9 +644,12 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
 struct TileChoice {
   int block_n, cg;
 };
-TileChoice choose_tile(long long m, int n_pad) {
+// max_tiles_per_unit > 0 restricts the choice to shapes where no CTA (pair) gets more tiles than
+// it has TMEM accumulators (512 / block_n): the fused GroupNorm keeps every tile resident.
+// Returns block_n = 0 when nothing fits.
+TileChoice choose_tile(long long m, int n_pad, bool keep_tiles_in_tmem = false) {
   const long long sms = num_sms();
-  TileChoice best{128, 1};
+  TileChoice best{keep_tiles_in_tmem ? 0 : 128, 1};
   long long best_cost = -1;
   const int bns[2] = {256, 128};
   for (int cg = 2; cg >= 1; --cg) {
@@ -503,6 +659,7 @@ TileChoice choose_tile(long long m, int n_pad) {
       const long long tiles = ((m + 128 * cg - 1) / (128 * cg)) * (n_pad / bn);
       const long long units = sms / cg;
       const long long waves = (tiles + units - 1) / units;
+      if (keep_tiles_in_tmem && waves > 512 / bn) continue;
       const long long per_kb = cg == 2 ? (bn == 256 ? 512 : 384) : (bn == 256 ? 768 : 512);
       const long long cost = waves * per_kb;
       if (best_cost < 0 || cost < best_cost) {
@@ -521,7 +678,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   using namespace lm2a;
   LM2A_REQUIRE(d != nullptr, "conv1d: null descriptor");
   LM2A_REQUIRE(d->seg[0].x != nullptr && d->w != nullptr && d->bias != nullptr &&
-                   d->out != nullptr,
+                   (d->out != nullptr || d->gn_gamma != nullptr),
                "conv1d: null x / w / bias / out pointer");
   LM2A_REQUIRE(d->m > 0 && d->tp > 0 && d->t_valid > 0 && d->t_valid <= d->tp &&
                    d->m % d->tp == 0,
@@ -574,7 +731,31 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     }
     k_total += ntaps * g.cin;
   }
+  const bool fuse_gn = d->gn_gamma != nullptr;
+  if (fuse_gn) {
+    LM2A_REQUIRE(d->gn_beta != nullptr && d->gn_out != nullptr && d->gn_barrier != nullptr &&
+                     d->stats != nullptr && d->stats_gran == 32,
+                 "conv1d: fused GroupNorm needs gn_beta, gn_out, gn_barrier and 32-channel stats");
+    LM2A_REQUIRE(d->out_mode == LM2A_OUT_BF16_SLAB && d->gn_groups > 0 &&
+                     d->n_valid % d->gn_groups == 0 && (d->n_valid / d->gn_groups) % 32 == 0 &&
+                     d->tp >= 32 && (d->film == nullptr || d->film_ld == 0),
+                 "conv1d: fused GroupNorm needs >= 32-channel groups, tp >= 32 and a uniform "
+                 "FiLM table (n=%d groups=%d tp=%d film_ld=%d)", d->n_valid, d->gn_groups,
+                 d->tp, d->film_ld);
+    LM2A_REQUIRE(d->gn_out_ld % 8 == 0 && d->gn_out_ld >= d->n_valid &&
+                     ((reinterpret_cast<uintptr_t>(d->gn_out) |
+                       reinterpret_cast<uintptr_t>(d->gn_gamma) |
+                       reinterpret_cast<uintptr_t>(d->gn_beta)) & 15) == 0,
+                 "conv1d: gn_out / gn_gamma / gn_beta alignment");
+  }
   int block_n = d->block_n, cg = d->cta_group;
+  if (fuse_gn && (block_n == 0 || cg == 0)) {
+    const TileChoice c = choose_tile(d->m, d->n_pad, true);
+    LM2A_REQUIRE(c.block_n != 0, "conv1d: fused GroupNorm: %lld x %d output does not fit the "
+                 "chip's TMEM accumulators (see lm2a_conv_gn_fusable)", (long long)d->m, d->n_pad);
+    block_n = c.block_n;
+    cg = c.cg;
+  }
   if (cg == 0) {
     // LM2A_CONV_CG=1|2 pins the auto choice (A/B measurements); unset = wave model
     static const int forced = [] {
@@ -647,7 +828,8 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
                  d->stats_gran, d->stats_sub, d->stats_ns, d->tp / 32 + 2);
   }
   if (d->out_mode == LM2A_OUT_BF16_SLAB) {
-    LM2A_REQUIRE(d->out_ld % 8 == 0 && d->out_ld >= d->n_valid && d->n_valid % 32 == 0,
+    LM2A_REQUIRE((d->out == nullptr || (d->out_ld % 8 == 0 && d->out_ld >= d->n_valid)) &&
+                     d->n_valid % 32 == 0,
                  "conv1d: bf16 slab output needs ld %% 8 == 0 and n_valid %% 32 == 0 (ld=%d n=%d)",
                  d->out_ld, d->n_valid);
   } else {
@@ -655,14 +837,34 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tmOut = tmB;  // unused in the fp32 output mode
-  if (d->out_mode == LM2A_OUT_BF16_SLAB &&
+  CUtensorMap tmOut = tmB, tmOut2 = tmB;  // unused in the fp32 output mode / without fusion
+  if (d->out_mode == LM2A_OUT_BF16_SLAB && d->out != nullptr &&
       encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
     return 1;
-  if (cg == 2) {
-    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
-    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  a.gn_gamma = d->gn_gamma;
+  a.gn_beta = d->gn_beta;
+  a.gn_groups = d->gn_groups;
+  a.gn_eps = d->gn_eps;
+  a.gn_barrier = reinterpret_cast<unsigned int*>(d->gn_barrier);
+  if (fuse_gn) {
+    const long long tiles = (long long)a.m_tiles * a.n_tiles;
+    const long long units = num_sms() / cg;
+    LM2A_REQUIRE((tiles + units - 1) / units <= 512 / block_n,
+                 "conv1d: fused GroupNorm: %lld tiles over %lld CTA%s exceed the %d TMEM "
+                 "accumulators", tiles, units, cg == 2 ? " pairs" : "s", 512 / block_n);
+    if (encode_2d_out(&tmOut2, d->gn_out, (uint64_t)d->n_valid, (uint64_t)d->m,
+                      (uint64_t)d->gn_out_ld))
+      return 1;
   }
-  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
-  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  if (cg == 2) {
+    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+  }
+  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+}
+
+extern "C" int lm2a_conv_gn_fusable(int64_t m, int32_t n_pad) {
+  if (m <= 0 || n_pad <= 0 || n_pad % 128 != 0) return 0;
+  return lm2a::choose_tile(m, n_pad, true).block_n != 0 ? 1 : 0;
 }

@@ -131,13 +131,6 @@ gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __r
 // clip-row, all channels; every thread owns one 8-channel vector column (4 slots of it).
 constexpr int kApplyVec = 4;  // 16-byte vectors per thread and pass
 
-__device__ __forceinline__ float silu_tanh(float v) {
-  // v * sigmoid(v) with sigmoid(v) = 0.5 + 0.5 tanh(v / 2): one MUFU op instead of two
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
-  return v * fmaf(0.5f, t, 0.5f);
-}
-
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
                 int y_ld, const float2* __restrict__ stats, int stats_sub, int stats_ns,

@@ -13,6 +13,7 @@ the conv padding, and Tp_l = 2 Tp_{l+1} makes the stride-2 conv a plain 4-tap GE
 slot *pairs* of the flattened slab.
 """
 import math
+import os
 
 import torch
 
@@ -209,7 +210,7 @@ class UNetPlan:
     (CFG: copies=2, rows = 2B, row k*B+b reads clip b)."""
 
     def __init__(self, pm, rows, t, lk, nslots, copies, use_cond, dev, uniform_t=False,
-                 uncond_rows=0):
+                 uncond_rows=0, fuse_gn=True):
         self.pm, self.rows, self.t, self.lk, self.nslots = pm, rows, t, lk, nslots
         # uniform_t: every clip-row is at the same timestep (sampling) -> one FiLM table row
         self.uniform_t = uniform_t
@@ -260,6 +261,7 @@ class UNetPlan:
         self.ops = []
         self.kv_ops = []
         self.use_side_stream = True
+        self.fuse_gn = fuse_gn and os.environ.get("LM2A_FUSE_GN", "1") != "0"
         self._side = None
         self._side_op = self._side_pending = self._partial_rows = False
         self._build()
@@ -339,11 +341,24 @@ class UNetPlan:
                   tv, cin, groups, eps, True, xo, 0, meta={"kind": "gn_apply", "flops": 0})
         gm, bt, groups, eps = p.gn2
         h1_st = self._stats(nr, lvl, cout, groups)
-        self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
-                   film=self.film, film_col=p.film_col, film_shift_off=cout,
-                   film_bcast=self.uniform_t, film_row=r0, stats=h1_st)
-        self._add(ops.gn_apply, h1, cout, norm2, cout, h1_st, gm, bt, nr, tp, tv, cout, groups,
-                  eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
+        # gn2 + SiLU fused into conv1: the tiles stay in TMEM across a grid barrier and are
+        # normalised from there (no h1 round trip, no separate launch). Needs one FiLM row for
+        # all clips (sampling), >= 32-channel groups and an output that fits one wave's TMEM.
+        n_pad1 = p.w1.shape[0]
+        fuse = (self.fuse_gn and self.uniform_t and (cout // groups) % 32 == 0 and tp >= 32
+                and h1_st.gran == 32 and ops.conv_gn_fusable(m, n_pad1))
+        if fuse:
+            barrier = torch.zeros(2, dtype=torch.int32, device=self.dev)
+            self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, None, cout,
+                       film=self.film, film_col=p.film_col, film_shift_off=cout,
+                       film_bcast=True, film_row=r0, stats=h1_st,
+                       gn=(gm, bt, groups, eps, norm2, cout, barrier))
+        else:
+            self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
+                       film=self.film, film_col=p.film_col, film_shift_off=cout,
+                       film_bcast=self.uniform_t, film_row=r0, stats=h1_st)
+            self._add(ops.gn_apply, h1, cout, norm2, cout, h1_st, gm, bt, nr, tp, tv, cout, groups,
+                      eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
         skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xo)] if p.has_skip else []
         res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xo)
         ost = out_st.view(r0, out_off)

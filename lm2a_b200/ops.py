@@ -70,7 +70,8 @@ class Seg:
 def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan_off=0,
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
-                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0):
+                   res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0,
+                   gn=None):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object."""
     d = ConvDesc()
@@ -95,15 +96,26 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
         d.residual = residual.data_ptr() + res_chan_off * 2
         d.res_ld = res_ld
     d.out_mode = out_mode
-    d.out = out.data_ptr() + out_chan_off * out.element_size()
+    if out is not None:
+        d.out = out.data_ptr() + out_chan_off * out.element_size()
     d.out_ld = out_ld
     d.block_n = block_n
     d.cta_group = cta_group
     if stats is not None:  # Stats view: partial GroupNorm sums of the output
         d.stats = stats.ptr()
         d.stats_sub, d.stats_ns, d.stats_gran = stats.sub, stats.ns, stats.gran
-    d._keep = (segs, w, bias, film, residual, out, stats)
+    if gn is not None:  # (gamma, beta, groups, eps, gn_out slab, gn_out_ld, barrier words)
+        gamma, beta, groups, eps, gn_out, gn_out_ld, barrier = gn
+        d.gn_gamma, d.gn_beta = gamma.data_ptr(), beta.data_ptr()
+        d.gn_groups, d.gn_eps = groups, eps
+        d.gn_out, d.gn_out_ld = gn_out.data_ptr(), gn_out_ld
+        d.gn_barrier = barrier.data_ptr()
+    d._keep = (segs, w, bias, film, residual, out, stats, gn)
     return d
+
+
+def conv_gn_fusable(m, n_pad):
+    return bool(_lib.load().lm2a_conv_gn_fusable(m, n_pad))
 
 
 def conv1d(desc):

@@ -244,6 +244,49 @@ def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0, cta_grou
     assert torch.equal(before, st.buf)
 
 
+@pytest.mark.parametrize("block_n,cta_group", [(0, 0), (256, 1), (256, 2), (128, 1), (128, 2)])
+@pytest.mark.parametrize("r,t,tp,cin,cout,groups,film", [
+    (4, 516, 520, 256, 256, 8, True),      # level 0 shape, few tiles
+    (64, 516, 520, 256, 256, 8, True),     # production level 0 conv1: 260 tiles, two per CTA
+    (32, 64, 65, 1024, 1024, 8, True),     # production mid level: 128-channel groups
+    (5, 129, 130, 128, 512, 8, False),     # 64-channel groups, no FiLM, clip straddles warps
+])
+def test_conv_fused_groupnorm(ops, r, t, tp, cin, cout, groups, film, block_n, cta_group):
+    """conv1 + FiLM + GroupNorm + SiLU in one launch (tiles resident in TMEM across a grid
+    barrier) == F.conv1d -> FiLM -> F.group_norm -> SiLU (unet1d_ultimate.py:138-147)."""
+    m, n_pad = r * tp, (cout + 127) // 128 * 128
+    if block_n:
+        tiles = -(-m // (128 * cta_group)) * (n_pad // block_n)
+        if -(-tiles // (148 // cta_group)) > 512 // block_n:
+            pytest.skip("shape does not fit the TMEM accumulators with this tile")
+    else:
+        assert ops.conv_gn_fusable(m, n_pad)
+    x = rnd(r, cin, t, seed=70)
+    w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=71)
+    b = rnd(cout, scale=0.3, seed=72)
+    gamma = 1 + 0.1 * rnd(cout, seed=73)
+    beta = 0.1 * rnd(cout, seed=74)
+    ftab = rnd(1, 2 * cout, scale=0.3, seed=75) if film else None
+    xs = to_slab(x, tp)
+    st = ops.Stats(r, tp, cout, 32, "cuda")
+    y = torch.full((m, cout), 3.0, dtype=BF16, device="cuda")
+    barrier = torch.zeros(2, dtype=torch.int32, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, m)], pack_w(w), pad_bias(b, n_pad), cout,
+                           m, tp, t, None, cout, film=ftab, film_col=0, film_shift_off=cout,
+                           film_bcast=True, stats=st, block_n=block_n, cta_group=cta_group,
+                           gn=(gamma, beta, groups, 1e-5, y, cout, barrier))
+    for _ in range(2):  # twice: the grid barrier must be reusable
+        ops.conv1d(d)
+    torch.cuda.synchronize()
+    h = F.conv1d(bf(x), bf(w), b, padding=1)
+    if film:
+        h = h * (1 + ftab[:, :cout, None]) + ftab[:, cout:, None]
+    ref = F.silu(F.group_norm(h, groups, gamma, beta, 1e-5))
+    assert_close(from_slab(y, r, tp, t, cout), ref, 6e-3, "conv + fused GroupNorm")
+    assert pads_are_zero(y, r, tp, t)
+    assert int(barrier[0]) == 0 and int(barrier[1]) == 2
+
+
 @pytest.mark.parametrize("r,t,tp,c,groups,gran", [(3, 129, 130, 512, 8, 32), (33, 64, 65, 1024, 8, 32),
                                                   (5, 9, 10, 64, 8, 8), (4, 516, 520, 256, 8, 32)])
 def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
