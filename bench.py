@@ -136,6 +136,31 @@ def cpu_reference_step(orc, torch, steps, warmup):
     return sum(times[warmup:]) / steps
 
 
+def torch_eager_gpu_step(orc, torch, dev, batch, steps, warmup, autocast):
+    """Same-box GPU baseline: the oracle restatement of the reference's loop body
+    run as PyTorch eager on the B200 (cuDNN / cuBLAS / ATen: the library path the reference
+    dispatches to), `batch` clips per step, fp32 (TF32 convs as PyTorch defaults) or bf16
+    autocast. CUDA-event timed; returns seconds per step."""
+    cfg = orc.UNetConfig.production()
+    sd = {k: v.to(dev) for k, v in orc.random_state_dict(cfg, 5).items()}
+    g = torch.Generator().manual_seed(43)
+    mf = torch.randn(batch, T_MEL, 128, generator=g).to(dev)
+    tf = torch.randn(batch, T_MEL, 128, generator=g).to(dev)
+    x = torch.randn(batch, 80, T_MEL, generator=g).to(dev)
+    tables = orc.diffusion_tables(TRAJ_STEPS, dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        for i in range(warmup + steps):
+            if i == warmup:
+                e0.record()
+            t = TRAJ_STEPS - 1 - i
+            eps = orc.cfg_step_eps(sd, cfg, x, t, mf, tf, GW)
+            x = orc.posterior_step(x, eps.float(), t, tables, torch.randn_like(x))
+        e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) * 1e-3 / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -301,6 +326,18 @@ def run_b200(args):
             "clocks": clk,
         }
         if world == 1 and not args.no_cpu:
+            try:
+                eb = 8
+                s32 = torch_eager_gpu_step(orc, torch, dev, eb, 5, 2, False)
+                s16 = torch_eager_gpu_step(orc, torch, dev, eb, 5, 2, True)
+                line["torch_eager_gpu_baseline"] = {
+                    "fp32_clips_per_s": eb / (TRAJ_STEPS * s32), "fp32_ms_per_step": s32 * 1e3,
+                    "bf16_autocast_clips_per_s": eb / (TRAJ_STEPS * s16),
+                    "bf16_autocast_ms_per_step": s16 * 1e3, "batch": eb,
+                    "what": "oracle restatement of sample.py:144-210 as PyTorch eager on this B200 "
+                            "(cuDNN/cuBLAS/ATen, K/V recomputed every step as the reference does)"}
+            except Exception as exc:  # a baseline, never a reason to lose the bench line
+                line["torch_eager_gpu_baseline"] = {"error": repr(exc)[:200]}
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             n = 20

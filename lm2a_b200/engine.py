@@ -123,7 +123,6 @@ def pack_block(blk, heads, dev, film_col):
             raise RuntimeError(f"attention head dim {e}/{heads} unsupported on the sm_100a path "
                                "(needs 32, 64 or 128)")
         p.e, p.heads = e, heads
-        p.w2, p.b2 = _finish(w2, b2, dev)
         qs = LOG2E / math.sqrt(e // heads)
         wq, bq, wkv, bkv, wo, bo = [], [], [], [], [], []
         for mha, kvp in ((ca.attn_motion, ca.motion_kv_proj), (ca.attn_text, ca.text_kv_proj)):
@@ -137,7 +136,10 @@ def pack_block(blk, heads, dev, film_col):
             bkv.append(torch.cat([wk @ bp_ + ipb[e:2 * e], wv @ bp_ + ipb[2 * e:]], dim=0))
             wo.append(_f64(mha.out_proj.weight))
             bo.append(_f64(mha.out_proj.bias))
-        p.wq, p.bq = _finish(torch.cat(wq, dim=0), torch.cat(bq, dim=0), dev)
+        # conv2 -> Q in-projection composed (h2 is only ever the attention query: the attention
+        # output replaces it, unet1d_ultimate.py:152-159): q = Wq (W2 * n + b2) + bq
+        wq_all, bq_all = torch.cat(wq, dim=0), torch.cat(bq, dim=0)
+        p.wq2, p.bq2 = _finish(wq_all @ w2, wq_all @ b2 + bq_all, dev)
         p.wkv_m, p.bkv_m = _finish(wkv[0], bkv[0], dev)
         p.wkv_t, p.bkv_t = _finish(wkv[1], bkv[1], dev)
         wf, bf = _f64(ca.fuse_proj.weight), _f64(ca.fuse_proj.bias)
@@ -241,8 +243,8 @@ class UNetPlan:
                 width = max(width, pm.dims[min(lvl + 1, n_down - 1)])  # upsampled input
             cmax = max(cmax, g.M[lvl] * max(width, pm.base))
         flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
-        self._norm, self._h1, self._norm2, self._h2, self._q, self._o, self._xup = (
-            flat(), flat(), flat(), flat(), flat(), flat(), flat())
+        self._norm, self._h1, self._norm2, self._q, self._o, self._xup = (
+            flat(), flat(), flat(), flat(), flat(), flat())
         self._pp = [flat(), flat()]  # block outputs ping-pong
         self.x_slab = z(g.M[0], pm.in_pad)
         self.cat = [z(g.M[lvl], 2 * pm.dims[lvl]) for lvl in range(n_down)]
@@ -367,12 +369,10 @@ class UNetPlan:
                        tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
             return
         e = p.e
-        h2 = self._view(self._h2, m, cout)
         q = self._view(self._q, m, 2 * e)
         o = self._view(self._o, m, 2 * e)
         (kv_m, kv_t), (vt_m, vt_t) = kv
-        self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.w2, p.b2, cout, m, tp, tv, h2, cout)
-        self._conv([Seg(h2, cout, cout, TAPS_K1, m)], p.wq, p.bq, 2 * e, m, tp, tv, q, 2 * e)
+        self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2, p.bq2, 2 * e, m, tp, tv, q, 2 * e)
         self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
                   ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad, ops._ptr(self.kv_slot, r0),
                   self.nslots, nr, tp, tv, self.lk, e, p.heads,

@@ -72,12 +72,13 @@ def test_geometry_and_plan():
     pm = PackedModel(net, torch.device("cpu"))
     plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
     kinds = [m["kind"] for _, _, m in plan.ops]
-    assert kinds.count("conv_gemm") == 56 and kinds.count("gn_apply") == 31
+    assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 31
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
-    # K/V hoisted + out_proj.fuse folded: production net = 28.23 GFLOP per row-step at T=516
+    # K/V hoisted, out_proj.fuse folded, conv2 o q-proj composed (costs 1.35 GF of executed
+    # work, saves a launch per attention block): production net = 29.58 GFLOP per row-step
     big = PackedModel(UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8), torch.device("cpu"))
     gf = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu")).flops() / 2 / 1e9
-    assert abs(gf - 28.23) < 0.02
+    assert abs(gf - 29.58) < 0.02
     with pytest.raises(RuntimeError, match="multiples of 64"):
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 
