@@ -141,7 +141,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  // everything above overlapped the previous kernel's tail; from here on we touch its output
+  // Everything above overlapped the previous kernel's tail. The weights are never written by
+  // a kernel, so the producer also starts the W boxes of the first pipeline stages before
+  // waiting for the previous kernel (their HBM latency hides under its tail); activations
+  // (A boxes, residual, FiLM table) are only touched after griddepcontrol.wait.
+  int w_prefetched = 0;
+  if (warp == 0 && lane == 0 && unit < total_tiles) {
+    const int n0 = (unit % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
+    w_prefetched = p.num_kb < STAGES ? p.num_kb : STAGES;
+    for (int kb = 0; kb < w_prefetched; ++kb) {
+      if (CG == 2) {
+        if (cta_rank == 0) mbar_expect_tx(full_bar(kb), 2 * L::kStageBytes);
+        tma_load_2d_cg2(b_tile(kb), &tmB, kb * kBlockK, n0, mapa_shared(full_bar(kb), 0));
+      } else {
+        mbar_expect_tx(full_bar(kb), L::kStageBytes);
+        tma_load_2d(b_tile(kb), &tmB, kb * kBlockK, n0, full_bar(kb));
+      }
+    }
+  }
   pdl_wait();
   pdl_launch_dependents();
 
@@ -173,18 +190,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
 #pragma unroll 1
             for (int cb = 0; cb < cblk; ++cb, ++kb) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
+              // first tile: the W box of the first stages is already in flight (see above)
+              const bool w_done = tile == unit && kb < w_prefetched;
+              if (!w_done) mbar_wait(empty_bar(stage), phase ^ 1u);
               if (CG == 2) {
                 // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
                 const uint32_t fb = mapa_shared(full_bar(stage), 0);
-                if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
+                if (cta_rank == 0 && !w_done) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
                 tma_load_2d_cg2(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift, fb);
-                tma_load_2d_cg2(b_tile(stage), &tmB, kb * kBlockK, n0, fb);
+                if (!w_done) tma_load_2d_cg2(b_tile(stage), &tmB, kb * kBlockK, n0, fb);
               } else {
-                mbar_expect_tx(full_bar(stage), L::kStageBytes);
+                if (!w_done) mbar_expect_tx(full_bar(stage), L::kStageBytes);
                 tma_load_2d(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift,
                             full_bar(stage));
-                tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
+                if (!w_done) tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
               }
               if (++stage == STAGES) {
                 stage = 0;
