@@ -76,6 +76,9 @@ struct SmemLayout {
   static constexpr int kBarOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
   static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
+  // fused GroupNorm pass 1 stages every output box of the CTA in the (then idle) pipeline area
+  static_assert(kEpiWarps * (512 / BLOCK_N) * (BLOCK_N / 2 / 32) * kOutBytesPerWarp <=
+                    STAGES * kStageBytes, "pass-1 staging must fit the operand pipeline");
 };
 
 // CG = 1: one CTA per 128 x BLOCK_N tile. CG = 2: a CTA pair (cluster of 2) per 256 x BLOCK_N
@@ -271,6 +274,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // partial GroupNorm sums, raw output. pass 1 (fused GroupNorm only): the same accumulator
     // again, now with the per-(clip-row, column) normalisation folded into the table, SiLU, and
     // the normalised tile goes out through tmOut2.
+    uint32_t box_ord = 0;  // pass 1: running index of this warp's output boxes
     auto run_tile = [&](int tile, uint32_t acc, uint32_t wait_parity, int pass) {
       const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
       const long long m = (long long)m_tile0 + row;
@@ -501,9 +505,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           // pad slots (t >= t_valid) are written as zeros to keep the conv padding intact.
           // (fused GroupNorm with no raw output requested: pass 0 stores nothing)
           if (pass == 1 || p.out != nullptr) {
-            if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the staging tile
-            __syncwarp();
-            const uint32_t srow = stg_base + (uint32_t)lane * 64u;
+            // pass 1 runs after every MMA of the CTA (pair): the operand pipeline's shared
+            // memory is idle, so each box gets a staging tile of its own there and no store
+            // waits for the previous one; pass 0 reuses this warp's single staging tile
+            uint32_t stg = stg_base;
+            if (pass == 1) {
+              stg = smem_base + ((uint32_t)((warp - 2) * kMaxAcc * (kHalfN / 32)) + box_ord) *
+                                    (uint32_t)L::kOutBytesPerWarp;
+              ++box_ord;
+            } else {
+              if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the tile
+              __syncwarp();
+            }
+            const uint32_t srow = stg + (uint32_t)lane * 64u;
             const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -522,7 +536,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && m_first < (int)p.m) {
-              tma_store_2d(tm_out, stg_base, n, m_first);
+              tma_store_2d(tm_out, stg, n, m_first);
               tma_store_commit();
             }
           }
