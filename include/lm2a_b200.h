@@ -24,7 +24,8 @@
  *                      146-147,362-363
  *   lm2a_cross_attn_bf16  softmax(q k^T) v core of nn.MultiheadAttention as used
  *                      at models/cross_attention.py:50-61
- *   lm2a_time_mlp / lm2a_film   models/embedding.py:19-43, unet1d_ultimate.py:43-65
+ *   lm2a_time_mlp / lm2a_time_embed / lm2a_film   models/embedding.py:19-43,
+ *                      unet1d_ultimate.py:43-65; legacy models/unet1d.py:23,48-49
  *   lm2a_upsample2x_bf16  F.interpolate(linear, align_corners=True) :231-236
  *   lm2a_ingest_x      torch.cat([x, x]) + layout change, sample.py:162
  *   lm2a_cfg_posterior sample.py:167-174 (CFG blend + clamps) and
@@ -39,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 4
+#define LM2A_ABI_VERSION 5
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -129,7 +130,7 @@ int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
 /* GroupNorm + SiLU as one streaming pass over a slab whose partial sums were
  * produced by the kernel that wrote it (lm2a_conv_desc.stats / lm2a_bias_add_bf16):
  * adds the slices in a fixed order (fp64), y = SiLU((x - mean) * rstd * gamma + beta).
- * c/8 must divide 256 or be a multiple of it; (c/groups) % stats_gran == 0.   */
+ * c % 8 == 0; (c/groups) % stats_gran == 0.                                  */
 int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                        int32_t y_ld, const void* stats, int32_t stats_sub,
                        int32_t stats_ns, int32_t stats_gran, const float* gamma,
@@ -142,7 +143,7 @@ int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
  * q is pre-scaled by log2(e)/sqrt(dh). k_s: bf16 [slots*lk, k_ld] (first e
  * channels used); vt_s: bf16 V^T [slots*e, vt_ld] (first lk keys of each row
  * used, vt_ld >= lk, multiple of 8). kv_slot[r] selects the cache slot of
- * clip-row r. dh = e/heads must be 32, 64 or 128.                           */
+ * clip-row r. dh = e/heads must be 32, 64, 96, 128, 192, 256 or 384.          */
 int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
                          int32_t o_ld, const void* k_motion,
                          const void* vt_motion, const void* k_text,
@@ -161,6 +162,13 @@ int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src_ld,
  * FiLM net is folded in); dim must be 256-thread friendly (<= 1024, even).  */
 int lm2a_time_mlp(void* stream, const int64_t* t, const float* w,
                   const float* b, float* silu_temb, int32_t rows, int32_t dim);
+/* out[r,:] = SiLU(W sinus(t[r]) + b), i.e. TimestepEmbedding.forward itself
+ * (models/embedding.py:33-43), with fold_silu != 0 one more SiLU on top (what
+ * lm2a_time_mlp computes). fold_silu == 0 feeds the legacy UNet1D's additive
+ * time_proj (models/unet1d.py:23,48-49), which has no SiLU of its own.        */
+int lm2a_time_embed(void* stream, const int64_t* t, const float* w,
+                    const float* b, float* out, int32_t rows, int32_t dim,
+                    int32_t fold_silu);
 /* film[r, j] = sum_k silu_temb[r,k] * w[j,k] + b[j], j < cols (all FiLM nets
  * of the model concatenated).                                               */
 int lm2a_film(void* stream, const float* silu_temb, const float* w,

@@ -30,7 +30,7 @@ class ConvDesc(ctypes.Structure):
                 ("gn_eps", c_float), ("_pad3", c_int32)]
 
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -54,6 +54,8 @@ SIGNATURES = {
                                          c_int32, c_int32]),
     "lm2a_time_mlp": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                 c_int32]),
+    "lm2a_time_embed": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                  c_int32, c_int32]),
     "lm2a_film": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                             c_int32]),
     "lm2a_ingest_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,

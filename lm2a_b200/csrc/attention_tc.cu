@@ -16,8 +16,10 @@
 //              max with lazy rescaling (O in TMEM is only corrected when the row max grows
 //              by more than 2^8), exp2, row sum, P -> bf16 -> 128B-swizzled shared tile;
 //              finally O / l -> bf16 slab
-// TMEM: S[0] cols 0-63, S[1] cols 64-127, O cols 128-(128+dh); 256 columns per CTA, two
-// CTAs per SM for dh <= 64.
+// TMEM: S[0] cols 0-63, S[1] cols 64-127, O in dh further columns; two CTAs per SM for
+// dh <= 128. Head dims: any multiple of 64 up to 384 (64-channel operand panels, 128B
+// swizzle) plus 32 and 96 (32-channel panels, 64B swizzle) — the legacy UNet1D
+// (reference models/unet1d.py:17-29: 4 heads over 256..1536 channels) needs 192, 256 and 384.
 #include "../../include/lm2a_b200.h"
 #include "common.cuh"
 
@@ -32,17 +34,22 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int DH>
 struct AttnSmem {
-  static constexpr int kPanels = DH > 64 ? DH / 64 : 1;  // 64-channel panels of Q / K tiles
-  static constexpr int kPanelW = DH > 64 ? 64 : DH;
+  static constexpr int kPanelW = DH % 64 == 0 ? 64 : 32;  // channel panels of the Q / K tiles
+  static constexpr int kPanels = DH / kPanelW;
+  static constexpr bool kSw64 = kPanelW == 32;
+  // V^T tile = DH rows x 64 keys; a TMA box / UMMA N is at most 256 rows
+  static constexpr int kVBoxRows = DH > 256 ? DH / 2 : DH;
+  static constexpr int kVBoxes = DH / kVBoxRows;
   static constexpr int kQPanelBytes = kBQ * kPanelW * 2;
   static constexpr int kKPanelBytes = kBK * kPanelW * 2;
   static constexpr int kQBytes = kBQ * DH * 2;
   static constexpr int kKBytes = kBK * DH * 2;
   static constexpr int kVBytes = DH * kBK * 2;
   static constexpr int kPBytes = kBQ * kBK * 2;
-  // dh = 128: two K + two V stages and one P tile keep a CTA at 112 KB so that two fit an SM
-  static constexpr int kKStages = DH > 64 ? 2 : 3;
-  static constexpr int kVStages = DH > 64 ? 2 : 3;
+  // dh = 128: two K + two V stages and one P tile keep a CTA at 112 KB so that two fit an SM;
+  // dh = 384: Q alone is 96 KB, one stage each (208 KB)
+  static constexpr int kKStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
+  static constexpr int kVStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
   static constexpr int kPBufs = DH > 64 ? 1 : 2;
   static constexpr int kPOff = kQBytes;
   static constexpr int kKOff = kPOff + kPBufs * kPBytes;
@@ -53,6 +60,12 @@ struct AttnSmem {
   // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
   // third is never scheduled
   static constexpr int kBytes = kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded;
+  static_assert(DH % 32 == 0 && DH >= 32 && DH <= 384, "head dim");
+  static_assert(kBytes <= 227 * 1024, "shared memory budget");
+  // TMEM: S = 128 columns + O = DH columns rounded up to a power of two; dh > 256 takes the
+  // whole 512 columns in one allocation (S first, O behind it)
+  static constexpr bool kOneAlloc = DH > 256;
+  static constexpr uint32_t kTmemColsO = DH <= 32 ? 32 : DH <= 64 ? 64 : DH <= 128 ? 128 : 256;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, bool sw64) {
@@ -97,7 +110,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                      int o_ld, const int* __restrict__ kv_slot, int tp, int t_valid, int lk,
                      int e, int heads) {
   using L = AttnSmem<DH>;
-  constexpr bool kSw64 = (DH == 32);
+  constexpr bool kSw64 = L::kSw64;
   constexpr int KS = L::kKStages, VS = L::kVStages, PB = L::kPBufs;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -117,8 +130,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   auto pv_done = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + PB + b); };
   const uint32_t o_full = bar_base + 8u * (3 + 2 * KS + 2 * VS + 2 * PB);
   const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);  // S, then O (+4 B)
-  // TMEM: two allocations (S: 128 columns, O: DH columns) so that three dh = 32 CTAs fit an SM
-  constexpr uint32_t kTmemColsO = DH < 32 ? 32 : DH;
+  constexpr uint32_t kTmemColsO = L::kTmemColsO;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.z;
@@ -156,8 +168,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     mbar_fence_init();
   }
   if (warp == 5) {
-    tmem_alloc(tmem_slot, kTmemColsS);
-    tmem_alloc(tmem_slot + 4, kTmemColsO);
+    if (L::kOneAlloc) {
+      tmem_alloc(tmem_slot, 512);
+    } else {
+      tmem_alloc(tmem_slot, kTmemColsS);
+      tmem_alloc(tmem_slot + 4, kTmemColsO);
+    }
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -165,7 +181,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   tc_fence_after_sync();
   uint32_t tmem_base, tmem_o;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_o) : "r"(tmem_slot + 4));
+  if (L::kOneAlloc) tmem_o = tmem_base + kTmemColsS;
+  else asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_o) : "r"(tmem_slot + 4));
   // everything above overlapped the previous kernel's tail; from here on we touch its output
   pdl_wait();
   pdl_launch_dependents();
@@ -184,13 +201,13 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         mbar_expect_tx(k_full(st), L::kKBytes);
 #pragma unroll
         for (int p = 0; p < L::kPanels; ++p)
-          tma_load_2d(k_tile(st) + p * L::kKPanelBytes, km, h * DH + p * 64,
+          tma_load_2d(k_tile(st) + p * L::kKPanelBytes, km, h * DH + p * L::kPanelW,
                       slot * lk + j * kBK, k_full(st));
       };
       mbar_expect_tx(q_full, L::kQBytes);
 #pragma unroll
       for (int p = 0; p < L::kPanels; ++p)
-        tma_load_2d(q_base + p * L::kQPanelBytes, &tmQ, stream * e + h * DH + p * 64,
+        tma_load_2d(q_base + p * L::kQPanelBytes, &tmQ, stream * e + h * DH + p * L::kPanelW,
                     r * tp + q0, q_full);
       load_k(0);
       for (int j = 0; j < ntiles; ++j) {
@@ -198,14 +215,17 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         const int st = j % VS;
         mbar_wait(v_empty(st), ((uint32_t)(j / VS) & 1u) ^ 1u);
         mbar_expect_tx(v_full(st), L::kVBytes);
-        tma_load_2d(v_tile(st), vm, j * kBK, slot * e + h * DH, v_full(st));
+#pragma unroll
+        for (int c = 0; c < L::kVBoxes; ++c)
+          tma_load_2d(v_tile(st) + c * L::kVBoxRows * kBK * 2, vm, j * kBK,
+                      slot * e + h * DH + c * L::kVBoxRows, v_full(st));
       }
     }
   } else if (warp == 5) {
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, DH);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, L::kVBoxRows);
       auto issue_pv = [&](int jj) {
         const int pb = jj % PB, st = jj % VS;
         mbar_wait(v_full(st), (uint32_t)(jj / VS) & 1u);
@@ -215,9 +235,14 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         const int ksteps = (keys + 15) >> 4;
         const uint64_t adesc = umma_desc_kmajor(p_tile(pb), false);
         const uint64_t bdesc = umma_desc_kmajor(v_tile(st), false);
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ss(tmem_o, adesc + 2u * k, bdesc + 2u * k, idesc_pv,
-                       (jj | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int c = 0; c < L::kVBoxes; ++c) {
+          // rows [c * kVBoxRows, ...) of the V^T tile -> O columns of the same range
+          const uint64_t bd = bdesc + (uint64_t)((c * L::kVBoxRows * kBK * 2) >> 4);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ss(tmem_o + c * L::kVBoxRows, adesc + 2u * k, bd + 2u * k, idesc_pv,
+                         (jj | k) != 0 ? 1u : 0u);
+        }
         umma_commit(v_empty(st));
         umma_commit(pv_done(pb));
       };
@@ -357,8 +382,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   __syncthreads();
   if (warp == 5) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemColsS);
-    tmem_dealloc(tmem_o, kTmemColsO);
+    if (L::kOneAlloc) {
+      tmem_dealloc(tmem_base, 512);
+    } else {
+      tmem_dealloc(tmem_base, kTmemColsS);
+      tmem_dealloc(tmem_o, kTmemColsO);
+    }
   }
 }
 
@@ -389,7 +418,7 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
                 const int32_t* kv_slot, int slots, int rows, int tp, int t_valid, int lk, int e,
                 int heads) {
   using L = AttnSmem<DH>;
-  constexpr bool sw64 = (DH == 32);
+  constexpr bool sw64 = L::kSw64;
   auto kern = cross_attn_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) {
@@ -406,10 +435,10 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
       encode_map(&tkt, k_t, (uint64_t)e, (uint64_t)slots * lk, (uint64_t)k_ld, L::kPanelW, kBK,
                  sw64))
     return 1;
-  if (encode_map(&tvm, vt_m, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK, DH,
-                 false) ||
-      encode_map(&tvt, vt_t, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK, DH,
-                 false))
+  if (encode_map(&tvm, vt_m, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK,
+                 L::kVBoxRows, false) ||
+      encode_map(&tvt, vt_t, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK,
+                 L::kVBoxRows, false))
     return 1;
   dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
   LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, st, tq, tkm, tkt, tvm, tvt,
@@ -448,18 +477,22 @@ extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, v
                "cross_attn: tensors must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int dh = e / heads;
+#define LM2A_ATTN_CASE(D)                                                                     \
+  case D:                                                                                     \
+    return launch_attn<D>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,   \
+                          vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads)
   switch (dh) {
-    case 32:
-      return launch_attn<32>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
-                             vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
-    case 64:
-      return launch_attn<64>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
-                             vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
-    case 128:
-      return launch_attn<128>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,
-                              vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads);
+    LM2A_ATTN_CASE(32);
+    LM2A_ATTN_CASE(64);
+    LM2A_ATTN_CASE(96);
+    LM2A_ATTN_CASE(128);
+    LM2A_ATTN_CASE(192);
+    LM2A_ATTN_CASE(256);
+    LM2A_ATTN_CASE(384);
     default:
-      LM2A_REQUIRE(false, "cross_attn: head dim %d unsupported (32, 64 or 128)", dh);
+      LM2A_REQUIRE(false, "cross_attn: head dim %d unsupported (32, 64, 96, 128, 192, 256, 384)",
+                   dh);
   }
+#undef LM2A_ATTN_CASE
   return 0;
 }

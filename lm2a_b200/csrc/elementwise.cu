@@ -284,7 +284,7 @@ transpose_kv_kernel(const __nv_bfloat16* __restrict__ src, int src_ld,
 // each warp produces outputs with a shuffle reduction over the input dim.
 __global__ void __launch_bounds__(256)
 time_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w,
-                const float* __restrict__ b, float* __restrict__ out, int dim) {
+                const float* __restrict__ b, float* __restrict__ out, int dim, int fold_silu) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ float emb[];
@@ -308,7 +308,7 @@ time_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w,
     acc = warp_sum(acc);
     if (lane == 0) {
       const float v = silu_accurate(acc + __ldg(b + j));
-      out[(size_t)r * dim + j] = silu_accurate(v);
+      out[(size_t)r * dim + j] = fold_silu ? silu_accurate(v) : v;
     }
   }
 }
@@ -513,16 +513,22 @@ extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, voi
   return 0;
 }
 
-extern "C" int lm2a_time_mlp(void* stream, const int64_t* t, const float* w, const float* b,
-                             float* silu_temb, int32_t rows, int32_t dim) {
+extern "C" int lm2a_time_embed(void* stream, const int64_t* t, const float* w, const float* b,
+                               float* out, int32_t rows, int32_t dim, int32_t fold_silu) {
   using namespace lm2a;
-  LM2A_REQUIRE(t && w && b && silu_temb, "time_mlp: null pointer");
+  LM2A_REQUIRE(t && w && b && out, "time_mlp: null pointer");
   LM2A_REQUIRE(rows > 0 && dim >= 4 && dim % 2 == 0 && dim <= 4096, "time_mlp: bad dim %d", dim);
-  LM2A_CUDA_OK(launch_kernel(time_mlp_kernel, dim3(dim3(rows, (dim + 7) / 8)), dim3(256), dim * sizeof(float), reinterpret_cast<cudaStream_t>(stream), 
-      t, w, b, silu_temb, dim));
+  LM2A_CUDA_OK(launch_kernel(time_mlp_kernel, dim3(dim3(rows, (dim + 7) / 8)), dim3(256),
+                             dim * sizeof(float), reinterpret_cast<cudaStream_t>(stream), t, w, b,
+                             out, dim, fold_silu != 0 ? 1 : 0));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+extern "C" int lm2a_time_mlp(void* stream, const int64_t* t, const float* w, const float* b,
+                             float* silu_temb, int32_t rows, int32_t dim) {
+  return lm2a_time_embed(stream, t, w, b, silu_temb, rows, dim, 1);
 }
 
 extern "C" int lm2a_film(void* stream, const float* silu_temb, const float* w, const float* b,

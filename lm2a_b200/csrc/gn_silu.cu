@@ -149,6 +149,9 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
   const int passes = (vpr + kGnThreads - 1) / kGnThreads;
   const int tstep = kGnThreads / lanes;
   const int cvl = threadIdx.x % lanes, tl = threadIdx.x / lanes;
+  // vector-column counts that do not divide the CTA (c = 768, 1536: legacy UNet1D concat
+  // slabs) leave the last kGnThreads % lanes threads / the tail of the last pass idle
+  const bool active = tl < tstep;
   const int t_begin = blockIdx.x * (kApplyVec * tstep);
   const size_t row_base = (size_t)r * tp;
   uint4 q[kApplyVec];
@@ -156,7 +159,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
   for (int k = 0; k < kApplyVec; ++k) {
     const int t = t_begin + tl + k * tstep;
     q[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (t < t_valid)
+    if (active && t < t_valid)
       q[k] = __ldg(reinterpret_cast<const uint4*>(x + (row_base + t) * x_ld + cvl * 8));
   }
   const int sub_per_group = cg / stats_gran;
@@ -187,6 +190,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
 
   for (int pass = 0; pass < passes; ++pass) {
     const int cv = pass * kGnThreads + cvl;
+    if (!active || cv >= vpr) break;
     if (pass > 0) {
 #pragma unroll
       for (int k = 0; k < kApplyVec; ++k) {
@@ -246,8 +250,7 @@ extern "C" int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, voi
                "gn_apply: c=%d not divisible by groups=%d (<= 64)", c, groups);
   const int cg = c / groups;
   const int vpr = c / 8;
-  LM2A_REQUIRE(c % 8 == 0 && (kGnThreads % vpr == 0 || vpr % kGnThreads == 0),
-               "gn_apply: c/8 (%d) must divide or be a multiple of %d", vpr, kGnThreads);
+  LM2A_REQUIRE(c % 8 == 0 && vpr > 0, "gn_apply: c=%d must be a positive multiple of 8", c);
   LM2A_REQUIRE((stats_gran == 8 || stats_gran == 16 || stats_gran == 32) &&
                    cg % stats_gran == 0 && stats_sub >= c / stats_gran &&
                    stats_ns >= tp / 32 + 2,

@@ -1,4 +1,4 @@
-"""Launch planner for UNet1D_ultimate on B200.
+"""Launch planner for UNet1D_ultimate (and the legacy UNet1D) on B200.
 
 Turns the parameter tree of models/unet1d_ultimate.py into
   (1) packed device weights: bf16 K-major GEMM operands with the algebraic folds
@@ -97,16 +97,24 @@ def _check_channels(c, what):
                            "multiples of 64 (64-wide K blocks, 8-channel GroupNorm vectors)")
 
 
+HEAD_DIMS = (32, 64, 96, 128, 192, 256, 384)
+
+
 def pack_block(blk, heads, dev, film_col):
+    """Packs one ResBlock: UNet1D_ultimate's (gn1/gn2, FiLM, optional skip conv and attention)
+    or the legacy UNet1D's (norm1/norm2, constant width, always attention, identity residual —
+    reference models/unet1d.py:15-60)."""
     cin, cout = blk.in_channels, blk.out_channels
     _check_channels(cin, "in_channels")
     _check_channels(cout, "out_channels")
     p = PackedBlock()
-    p.cin, p.cout, p.attn = cin, cout, bool(blk.use_attn)
-    p.gn1, p.gn2 = _gn(blk.gn1, dev), _gn(blk.gn2, dev)
+    p.cin, p.cout, p.attn = cin, cout, bool(getattr(blk, "use_attn", True))
+    gn1 = blk.gn1 if hasattr(blk, "gn1") else blk.norm1
+    gn2 = blk.gn2 if hasattr(blk, "gn2") else blk.norm2
+    p.gn1, p.gn2 = _gn(gn1, dev), _gn(gn2, dev)
     p.film_col = film_col
     p.w1, p.b1 = _finish(_conv_w(blk.conv1.weight), _f64(blk.conv1.bias), dev)
-    has_skip = not isinstance(blk.skip, torch.nn.Identity)
+    has_skip = hasattr(blk, "skip") and not isinstance(blk.skip, torch.nn.Identity)
     p.has_skip = has_skip
     w2, b2 = _conv_w(blk.conv2.weight), _f64(blk.conv2.bias)
     wskip = _f64(blk.skip.weight)[:, :, 0] if has_skip else None
@@ -119,9 +127,9 @@ def pack_block(blk, heads, dev, film_col):
     if p.attn:
         ca = blk.cross_attn
         e = cout
-        if e % heads != 0 or (e // heads) not in (32, 64, 128):
+        if e % heads != 0 or (e // heads) not in HEAD_DIMS:
             raise RuntimeError(f"attention head dim {e}/{heads} unsupported on the sm_100a path "
-                               "(needs 32, 64 or 128)")
+                               f"(needs one of {HEAD_DIMS})")
         p.e, p.heads = e, heads
         qs = LOG2E / math.sqrt(e // heads)
         wq, bq, wkv, bkv, wo, bo = [], [], [], [], [], []
@@ -159,6 +167,19 @@ def pack_block(blk, heads, dev, film_col):
 
 
 class PackedModel:
+    kind = "ultimate"
+
+    def scratch_width(self, lvl):
+        """Widest bf16 scratch slab (in channels) any launch of level `lvl` needs."""
+        n = len(self.dims)
+        width = 2 * self.dims[min(lvl, n - 1)]
+        if lvl < n:
+            width = max(width, self.dims[min(lvl + 1, n - 1)])  # upsampled input
+        return max(width, self.base)
+
+    def cat_width(self, lvl):
+        return 2 * self.dims[lvl]
+
     def __init__(self, model, dev):
         self.in_dim = model.in_dim
         self.in_pad = _pad_to(model.in_dim, 64)
@@ -205,6 +226,81 @@ class PackedModel:
         self.attn_blocks += [b for _, _, blocks in self.ups for b in blocks if b.attn]
 
 
+def _convT_w(w):
+    """ConvTranspose1d k4 s2 p1 weight [Cin, Cout, 4] -> two k3 GEMM operands [Cout, 3*Cin]
+    (tap-major K over input slots m-1, m, m+1) for the even / odd output slots:
+    y[2m] = W1 x[m] + W3 x[m-1], y[2m+1] = W2 x[m] + W0 x[m+1] (t' = 2t - 1 + k)."""
+    w = _f64(w)
+    cin, cout, k = w.shape
+    assert k == 4
+    z = torch.zeros(cout, cin, dtype=torch.float64, device=w.device)
+    tap = lambda i: w[:, :, i].t()  # noqa: E731
+    even = torch.cat([tap(3), tap(1), z], dim=1)
+    odd = torch.cat([z, tap(2), tap(0)], dim=1)
+    return even, odd
+
+
+class PackedLegacy:
+    """Packed weights of the legacy UNet1D (reference models/unet1d.py:64-154): level l has one
+    block of width c_l (c_0 = base, c_l = dims[l-1]); the decoder block of level l is
+    dims[l] + c_l wide (transposed-conv output | skip)."""
+    kind = "legacy"
+
+    def scratch_width(self, lvl):
+        n = len(self.dims)
+        return 2 * (self.dims[lvl] + self.c[lvl]) if lvl < n else 2 * self.dims[n - 1]
+
+    def cat_width(self, lvl):
+        return self.dims[lvl] + self.c[lvl]
+
+    def __init__(self, model, dev):
+        self.in_dim = model.in_dim
+        self.in_pad = _pad_to(model.in_dim, 64)
+        self.base = model.base_dim
+        self.dims = [model.base_dim * m for m in model.dim_mults]
+        self.c = [self.base] + self.dims[:-1]
+        self.cond_dim = model.cond_dim
+        _check_channels(model.cond_dim, "cond_dim")
+        self.time_dim = td = model.time_emb_dim
+        lin = model.time_embedding.time_mlp[1]
+        self.time_w = lin.weight.detach().to(dev, torch.float32).contiguous()
+        self.time_b = lin.bias.detach().to(dev, torch.float32).contiguous()
+        self.w_in, self.b_in = _finish(_conv_w(model.input_proj.weight, self.in_pad),
+                                       _f64(model.input_proj.bias), dev)
+        film_w, film_b = [], []
+        col = [0]
+
+        def pack(blk):
+            pb = pack_block(blk, blk.num_heads, dev, col[0])
+            ch = blk.out_channels
+            # additive timestep term as a FiLM table with scale == 0: h * (1 + 0) + time_proj(t)
+            tw, tb = blk.time_proj.weight.detach().float(), blk.time_proj.bias.detach().float()
+            film_w.append(torch.cat([torch.zeros_like(tw), tw], dim=0))
+            film_b.append(torch.cat([torch.zeros_like(tb), tb], dim=0))
+            col[0] += 2 * ch
+            return pb
+
+        self.downs = []
+        for blk, conv in model.downs:
+            wd, bd = _finish(_conv_w(conv.weight), _f64(conv.bias), dev)
+            self.downs.append((pack(blk), wd, bd))
+        self.mid = pack(model.mid)
+        self.ups = []
+        for convT, blk in model.ups:
+            even, odd = _convT_w(convT.weight)
+            we, bu = _finish(even, _f64(convT.bias), dev)
+            wo, _ = _finish(odd, _f64(convT.bias), dev)
+            self.ups.append((we, wo, bu, pack(blk)))
+        self.film_cols = col[0]
+        self.film_w = torch.cat(film_w, dim=0).to(dev).contiguous()
+        self.film_b = torch.cat(film_b, dim=0).to(dev).contiguous()
+        assert self.film_w.shape == (self.film_cols, td)
+        self.w_out, self.b_out = _finish(_conv_w(model.out_proj.weight), _f64(model.out_proj.bias),
+                                         dev)
+        self.attn_blocks = ([b for b, _, _ in self.downs] + [self.mid]
+                            + [b for _, _, _, b in self.ups])
+
+
 # ------------------------------------------------------------------------------ the plan
 class UNetPlan:
     """Static launch list for `rows` clip-rows of length T attending to `lk` condition
@@ -236,18 +332,13 @@ class UNetPlan:
         self.film = torch.zeros(self.t_rows, pm.film_cols, dtype=torch.float32, device=dev)
 
         # scratch slabs shared by all blocks (sized for the largest level)
-        cmax = 0
-        for lvl in range(n_down + 1):
-            width = 2 * pm.dims[min(lvl, n_down - 1)]
-            if lvl < n_down:
-                width = max(width, pm.dims[min(lvl + 1, n_down - 1)])  # upsampled input
-            cmax = max(cmax, g.M[lvl] * max(width, pm.base))
+        cmax = max(g.M[lvl] * pm.scratch_width(lvl) for lvl in range(n_down + 1))
         flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
         self._norm, self._h1, self._norm2, self._q, self._o, self._xup = (
             flat(), flat(), flat(), flat(), flat(), flat())
         self._pp = [flat(), flat()]  # block outputs ping-pong
         self.x_slab = z(g.M[0], pm.in_pad)
-        self.cat = [z(g.M[lvl], 2 * pm.dims[lvl]) for lvl in range(n_down)]
+        self.cat = [z(g.M[lvl], pm.cat_width(lvl)) for lvl in range(n_down)]
 
         # K/V caches per attention block and stream: [nslots*lk, 2E] (K | V) written by the
         # projection GEMM, plus V^T [nslots*E, lk_pad] (keys contiguous: the K-major B operand
@@ -266,7 +357,10 @@ class UNetPlan:
         self.fuse_gn = fuse_gn and os.environ.get("LM2A_FUSE_GN", "1") != "0"
         self._side = None
         self._side_op = self._side_pending = self._partial_rows = False
-        self._build()
+        if pm.kind == "legacy":
+            self._build_legacy()
+        else:
+            self._build()
 
     # -- helpers -------------------------------------------------------------------------
     def _view(self, flat, m, c):
@@ -381,22 +475,94 @@ class UNetPlan:
                    out, out_ld, out_chan_off=oo, stats=ost, **res)
 
     # -- plan construction ----------------------------------------------------------------
+    def _build_kv_ops(self):
+        """Per-clip K/V cache build: one projection GEMM + one V transpose per block and stream."""
+        pm = self.pm
+        if not self.use_cond:
+            return
+        for p, (kv_m, kv_t), (vt_m, vt_t) in zip(pm.attn_blocks, self.kv, self.vt):
+            n = self.nslots * self.lk
+            for cond, w, b, dst, vt in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m, vt_m),
+                                        (self.cond_t, p.wkv_t, p.bkv_t, kv_t, vt_t)):
+                self.kv_ops.append((ops.conv1d, (ops.make_conv_desc(
+                    [Seg(cond, pm.cond_dim, pm.cond_dim, TAPS_K1, n)], w, b, 2 * p.e, n,
+                    self.lk, self.lk, dst, 2 * p.e),)))
+                self.kv_ops.append((ops.transpose_kv, (dst, 2 * p.e, p.e, vt, self.lk_pad,
+                                                       self.nslots, self.lk, p.e)))
+
+    def _build_legacy(self):
+        """Launch list of the legacy UNet1D.forward (reference models/unet1d.py:113-154)."""
+        pm, g, rows = self.pm, self.geo, self.rows
+        if not self.use_cond:
+            raise RuntimeError("legacy UNet1D needs motion_f / text_f (every block cross-attends)")
+        n_down = len(pm.dims)
+        kv_iter = iter(zip(self.kv, self.vt))
+        self._build_kv_ops()
+        # TimestepEmbedding output itself (one SiLU): time_proj has no activation in front
+        self._add(ops.time_embed, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,
+                  pm.time_dim, False, meta={"kind": "time_mlp", "flops": 0})
+        self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, self.t_rows,
+                  pm.time_dim, pm.film_cols)
+        self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
+                  self.t, g.Tp[0], pm.in_pad)
+        cur = self._view(self._pp[0], g.M[0], pm.base)
+        cur_st = self._stats(rows, 0, pm.base, 8)
+        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
+                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim, stats=cur_st)
+        cur_c, pp = pm.base, 1
+        # concat slab of level l: [transposed-conv output (dims[l]) | skip (c_l)], normalised as
+        # a whole by the decoder block. The transposed conv writes it as two launches (even / odd
+        # slots) in the geometry of level l+1, so its statistics need two slice ranges.
+        self.cat_st = []
+        for lvl in range(n_down):
+            ns_lo = g.Tp[lvl + 1] // 32 + 2
+            wcat = pm.cat_width(lvl)
+            self.cat_st.append(ops.Stats(rows, g.Tp[lvl], wcat, _stats_gran(wcat, 8), self.dev,
+                                         ns=max(g.Tp[lvl] // 32 + 2, 2 * ns_lo)))
+        for lvl, (p, wd, bd) in enumerate(pm.downs):
+            dim, wcat = pm.dims[lvl], pm.cat_width(lvl)
+            self._resblock(p, lvl, cur, cur_c, 0, cur_st, self.cat[lvl], wcat, dim,
+                           self.cat_st[lvl], next(kv_iter))
+            nxt = self._view(self._pp[pp], g.M[lvl + 1], dim)
+            pp ^= 1
+            nxt_st = self._stats(rows, lvl + 1, dim, 8)
+            self._conv([Seg(self.cat[lvl], wcat, p.cout, TAPS_K4S2, g.M[lvl], dim)], wd, bd, dim,
+                       g.M[lvl + 1], g.Tp[lvl + 1], g.T[lvl + 1], nxt, dim, stats=nxt_st)
+            cur, cur_c, cur_st = nxt, dim, nxt_st
+        lvl = n_down
+        out = self._view(self._pp[pp], g.M[lvl], cur_c)
+        pp ^= 1
+        self._resblock(pm.mid, lvl, cur, cur_c, 0, cur_st, out, cur_c, 0,
+                       self._stats(rows, lvl, cur_c, 8), next(kv_iter))
+        cur = out
+        for i, (we, wo, bu, p) in enumerate(pm.ups):
+            lvl = n_down - 1 - i
+            dim, wcat = pm.dims[lvl], pm.cat_width(lvl)
+            lo = lvl + 1
+            assert 2 * g.T[lo] <= g.T[lvl] and g.Tp[lvl] == 2 * g.Tp[lo]
+            # ConvTranspose1d k4 s2 p1: even slots 2m and odd slots 2m+1 of the level-l slab are
+            # the two halves of a row of the [M_{l+1}, 2 * wcat] view of the concat slab; slots
+            # past 2 * T_{l+1} are written as zero (= the reference's F.pad, unet1d.py:141-147)
+            for half, w in enumerate((we, wo)):
+                self._conv([Seg(cur, cur_c, cur_c, TAPS_K3, g.M[lo])], w, bu, dim, g.M[lo],
+                           g.Tp[lo], g.T[lo], self.cat[lvl], 2 * wcat, out_chan_off=half * wcat,
+                           k_real=2 * cur_c,
+                           stats=self.cat_st[lvl].view(0, 0, half * (g.Tp[lo] // 32 + 2)))
+            out = self._view(self._pp[pp], g.M[lvl], wcat)
+            pp ^= 1
+            self._resblock(p, lvl, self.cat[lvl], wcat, 0, self.cat_st[lvl], out, wcat, 0,
+                           self._stats(rows, lvl, wcat, 8), next(kv_iter))
+            cur, cur_c = out, wcat
+        self._conv([Seg(cur, cur_c, cur_c, TAPS_K1, g.M[0])], pm.w_out, pm.b_out, pm.in_dim,
+                   g.M[0], g.Tp[0], g.T[0], self.eps, 0, out_mode=OUT_F32_NCT, block_n=128)
+
     def _build(self):
         pm, g, rows = self.pm, self.geo, self.rows
         n_down = len(pm.dims)
         kv_iter = iter(zip(self.kv, self.vt)) if self.use_cond else iter(())
         next_kv = lambda p: next(kv_iter) if (p.attn and self.use_cond) else None  # noqa: E731
 
-        if self.use_cond:
-            for p, (kv_m, kv_t), (vt_m, vt_t) in zip(pm.attn_blocks, self.kv, self.vt):
-                n = self.nslots * self.lk
-                for cond, w, b, dst, vt in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m, vt_m),
-                                            (self.cond_t, p.wkv_t, p.bkv_t, kv_t, vt_t)):
-                    self.kv_ops.append((ops.conv1d, (ops.make_conv_desc(
-                        [Seg(cond, pm.cond_dim, pm.cond_dim, TAPS_K1, n)], w, b, 2 * p.e, n,
-                        self.lk, self.lk, dst, 2 * p.e),)))
-                    self.kv_ops.append((ops.transpose_kv, (dst, 2 * p.e, p.e, vt, self.lk_pad,
-                                                           self.nslots, self.lk, p.e)))
+        self._build_kv_ops()
 
         # timestep embedding + all FiLM tables, once per step
         self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,
@@ -571,7 +737,8 @@ class UNetEngine:
         p = next(model.parameters())
         ops.require_device(p)
         self.dev = p.device
-        self.pm = PackedModel(model, self.dev)
+        legacy = hasattr(model, "input_proj")  # models/unet1d.py names vs unet1d_ultimate.py
+        self.pm = PackedLegacy(model, self.dev) if legacy else PackedModel(model, self.dev)
         self.plans = {}
         self._cond_key = None
 

@@ -42,20 +42,22 @@ class Stats:
     the producing kernel's epilogue, read by gn_apply. `view(row0, chan0)` addresses a
     row / channel sub-range (a launch over part of the rows, or one half of a concat slab)."""
 
-    def __init__(self, rows, tp, c, gran, dev, buf=None, row0=0, chan0=0):
+    def __init__(self, rows, tp, c, gran, dev, buf=None, row0=0, chan0=0, slice0=0, ns=None):
         self.rows, self.tp, self.c, self.gran = rows, tp, c, gran
         self.sub = c // gran
-        self.ns = tp // 32 + 2
+        # `ns` > tp/32 + 2: room for a second producer of the same (row, channels) whose slices
+        # start at `slice0` (the odd-slot launch of a transposed conv)
+        self.ns = ns if ns is not None else tp // 32 + 2
         self.buf = buf if buf is not None else torch.zeros(rows * self.sub * self.ns, 2,
                                                            dtype=torch.float32, device=dev)
-        self.row0, self.chan0 = row0, chan0
+        self.row0, self.chan0, self.slice0 = row0, chan0, slice0
 
-    def view(self, row0=0, chan0=0):
+    def view(self, row0=0, chan0=0, slice0=0):
         return Stats(self.rows, self.tp, self.c, self.gran, None, self.buf, self.row0 + row0,
-                     self.chan0 + chan0)
+                     self.chan0 + chan0, self.slice0 + slice0, self.ns)
 
     def ptr(self):
-        off = (self.row0 * self.sub + self.chan0 // self.gran) * self.ns
+        off = (self.row0 * self.sub + self.chan0 // self.gran) * self.ns + self.slice0
         return self.buf.data_ptr() + off * 8
 
 
@@ -145,6 +147,11 @@ def transpose_kv(src, src_ld, src_off, dst, dst_ld, slots, lk, c):
 def time_mlp(t, w, b, out, rows, dim):
     _lib.check(_lib.load().lm2a_time_mlp(_stream(), _ptr(t), _ptr(w), _ptr(b), _ptr(out), rows,
                                          dim), "lm2a_time_mlp")
+
+
+def time_embed(t, w, b, out, rows, dim, fold_silu):
+    _lib.check(_lib.load().lm2a_time_embed(_stream(), _ptr(t), _ptr(w), _ptr(b), _ptr(out), rows,
+                                           dim, 1 if fold_silu else 0), "lm2a_time_embed")
 
 
 def film(s, w, b, out, rows, dim, cols):

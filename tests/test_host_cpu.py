@@ -83,6 +83,38 @@ def test_geometry_and_plan():
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 
 
+def test_legacy_model_layout_and_plan():
+    """Legacy UNet1D mirror keeps the reference's state_dict (models/unet1d.py) and its launch
+    plan has the expected shape; the transposed-conv even/odd split is exact in fp64."""
+    from lm2a_b200.engine import PackedLegacy, UNetPlan, _convT_w
+    from lm2a_b200.models import UNet1D
+    cfg = orc.LegacyConfig(80, 128, (1, 2, 4), 128, 256)
+    net = UNet1D(80, 128, (1, 2, 4), 128, 256)
+    spec = orc.legacy_state_dict_spec(cfg)   # pinned to the reference by make_golden_legacy.py
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(tuple(sd[k].shape) == shp for k, shp in spec)
+    with pytest.raises(RuntimeError, match="motion_f"):
+        net(torch.zeros(1, 80, 64), torch.zeros(1, dtype=torch.long), None, None)
+    pm = PackedLegacy(net, torch.device("cpu"))
+    assert [b.e // b.heads for b in pm.attn_blocks] == [32, 32, 64, 128, 192, 96, 64]
+    plan = UNetPlan(pm, 4, 100, 60, 3, 2, True, torch.device("cpu"), uniform_t=True, uncond_rows=2)
+    kinds = [m["kind"] for _, _, m in plan.ops]
+    assert kinds.count("cross_attn") == 7 and kinds.count("bias_add") == 7
+    assert len(plan.kv_ops) == 28
+    # ConvTranspose1d k4 s2 p1 == two k3 GEMMs over (x[m-1], x[m], x[m+1]) -> slots 2m / 2m+1
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(6, 4, 4, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 6, 9, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv_transpose1d(x, w, stride=2, padding=1)
+    even, odd = _convT_w(w)
+    xp = torch.nn.functional.pad(x, (1, 1))
+    cols = torch.cat([xp[:, :, 0:9], xp[:, :, 1:10], xp[:, :, 2:11]], dim=1)  # [B, 3*Cin, T]
+    got = torch.stack([torch.einsum("ok,bkt->bot", even, cols),
+                       torch.einsum("ok,bkt->bot", odd, cols)], dim=-1).reshape(2, 4, 18)
+    assert float((got - ref).abs().max()) < 1e-12
+
+
 def test_weight_folds_are_exact_in_fp64():
     """q-scale, kv_proj o in_proj and out_proj o fuse_proj folds (engine.pack_block) reproduce
     CrossAttentionFusion (cross_attention.py:38-67) when evaluated in fp64."""

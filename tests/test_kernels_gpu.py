@@ -314,6 +314,10 @@ def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
     (1024, 8, 129, 516, 1.0),    # production level 2: dh = 128, two query tiles
     (512, 8, 130, 2064, 1.0),    # long-clip K/V
     (256, 8, 200, 300, 6.0), (1024, 8, 70, 200, 6.0),  # peaked softmax: running max grows, O is rescaled
+    # legacy UNet1D head dims (4 heads over 384 / 768 / 1024 / 1536 channels): 96 (32-channel
+    # panels), 192, 256, 384 (two V^T boxes, one 512-column TMEM allocation, single-stage rings)
+    (384, 4, 50, 60, 1.0), (768, 4, 129, 150, 1.0), (1024, 4, 64, 516, 1.0),
+    (1536, 4, 129, 516, 1.0), (1536, 4, 40, 100, 6.0),
 ])
 def test_cross_attention_core(ops, e, heads, t, lk, qgain):
     r, slots, tp = 3, 2, t + 2
@@ -347,6 +351,71 @@ def test_cross_attention_core(ops, e, heads, t, lk, qgain):
         p = torch.softmax(qq @ k.transpose(-1, -2), dim=-1)
         ref = (p @ v).transpose(1, 2).reshape(r, t, e).permute(0, 2, 1)
         assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"attention stream {s}")
+
+
+@pytest.mark.parametrize("r,t,tp,c,groups", [(2, 129, 130, 1536, 8), (3, 50, 52, 768, 8),
+                                               (2, 33, 36, 384, 8), (2, 70, 72, 192, 8)])
+def test_gn_apply_channel_counts_off_the_cta_grid(ops, r, t, tp, c, groups):
+    """c / 8 that neither divides nor is a multiple of the 256-thread CTA (legacy UNet1D concat
+    widths 1536 / 768 / 384 / 192): statistics from bias_add, then the streaming apply."""
+    x = rnd(r, c, t, seed=60)
+    xs = to_slab(x, tp)
+    bias = rnd(c, seed=61, scale=0.1)
+    gamma, beta = 1.0 + 0.1 * rnd(c, seed=62), 0.1 * rnd(c, seed=63)
+    gran = 32 if (c // groups) % 32 == 0 else (16 if (c // groups) % 16 == 0 else 8)
+    st = ops.Stats(r, tp, c, gran, "cuda")
+    y = torch.zeros_like(xs)
+    z = torch.zeros_like(xs)
+    ops.bias_add(xs, c, 0, y, c, 0, bias, r * tp, tp, t, c, st)
+    ops.gn_apply(y, c, z, c, st, gamma, beta, r, tp, t, c, groups)
+    torch.cuda.synchronize()
+    yf = from_slab(y, r, tp, t, c)
+    ref = F.silu(F.group_norm(yf, groups, gamma, beta, 1e-5))
+    assert_close(from_slab(z, r, tp, t, c), ref, 6e-3, "gn_apply")
+    assert pads_are_zero(z, r, tp, t)
+
+
+@pytest.mark.parametrize("r,t_lo,cin,cout,skip", [(2, 64, 128, 128, 64), (3, 129, 256, 128, 128),
+                                                    (2, 16, 192, 64, 64)])
+def test_conv_transpose_k4s2_as_two_k3_gemms(ops, r, t_lo, cin, cout, skip):
+    """ConvTranspose1d k4 s2 p1 (legacy models/unet1d.py:105) = an even-slot and an odd-slot k3
+    GEMM writing one row pair of the [M_lo, 2 * ld] view of the level-above concat slab; the
+    statistics of both launches land in disjoint slice ranges and feed gn_apply."""
+    from lm2a_b200.engine import _convT_w, _finish
+    tp_lo, tp_hi = t_lo + 1, 2 * (t_lo + 1)
+    t_hi = 2 * t_lo + 1          # the skip is one frame longer (129 vs 2 * 64): F.pad path
+    ld = cout + skip
+    x = rnd(r, cin, t_lo, seed=70)
+    w = rnd(cin, cout, 4, seed=71, scale=1.0 / math.sqrt(2 * cin))
+    b = rnd(cout, seed=72, scale=0.1)
+    xs = to_slab(x, tp_lo)
+    even, odd = _convT_w(w)
+    we, bias = _finish(even, b.double(), "cuda")
+    wo, _ = _finish(odd, b.double(), "cuda")
+    cat = torch.zeros(r * tp_hi, ld, dtype=BF16, device="cuda")
+    cat[:, cout:] = 1.0   # the skip half must survive untouched
+    ns_lo = tp_lo // 32 + 2
+    st = ops.Stats(r, tp_hi, ld, 8, "cuda", ns=max(tp_hi // 32 + 2, 2 * ns_lo))
+    for half, wt in enumerate((we, wo)):
+        d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, r * tp_lo)], wt, bias, cout,
+                               r * tp_lo, tp_lo, t_lo, cat, 2 * ld, out_chan_off=half * ld,
+                               stats=st.view(0, 0, half * ns_lo))
+        ops.conv1d(d)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose1d(bf(x), bf(w), b, stride=2, padding=1)       # [r, cout, 2 * t_lo]
+    got = from_slab(cat, r, tp_hi, 2 * t_lo, cout)
+    assert_close(got, ref, 1e-2, "conv transpose")
+    v = cat.view(r, tp_hi, ld)
+    assert bool((v[:, 2 * t_lo:, :cout] == 0).all()), "slots past 2*T_lo must be zero (F.pad)"
+    assert bool((v[:, :, cout:] == 1.0).all()), "skip half overwritten"
+    # statistics of the h half: GroupNorm over [cout] channels of the written slab
+    gamma, beta = torch.ones(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    z = torch.zeros(r * tp_hi, cout, dtype=BF16, device="cuda")
+    ops.gn_apply(cat, ld, z, cout, st, gamma, beta, r, tp_hi, t_hi, cout, 8, silu=False)
+    torch.cuda.synchronize()
+    hpad = F.pad(got, (0, 1))
+    refn = F.group_norm(hpad, 8, gamma, beta, 1e-5)
+    assert_close(from_slab(z, r, tp_hi, t_hi, cout), refn, 6e-3, "convT stats -> gn_apply")
 
 
 def test_upsample2x(ops):

@@ -40,6 +40,29 @@ def test_unet_forward_matches_reference(golden_dir, name):
     assert _rel(eps64.numpy(), d["eps"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["legacy_b128", "legacy_b256"])
+def test_legacy_unet_forward_matches_reference(golden_dir, name):
+    """Legacy UNet1D (reference models/unet1d.py) — fixtures written by
+    oracle/make_golden_legacy.py from the reference module itself."""
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    a = [int(v) for v in d["cfg"]]
+    cfg = orc.LegacyConfig(a[0], a[1], tuple(a[4:]), a[2], a[3])
+    sd = orc.legacy_random_state_dict(cfg, int(d["seed"]))
+    x, t = torch.from_numpy(d["x"]), torch.from_numpy(d["t"])
+    mf, tf = torch.from_numpy(d["motion_f"]), torch.from_numpy(d["text_f"])
+    with torch.no_grad():
+        eps = orc.legacy_unet_forward(sd, cfg, x, t, mf, tf)
+        eps0 = orc.legacy_unet_forward(sd, cfg, x, t, mf * 0, tf * 0)
+    assert _rel(eps.numpy(), d["eps"]) < 2e-5
+    assert _rel(eps0.numpy(), d["eps_zero"]) < 2e-5
+
+
+def test_legacy_state_dict_inventory():
+    # SURVEY.md §8 a15: 88.2 M parameters at base_dim = 256
+    spec = orc.legacy_state_dict_spec(orc.LegacyConfig(80, 256, (1, 2, 4), 128, 256))
+    assert abs(sum(int(np.prod(s)) for _, s in spec) - 88.2e6) < 0.1e6
+
+
 def test_state_dict_spec_matches_production_inventory():
     # SURVEY.md §0.4: 134 292 816 params in 306 tensors for the production config
     spec = orc.state_dict_spec(orc.UNetConfig.production())
