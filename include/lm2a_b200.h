@@ -183,6 +183,17 @@ int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t batch,
 /* fp32 [rows, t, c] -> bf16 slab [rows, tp, ld] (channels >= c zero)        */
 int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t rows,
                     int32_t t, int32_t c, int32_t tp, int32_t ld);
+/* match_len(arr, t_out, mode='interp') of the reference (datasetcode/dataset.py:
+ * 49-87, called at sample.py:124-125) for a padded batch: x fp32 [rows, t_in_max, c],
+ * lens[r] (NULL = t_in_max) valid frames of row r. Per feature
+ * np.interp(linspace(0, len-1, t_out), arange(len), x[:, d]) evaluated in fp64 with
+ * numpy's operation order, cast to fp32: bit-identical to the host code. Writes
+ * out_f32 [rows, t_out, c] and / or the bf16 slab [rows, tp, ld] (pad zeroed) the
+ * CondProjection GEMM reads; either may be NULL.                              */
+int lm2a_resample_seq(void* stream, const float* x, const int32_t* lens,
+                      float* out_f32, void* out_slab, int32_t rows,
+                      int32_t t_in_max, int32_t c, int32_t t_out, int32_t tp,
+                      int32_t ld);
 /* linear x2, align_corners=True: [R, tp_in, ld_in] (t_in valid) ->
  * [R, tp_out, ld_out] (2*t_in valid, rest zero)                             */
 int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,

@@ -62,6 +62,8 @@ SIGNATURES = {
                                 c_int32, c_int32, c_int32]),
     "lm2a_ingest_seq": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_int32, c_int32]),
+    "lm2a_resample_seq": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                    c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lm2a_upsample2x_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                        c_int32, c_int32, c_int32, c_int32]),
     "lm2a_bias_add_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,

@@ -55,6 +55,52 @@ ingest_seq_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab,
 }
 
 // ---------------------------------------------------------------------------
+// Condition resampling to the mel length: match_len(arr, T, mode='interp') of the reference
+// (datasetcode/dataset.py:49-87 -> interpolate_seq, called from sample.py:124-125), i.e. per
+// feature np.interp(linspace(0, L-1, T), arange(L), arr[:, d]) cast to float32. The arithmetic
+// follows numpy step by step in fp64 with explicit round-to-nearest ops (no FMA contraction):
+//   step = (L-1)/(T-1); x = i*step, x[T-1] = L-1; j = floor(x);
+//   y = (f[j+1]-f[j]) * (x - j) + f[j]   (f[L-1] when j == L-1)
+// so the fp32 result is bit-identical to the host code. Optionally also writes the bf16 slab
+// the CondProjection GEMM consumes (channels >= c and slots >= t_out zeroed).
+__global__ void __launch_bounds__(256)
+resample_seq_kernel(const float* __restrict__ x, const int* __restrict__ lens,
+                    float* __restrict__ out, __nv_bfloat16* __restrict__ slab, long long total,
+                    int t_in_max, int c, int t_out, int tp, int ld) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cc = (int)(i % ld);
+  const long long slot = i / ld;
+  const int t = (int)(slot % tp);
+  const int r = (int)(slot / tp);
+  float v = 0.f;
+  if (t < t_out && cc < c) {
+    const int len = lens != nullptr ? lens[r] : t_in_max;
+    const float* f = x + (size_t)r * t_in_max * c + cc;
+    if (len == t_out) {
+      v = __ldg(f + (size_t)t * c);
+    } else {
+      const double stop = (double)(len - 1);
+      const double step = t_out > 1 ? __ddiv_rn(stop, (double)(t_out - 1)) : 0.0;
+      const double xn = (t == t_out - 1 && t_out > 1) ? stop : __dmul_rn((double)t, step);
+      int j = (int)xn;
+      if (j >= len - 1) {
+        v = __ldg(f + (size_t)(len - 1) * c);
+      } else {
+        const double f0 = (double)__ldg(f + (size_t)j * c);
+        const double f1 = (double)__ldg(f + (size_t)(j + 1) * c);
+        const double slope = __dsub_rn(f1, f0);
+        v = __double2float_rn(__dadd_rn(__dmul_rn(slope, __dsub_rn(xn, (double)j)), f0));
+      }
+    }
+    if (out != nullptr) out[((size_t)r * t_out + t) * c + cc] = v;
+  }
+  if (slab != nullptr) slab[i] = __float2bfloat16_rn(v);
+}
+
+// ---------------------------------------------------------------------------
 // F.interpolate(scale_factor=2, mode='linear', align_corners=True) on a slab:
 // src = i * (T-1)/(2T-1); out = (1-w) x[floor(src)] + w x[min(floor(src)+1, T-1)]
 // (reference models/unet1d_ultimate.py:231-236).
@@ -435,6 +481,25 @@ extern "C" int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t
   const int blocks = (int)((total + 255) / 256);
   LM2A_CUDA_OK(launch_kernel(ingest_seq_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(slab), total, t, c, tp, ld));
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_resample_seq(void* stream, const float* x, const int32_t* lens,
+                                 float* out_f32, void* out_slab, int32_t rows, int32_t t_in_max,
+                                 int32_t c, int32_t t_out, int32_t tp, int32_t ld) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && (out_f32 || out_slab), "resample_seq: null pointer");
+  LM2A_REQUIRE(rows > 0 && t_in_max > 0 && c > 0 && t_out > 0 && tp >= t_out && ld >= c,
+               "resample_seq: bad geometry (rows=%d t_in=%d c=%d t_out=%d tp=%d ld=%d)", rows,
+               t_in_max, c, t_out, tp, ld);
+  const long long total = (long long)rows * tp * ld;
+  const int blocks = (int)((total + 255) / 256);
+  LM2A_CUDA_OK(launch_kernel(resample_seq_kernel, dim3(blocks), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), x, lens, out_f32,
+                             reinterpret_cast<__nv_bfloat16*>(out_slab), total, t_in_max, c,
+                             t_out, tp, ld));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

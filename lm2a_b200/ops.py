@@ -169,6 +169,12 @@ def ingest_seq(x, slab, rows, t, c, tp, ld):
                "lm2a_ingest_seq")
 
 
+def resample_seq(x, lens, out_f32, out_slab, rows, t_in_max, c, t_out, tp, ld):
+    _lib.check(_lib.load().lm2a_resample_seq(_stream(), _ptr(x), _ptr(lens), _ptr(out_f32),
+                                             _ptr(out_slab), rows, t_in_max, c, t_out, tp, ld),
+               "lm2a_resample_seq")
+
+
 def upsample2x(x, x_ld, y, y_ld, rows, tp_in, t_in, tp_out, c):
     _lib.check(_lib.load().lm2a_upsample2x_bf16(_stream(), _ptr(x), x_ld, _ptr(y), y_ld, rows,
                                                 tp_in, t_in, tp_out, c), "lm2a_upsample2x_bf16")
