@@ -30,6 +30,9 @@
  *   lm2a_ingest_x      torch.cat([x, x]) + layout change, sample.py:162
  *   lm2a_cfg_posterior sample.py:167-174 (CFG blend + clamps) and
  *                      sample.py:186-210 == models/diffusion.py:71-102
+ *   lm2a_cfg_ddim      models/diffusion.py:124-165 (ddim_sample)
+ *   lm2a_resample_seq  datasetcode/dataset.py:49-87 (match_len 'interp')
+ *   lm2a_mel_metrics   val.py:25-113 (compute_metrics)
  */
 #ifndef LM2A_B200_H
 #define LM2A_B200_H
@@ -224,6 +227,32 @@ int lm2a_cfg_posterior(void* stream, float* x, const float* eps,
                        int64_t* t_dev, int32_t n_t, uint32_t* ticket,
                        int32_t batch, int64_t elems_per_clip, float guidance,
                        int32_t guided, int32_t advance, float* eps_out);
+
+/* ---- CFG blend + DDIM update over a strided timestep sequence ------------- */
+/* Reference models/diffusion.py:124-165 (ddim_sample; never called by the
+ * reference's own loop). table: fp32 [steps, 8] rows {sqrt(1-abar_t), sqrt(abar_t),
+ * sqrt(abar_prev), sqrt(1-abar_prev-sigma^2), sigma, (t_prev > 0), 0, 0} built by
+ * the caller with the reference's expressions; step_idx: device int32 selecting
+ * the row. x0 = clamp((x - eps*c0)/c1, -2, 2); x <- (c2*x0 + c3*eps) + sigma*z.
+ * advance != 0: the last block sets every t_dev entry to t_seq[step+1] (int64
+ * [steps+1], the UNet's next timestep) and increments *step_idx. x0_out
+ * (optional) receives the clamped x0 prediction. eps / guidance as in
+ * lm2a_cfg_posterior.                                                        */
+int lm2a_cfg_ddim(void* stream, float* x, const float* eps, const float* noise,
+                  const float* table, const int64_t* t_seq, int32_t* step_idx,
+                  int64_t* t_dev, int32_t n_t, uint32_t* ticket, int32_t batch,
+                  int64_t elems_per_clip, float guidance, int32_t guided,
+                  int32_t advance, float* x0_out);
+
+/* ---- mel evaluation metrics ------------------------------------------------ */
+/* Reference val.py:25-113 (compute_metrics) for a batch: gen / real fp32
+ * [B, n_mels, T]; gen is de-normalised on the fly (gen * gen_scale + gen_shift,
+ * sample.py:230; pass 1, 0 for an already de-normalised mel). out: fp64 [B, 8]
+ * {mse, ssim, avg_cos_sim, mean_error, std_error, snr, real_var, 0}; the host
+ * rounds to 6 decimals as val.py:106-113 does. T >= 11 (SSIM window).          */
+int lm2a_mel_metrics(void* stream, const float* gen, const float* real,
+                     double* out, int32_t batch, int32_t n_mels, int32_t t,
+                     float gen_scale, float gen_shift);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,11 @@ SIGNATURES = {
     "lm2a_cfg_posterior": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_int32, c_int64, c_float, c_int32,
                                      c_int32, c_void_p]),
+    "lm2a_cfg_ddim": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_float,
+                                c_int32, c_int32, c_void_p]),
+    "lm2a_mel_metrics": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                   c_int32, c_float, c_float]),
 }
 
 _lib = None

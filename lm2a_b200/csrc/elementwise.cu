@@ -454,6 +454,220 @@ cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
   }
 }
 
+// ---------------------------------------------------------------------------
+// CFG blend + DDIM update (reference models/diffusion.py:124-165, `ddim_sample`) over a
+// strided timestep sequence. Row k of `table` (fp32 x 8) holds, for step k of the sequence,
+//   {sqrt(1 - abar_t), sqrt(abar_t), sqrt(abar_prev), sqrt(1 - abar_prev - sigma^2), sigma,
+//    noise gate (1 if t_prev > 0 else 0), 0, 0}
+// computed by the caller with the reference's torch expressions, so with the same eps and
+// noise the result is bit-identical to the torch op sequence (explicit rn ops, no FMA):
+//   x0 = clamp((x - eps * c0) / c1, -2, 2);  x = (c2 * x0 + c3 * eps) + sigma * z
+// The last CTA advances the device-side step index and loads the next timestep of the
+// sequence into t_dev (graph replay needs no host).
+__global__ void __launch_bounds__(256)
+cfg_ddim_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                const float* __restrict__ noise, const float* __restrict__ table,
+                const int64_t* __restrict__ t_seq, int* __restrict__ step_idx,
+                int64_t* __restrict__ t_dev, int n_t, unsigned int* __restrict__ ticket,
+                long long total_vec, long long clip_vec, int batch, float gw, int guided,
+                int advance, float* __restrict__ x0_out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int k = *step_idx;
+  const float4 ca = __ldg(reinterpret_cast<const float4*>(table) + 2 * k);
+  const float4 cb = __ldg(reinterpret_cast<const float4*>(table) + 2 * k + 1);
+  const float c0 = ca.x, c1 = ca.y, c2 = ca.z, c3 = ca.w, sigma = cb.x;
+  const bool add_noise = cb.y != 0.f && noise != nullptr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long uncond_to_cond = (long long)batch * clip_vec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += stride) {
+    const float4 xv4 = reinterpret_cast<const float4*>(x)[i];
+    float e[4];
+    if (guided) {
+      const float4 eu = __ldg(reinterpret_cast<const float4*>(eps) + i);
+      const float4 ec = __ldg(reinterpret_cast<const float4*>(eps) + i + uncond_to_cond);
+      const float u[4] = {eu.x, eu.y, eu.z, eu.w};
+      const float c[4] = {ec.x, ec.y, ec.z, ec.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float d = __fsub_rn(c[q], u[q]);
+        d = fminf(fmaxf(d, -5.0f), 5.0f);
+        const float g = __fadd_rn(u[q], __fmul_rn(gw, d));
+        e[q] = fminf(fmaxf(g, -10.0f), 10.0f);
+      }
+    } else {
+      const float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
+      e[0] = ev.x; e[1] = ev.y; e[2] = ev.z; e[3] = ev.w;
+    }
+    float4 nz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add_noise) nz = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+    const float zv[4] = {nz.x, nz.y, nz.z, nz.w};
+    float o[4], x0[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float p0 = __fdiv_rn(__fsub_rn(xv[q], __fmul_rn(e[q], c0)), c1);
+      p0 = fminf(fmaxf(p0, -2.0f), 2.0f);
+      x0[q] = p0;
+      o[q] = __fadd_rn(__fadd_rn(__fmul_rn(c2, p0), __fmul_rn(c3, e[q])),
+                       __fmul_rn(sigma, zv[q]));
+    }
+    reinterpret_cast<float4*>(x)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (x0_out != nullptr)
+      reinterpret_cast<float4*>(x0_out)[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+  }
+  if (advance) {
+    __shared__ unsigned int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int done = atomicAdd(ticket, 1u);
+      is_last = (done == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (is_last) {
+      const int64_t t_next = t_seq[k + 1];
+      for (int q = threadIdx.x; q < n_t; q += blockDim.x) t_dev[q] = t_next;
+      if (threadIdx.x == 0) {
+        *step_idx = k + 1;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Mel-spectrogram evaluation metrics of reference val.py:25-113 (`compute_metrics`), one CTA
+// per clip, fp64 accumulation: MSE, SSIM (skimage.metrics.structural_similarity as val.py
+// calls it: per mel band 1-D, Gaussian window sigma 1.5 / radius 5, data_range 1, population
+// covariance, border of 5 frames cropped, mean over bands; inputs min-max normalised with the
+// REAL mel's range and clipped to [0, 1]), mean frame cosine, |mean error|, |std error|, SNR.
+// gen is de-normalised on the fly (gen * std + mean, sample.py:230). out: fp64 [B, 8]
+// {mse, ssim, avg_cos_sim, mean_error, std_error, snr, real_var, 0}.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];  // fixed order
+  return t;
+}
+__device__ __forceinline__ float block_minmax(float v, bool is_max, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : fminf(v, u);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = is_max ? fmaxf(t, red[w]) : fminf(t, red[w]);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+mel_metrics_kernel(const float* __restrict__ gen, const float* __restrict__ real,
+                   double* __restrict__ out, int n_mels, int T, float g_scale, float g_shift) {
+  __shared__ double red[8];
+  __shared__ float redf[8];
+  const int b = blockIdx.x;
+  const float* g = gen + (size_t)b * n_mels * T;
+  const float* r = real + (size_t)b * n_mels * T;
+  const int n = n_mels * T;
+  double se = 0.0, sr = 0.0, srr = 0.0, sg = 0.0, sgg = 0.0;
+  float rmin = INFINITY, rmax = -INFINITY, gmin = INFINITY, gmax = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float rv = r[i];
+    const float gv = __fadd_rn(__fmul_rn(g[i], g_scale), g_shift);
+    const double d = (double)rv - (double)gv;
+    se += d * d;
+    sr += rv; srr += (double)rv * rv;
+    sg += gv; sgg += (double)gv * gv;
+    rmin = fminf(rmin, rv); rmax = fmaxf(rmax, rv);
+    gmin = fminf(gmin, gv); gmax = fmaxf(gmax, gv);
+  }
+  se = block_sum(se, red);
+  sr = block_sum(sr, red); srr = block_sum(srr, red);
+  sg = block_sum(sg, red); sgg = block_sum(sgg, red);
+  rmin = block_minmax(rmin, false, redf); rmax = block_minmax(rmax, true, redf);
+  gmin = block_minmax(gmin, false, redf); gmax = block_minmax(gmax, true, redf);
+  // frame cosine (sklearn cosine_similarity of the two 80-vectors of a frame), averaged
+  double cs = 0.0;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    double ab = 0.0, aa = 0.0, bb = 0.0;
+    for (int c = 0; c < n_mels; ++c) {
+      const double rv = r[(size_t)c * T + t];
+      const double gv = __fadd_rn(__fmul_rn(g[(size_t)c * T + t], g_scale), g_shift);
+      ab += rv * gv; aa += rv * rv; bb += gv * gv;
+    }
+    const double na = sqrt(aa), nb = sqrt(bb);
+    cs += ab / ((na == 0.0 ? 1.0 : na) * (nb == 0.0 ? 1.0 : nb));
+  }
+  cs = block_sum(cs, red);
+  // SSIM
+  float lo = rmin, hi = rmax;
+  if (hi - lo < 1e-6f) {
+    lo = fminf(rmin, gmin);
+    hi = fmaxf(rmax, gmax);
+  }
+  const double inv_range = 1.0 / ((double)hi - (double)lo + 1e-8);
+  double w[11];
+  {
+    double ws = 0.0;
+    for (int k = -5; k <= 5; ++k) {
+      w[k + 5] = exp(-0.5 * (double)(k * k) / (1.5 * 1.5));
+      ws += w[k + 5];
+    }
+    for (int k = 0; k < 11; ++k) w[k] /= ws;
+  }
+  const double C1 = 0.01 * 0.01, C2 = 0.03 * 0.03;
+  const int span = T - 10;  // frames 5 .. T-6 survive the crop
+  double ss = 0.0;
+  if (span > 0) {
+    for (int i = threadIdx.x; i < n_mels * span; i += blockDim.x) {
+      const int c = i / span, t = 5 + i % span;
+      double ux = 0, uy = 0, uxx = 0, uyy = 0, uxy = 0;
+#pragma unroll
+      for (int k = 0; k < 11; ++k) {
+        const size_t idx = (size_t)c * T + t - 5 + k;
+        double xv = ((double)r[idx] - (double)lo) * inv_range;
+        double yv = ((double)__fadd_rn(__fmul_rn(g[idx], g_scale), g_shift) - (double)lo) * inv_range;
+        xv = fmin(fmax(xv, 0.0), 1.0);
+        yv = fmin(fmax(yv, 0.0), 1.0);
+        ux += w[k] * xv; uy += w[k] * yv;
+        uxx += w[k] * xv * xv; uyy += w[k] * yv * yv; uxy += w[k] * xv * yv;
+      }
+      const double vx = uxx - ux * ux, vy = uyy - uy * uy, vxy = uxy - ux * uy;
+      ss += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+    }
+  }
+  ss = block_sum(ss, red);
+  if (threadIdx.x == 0) {
+    const double inv = 1.0 / (double)n;
+    const double mse = se * inv;
+    const double mr = sr * inv, mg = sg * inv;
+    double vr = srr * inv - mr * mr, vg = sgg * inv - mg * mg;
+    vr = vr > 0 ? vr : 0; vg = vg > 0 ? vg : 0;
+    double ssim = span > 0 ? ss / ((double)n_mels * span) : 0.0;
+    ssim = fmin(fmax(ssim, 0.0), 1.0);
+    double* o = out + (size_t)b * 8;
+    o[0] = mse;
+    o[1] = ssim;
+    o[2] = cs / (double)T;
+    o[3] = fabs(mr - mg);
+    o[4] = fabs(sqrt(vr) - sqrt(vg));
+    o[5] = vr < 1e-8 ? 0.0 : 10.0 * log10(vr / (mse + 1e-8));
+    o[6] = vr;
+    o[7] = 0.0;
+  }
+}
+
 }  // namespace
 }  // namespace lm2a
 
@@ -637,6 +851,49 @@ extern "C" int lm2a_cfg_posterior(void* stream, float* x, const float* eps, cons
   LM2A_CUDA_OK(launch_kernel(cfg_posterior_kernel, dim3((int)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, eps, noise, sched, t_dev, n_t, ticket, total_vec, clip_vec, batch, guidance, guided,
       advance, eps_out));
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_cfg_ddim(void* stream, float* x, const float* eps, const float* noise,
+                             const float* table, const int64_t* t_seq, int32_t* step_idx,
+                             int64_t* t_dev, int32_t n_t, uint32_t* ticket, int32_t batch,
+                             int64_t elems_per_clip, float guidance, int32_t guided,
+                             int32_t advance, float* x0_out) {
+  using namespace lm2a;
+  LM2A_REQUIRE(x && eps && table && step_idx, "cfg_ddim: null pointer");
+  LM2A_REQUIRE(batch > 0 && elems_per_clip > 0 && elems_per_clip % 4 == 0,
+               "cfg_ddim: elems_per_clip must be a positive multiple of 4");
+  LM2A_REQUIRE(!advance || (ticket != nullptr && t_seq != nullptr && t_dev != nullptr && n_t > 0),
+               "cfg_ddim: advance needs ticket, t_seq, t_dev and n_t > 0");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
+                 reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(table) |
+                 reinterpret_cast<uintptr_t>(x0_out)) & 15) == 0,
+               "cfg_ddim: tensors must be 16-byte aligned");
+  const long long clip_vec = elems_per_clip / 4;
+  const long long total_vec = clip_vec * batch;
+  long long blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  LM2A_CUDA_OK(launch_kernel(cfg_ddim_kernel, dim3((int)blocks), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), x, eps, noise, table, t_seq,
+                             step_idx, t_dev, n_t, ticket, total_vec, clip_vec, batch, guidance,
+                             guided, advance, x0_out));
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_mel_metrics(void* stream, const float* gen, const float* real, double* out,
+                                int32_t batch, int32_t n_mels, int32_t t, float gen_scale,
+                                float gen_shift) {
+  using namespace lm2a;
+  LM2A_REQUIRE(gen && real && out, "mel_metrics: null pointer");
+  LM2A_REQUIRE(batch > 0 && n_mels > 0 && t > 0, "mel_metrics: bad geometry");
+  LM2A_REQUIRE(t >= 11, "mel_metrics: SSIM window (11 frames) exceeds the clip length %d", t);
+  LM2A_CUDA_OK(launch_kernel(mel_metrics_kernel, dim3(batch), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), gen, real, out, n_mels, t,
+                             gen_scale, gen_shift));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

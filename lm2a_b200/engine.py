@@ -672,6 +672,21 @@ class UNetPlan:
             fn(*args)
         self.kv_slot.copy_(kv_slot.to(torch.int32))
 
+    def cond_slabs(self, first_slot=0):
+        """bf16 views [ (nslots - first_slot) * lk, cond_dim ] of the motion / lyrics condition
+        slabs from cache slot `first_slot` on: CondProjection.project_raw writes the projected
+        conditions straight into them; `build_kv` then builds the caches."""
+        assert self.use_cond
+        o = first_slot * self.lk
+        return self.cond_m[o:], self.cond_t[o:]
+
+    def build_kv(self, kv_slot):
+        """K/V cache build from the condition slabs as they are (see cond_slabs)."""
+        assert self.use_cond
+        for fn, args in self.kv_ops:
+            fn(*args)
+        self.kv_slot.copy_(kv_slot.to(torch.int32))
+
     def run(self):
         """Launches the plan on torch's current stream. Ops tagged `side` (the uncond rows'
         `skip(x) + const` kernels and the timestep / FiLM tables: small launches that nothing

@@ -87,28 +87,65 @@ class GaussianDiffusion:
             x = self.p_sample(x, t_batch, motion_f, text_f)
         return x
 
-    def ddim_sample(self, x, t, t_prev, eps, eta=0.0):
-        """diffusion.py:124-165 (the reference marks it undebugged and never calls it; kept
-        for API parity, elementwise torch)."""
-        one = torch.tensor(1.0, device=x.device)
+    def ddim_coefficients(self, t, t_prev, eta=0.0):
+        """The five scalars of one DDIM update, evaluated with the reference's own expressions
+        (diffusion.py:125-157) in fp32 on `device`: one row of lm2a_cfg_ddim's table
+        {sqrt(1-abar_t), sqrt(abar_t), sqrt(abar_prev), sqrt(1-abar_prev-sigma^2), sigma,
+        noise gate, 0, 0}."""
+        one = torch.tensor(1.0, device=self.alpha_bars.device)
         abar_prev = one if t_prev < 0 else self.alpha_bars[t_prev]
         abar = one if t < 0 else self.alpha_bars[t]
-        abar, abar_prev = abar[..., None, None], abar_prev[..., None, None]
-        x0_pred = torch.clamp((x - eps * torch.sqrt(1 - abar)) / torch.sqrt(abar), -2.0, 2.0)
         sigma = eta * torch.sqrt((1 - abar_prev) / (1 - abar) * (1 - abar / abar_prev))
         sigma = torch.nan_to_num(sigma, nan=0.0, posinf=0.0, neginf=0.0)
-        noise = torch.randn_like(x) if t_prev > 0 else torch.zeros_like(x)
-        x_prev = (torch.sqrt(abar_prev) * x0_pred
-                  + torch.sqrt(1 - abar_prev - sigma ** 2) * eps + sigma * noise)
+        zero = torch.zeros_like(one)
+        return torch.stack([torch.sqrt(1 - abar), torch.sqrt(abar), torch.sqrt(abar_prev),
+                            torch.sqrt(1 - abar_prev - sigma ** 2), sigma,
+                            one if t_prev > 0 else zero, zero, zero]).float()
+
+    @torch.no_grad()
+    def ddim_sample(self, x, t, t_prev, eps, eta=0.0):
+        """One DDIM update (x_t, eps) -> (x_{t_prev}, clamped x0 prediction); same signature
+        and arithmetic as reference diffusion.py:124-165, executed by lm2a_cfg_ddim. Draws
+        randn_like(x) only when t_prev > 0, like the reference."""
+        ops.require_device(x)
+        table = self.ddim_coefficients(int(t), int(t_prev), eta).contiguous()
+        noise = torch.randn_like(x) if t_prev > 0 else None
+        x_prev = x.contiguous().float().clone()
+        x0_pred = torch.empty_like(x_prev)
+        step = torch.zeros(1, dtype=torch.int32, device=x.device)
+        ops.cfg_ddim(x_prev, eps.contiguous().float(), noise, table, None, step, None, None,
+                     x.size(0), x[0].numel(), 1.0, False, False, x0_pred)
         return x_prev, x0_pred
 
+    def ddim_timesteps(self, num_steps):
+        """Strided sub-sequence of the T training timesteps, descending from T-1 to 0."""
+        num_steps = max(1, min(int(num_steps), self.T))
+        taus = torch.linspace(self.T - 1, 0, num_steps).round().long().tolist()
+        out = []
+        for t in taus:  # strictly decreasing (rounding can repeat a value when S ~ T)
+            if not out or t < out[-1]:
+                out.append(int(t))
+        return out
+
+    @torch.no_grad()
+    def sample_ddim(self, shape, motion_f, text_f, num_steps=50, eta=0.0, guidance_weight=1.0,
+                    x_init=None, noises=None, use_graph=True, report=None):
+        """Few-step sampling: the CFG loop of sample.py:144-210 with the posterior
+        update replaced by `ddim_sample` over `ddim_timesteps(num_steps)`; step i goes from
+        tau_i to tau_{i+1} (t_prev = -1 after the last). Same graph-replayed launch sequence as
+        sample_cfg, num_steps model evaluations instead of T."""
+        bsz, _, t_len = shape
+        s = self.sampler(bsz, t_len, motion_f.shape[1], guidance_weight > 1.0,
+                         ddim=(tuple(self.ddim_timesteps(num_steps)), float(eta)))
+        return s.run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report)
+
     # ---- batched classifier-free-guided sampling (sample.py:131-225, any B) -----------
-    def sampler(self, batch, t_len, lk, guided=True, uncond_shortcut=None):
+    def sampler(self, batch, t_len, lk, guided=True, uncond_shortcut=None, ddim=None):
         if uncond_shortcut is None:
             uncond_shortcut = self.uncond_shortcut
-        key = (batch, t_len, lk, bool(guided), bool(uncond_shortcut))
+        key = (batch, t_len, lk, bool(guided), bool(uncond_shortcut), ddim)
         if key not in self._samplers:
-            self._samplers[key] = CfgSampler(self, batch, t_len, lk, guided, uncond_shortcut)
+            self._samplers[key] = CfgSampler(self, batch, t_len, lk, guided, uncond_shortcut, ddim)
         return self._samplers[key]
 
     @torch.no_grad()
@@ -129,8 +166,11 @@ class GaussianDiffusion:
 class CfgSampler:
     """State + CUDA Graph of the per-step launch sequence for a fixed (B, T, Lk)."""
 
-    def __init__(self, diffusion, batch, t_len, lk, guided, uncond_shortcut=True):
+    def __init__(self, diffusion, batch, t_len, lk, guided, uncond_shortcut=True, ddim=None):
         self.d = diffusion
+        # ddim = (descending timestep tuple, eta): DDIM updates over that sub-sequence instead
+        # of the T-step DDPM posterior
+        self.ddim = ddim
         self.batch, self.t_len, self.lk, self.guided = batch, t_len, lk, guided
         eng = diffusion.model.engine()
         self.dev = eng.dev
@@ -145,6 +185,15 @@ class CfgSampler:
         self.gw = 1.0
         self.graph = None
         self.graph_gw = None
+        if ddim is not None:
+            taus, eta = ddim
+            prevs = list(taus[1:]) + [-1]
+            self.taus, self.eta = list(taus), eta
+            self.table = torch.stack([diffusion.ddim_coefficients(t, tp, eta)
+                                      for t, tp in zip(taus, prevs)]).to(self.dev).contiguous()
+            self.t_seq = torch.tensor(list(taus) + [0], dtype=torch.int64, device=self.dev)
+            self.step_idx = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            self.noise_gate = [eta > 0 and tp > 0 for tp in prevs]
         if guided:  # rows [0, B) uncond -> slot 0 (zero conditions); rows [B, 2B) -> 1 + b
             self.kv_slot = torch.cat([torch.zeros(batch, dtype=torch.int32),
                                       torch.arange(1, batch + 1, dtype=torch.int32)]).to(self.dev)
@@ -158,61 +207,92 @@ class CfgSampler:
             text_f = torch.cat([z, text_f], dim=0)
         self.plan.set_conditions(motion_f, text_f, self.kv_slot)
 
+    def cond_slabs(self):
+        """Where CondProjection.project_raw should write the B clips' projected conditions (the
+        zero slot of the uncond rows, if any, sits in front and is left untouched)."""
+        return self.plan.cond_slabs(1 if self.guided else 0)
+
     def _step(self, draw_noise):
         p = self.plan
         if draw_noise:
             self.noise.normal_()
         p.run()
-        ops.cfg_posterior(p.x_in, p.eps, self.noise, self.d.sched, p.t_in, self.ticket, self.batch,
-                          p.x_in[0].numel(), self.gw, self.guided, True)
+        if self.ddim is None:
+            ops.cfg_posterior(p.x_in, p.eps, self.noise, self.d.sched, p.t_in, self.ticket,
+                              self.batch, p.x_in[0].numel(), self.gw, self.guided, True)
+        else:
+            ops.cfg_ddim(p.x_in, p.eps, self.noise if self.eta > 0 else None, self.table,
+                         self.t_seq, self.step_idx, p.t_in, self.ticket, self.batch,
+                         p.x_in[0].numel(), self.gw, self.guided, True)
+
+    def _reset_clock(self):
+        """Device-side step state at the start of a trajectory."""
+        if self.ddim is None:
+            self.plan.t_in.fill_(self.d.T - 1)
+        else:
+            self.plan.t_in.fill_(self.taus[0])
+            self.step_idx.zero_()
 
     def _ensure_graph(self):
         if self.graph is not None and self.graph_gw == self.gw:
             return
         p = self.plan
-        keep_x, keep_t = p.x_in.clone(), p.t_in.clone()
+        keep_x = p.x_in.clone()
+        draw = self.ddim is None or self.eta > 0
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
-            p.t_in.fill_(self.d.T - 1)
-            self._step(True)  # warm-up outside capture: first-launch attribute setup
+            self._reset_clock()
+            self._step(draw)  # warm-up outside capture: first-launch attribute setup
         torch.cuda.current_stream(self.dev).wait_stream(side)
         g = torch.cuda.CUDAGraph()
-        p.t_in.fill_(self.d.T - 1)
+        self._reset_clock()
         with torch.cuda.graph(g):
-            self._step(True)
+            self._step(draw)
         p.x_in.copy_(keep_x)
-        p.t_in.copy_(keep_t)
         self.ticket.zero_()
         self.graph, self.graph_gw = g, self.gw
 
     @torch.no_grad()
     def run(self, motion_f, text_f, guidance_weight=1.0, x_init=None, noises=None,
             use_graph=True, report=None):
+        """motion_f / text_f None: the condition slabs were already filled in place
+        (cond_slabs + CondProjection.project_raw); only the K/V caches are (re)built."""
         d, p = self.d, self.plan
-        steps = d.T
+        steps = d.T if self.ddim is None else len(self.taus)
         self.gw = float(guidance_weight)
-        self.set_conditions(motion_f, text_f)
+        if motion_f is None and text_f is None:
+            if self.guided:
+                p.cond_m[: self.lk].zero_()
+                p.cond_t[: self.lk].zero_()
+            p.build_kv(self.kv_slot)
+        else:
+            self.set_conditions(motion_f, text_f)
         if x_init is None:
             x_init = torch.randn((self.batch, p.x_in.shape[1], self.t_len), device=self.dev)
         injected = noises is not None
         if use_graph and not injected:
             self._ensure_graph()
         p.x_in.copy_(x_init)
-        p.t_in.fill_(steps - 1)
+        self._reset_clock()
         interval = max(1, steps // 10)
         for i in range(steps):
-            t = steps - 1 - i
+            if self.ddim is None:
+                t = steps - 1 - i
+                needs_noise = t > 0
+            else:
+                t = self.taus[i]
+                needs_noise = self.noise_gate[i]
             if injected:
-                if t > 0:
+                if needs_noise:
                     nz = noises(i) if callable(noises) else noises[i]
                     self.noise.copy_(nz)
                 self._step(False)
             elif use_graph:
                 self.graph.replay()
             else:
-                self._step(t > 0)
-            if report is not None and (i % interval == 0 or t == 0):
+                self._step(needs_noise)
+            if report is not None and (i % interval == 0 or i == steps - 1):
                 # the reference's periodic non-finite guard (sample.py:216-223); outside the graph
                 if not report(t, p.x_in):
                     break

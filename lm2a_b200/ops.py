@@ -188,6 +188,21 @@ def cfg_posterior(x, eps, noise, sched, t_dev, ticket, batch, elems_per_clip, gu
         1 if advance else 0, _ptr(eps_out)), "lm2a_cfg_posterior")
 
 
+def cfg_ddim(x, eps, noise, table, t_seq, step_idx, t_dev, ticket, batch, elems_per_clip,
+             guidance, guided, advance, x0_out=None):
+    _lib.check(_lib.load().lm2a_cfg_ddim(
+        _stream(), _ptr(x), _ptr(eps), _ptr(noise), _ptr(table), _ptr(t_seq), _ptr(step_idx),
+        _ptr(t_dev), t_dev.numel() if t_dev is not None else 0, _ptr(ticket), batch,
+        elems_per_clip, float(guidance), 1 if guided else 0, 1 if advance else 0, _ptr(x0_out)),
+        "lm2a_cfg_ddim")
+
+
+def mel_metrics(gen, real, out, batch, n_mels, t, gen_scale=1.0, gen_shift=0.0):
+    _lib.check(_lib.load().lm2a_mel_metrics(_stream(), _ptr(gen), _ptr(real), _ptr(out), batch,
+                                            n_mels, t, float(gen_scale), float(gen_shift)),
+               "lm2a_mel_metrics")
+
+
 def bias_add(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c, stats=None):
     _lib.check(_lib.load().lm2a_bias_add_bf16(
         _stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld, _ptr(bias), slots, tp, t_valid, c,

@@ -144,6 +144,46 @@ def sample_clips(unet, cond_proj, diffusion, motions, lyrics, t_len, guidance_we
     return out.numpy(), motion_f, text_f
 
 
+def _pad_batch(seqs, pinned):
+    """List of (L_i, D) host arrays -> pinned fp32 (B, L_max, D) tensor + int32 lengths."""
+    lens = [int(a.shape[0]) for a in seqs]
+    d = int(seqs[0].shape[1])
+    buf = torch.zeros(len(seqs), max(lens), d, dtype=torch.float32)
+    if pinned:
+        buf = buf.pin_memory()
+    for i, a in enumerate(seqs):
+        buf[i, : lens[i]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return buf, torch.tensor(lens, dtype=torch.int32)
+
+
+@torch.no_grad()
+def sample_clips_raw(unet, cond_proj, diffusion, motions, lyrics, t_len, guidance_weight=1.0,
+                     x_init=None, noises=None, use_graph=True, report=None, pinned=True,
+                     want_resampled=False):
+    """Batched sampling straight from the npz-shaped RAW conditions: `motions` /
+    `lyrics` are lists of HOST arrays (L_i, 234) / (L_i, 768) of any per-clip length. The
+    resampling to T = t_len (match_len 'interp'), CondProjection and the K/V cache build all
+    run on the GPU as the per-batch prologue; nothing but the padded raw sequences crosses
+    PCIe. Returns (mel_norm (B, 80, T) host fp32, extras) where extras holds the projected
+    conditions and, if `want_resampled`, the resampled fp32 sequences (device tensors)."""
+    dev = next(unet.parameters()).device
+    m, m_lens = _pad_batch(motions, pinned)
+    ly, l_lens = _pad_batch(lyrics, pinned)
+    m, ly = m.to(dev, non_blocking=True), ly.to(dev, non_blocking=True)
+    m_lens, l_lens = m_lens.to(dev, non_blocking=True), l_lens.to(dev, non_blocking=True)
+    bsz = m.shape[0]
+    s = diffusion.sampler(bsz, t_len, t_len, guidance_weight > 1.0)
+    dst_m, dst_t = s.cond_slabs()
+    mf, tf, m_rs, l_rs = cond_proj.project_raw(m, m_lens, ly, l_lens, t_len, dst_m, dst_t,
+                                               want_resampled)
+    x = s.run(None, None, guidance_weight, x_init, noises, use_graph, report)
+    out = torch.empty(x.shape, dtype=torch.float32, pin_memory=pinned)
+    out.copy_(x, non_blocking=False)
+    extras = {"motion_f": mf.view(bsz, t_len, -1), "text_f": tf.view(bsz, t_len, -1),
+              "motion_rs": m_rs, "lyrics_rs": l_rs}
+    return out.numpy(), extras
+
+
 def sample_from_npz(npz_path, ckpt_path, out_dir, device="cuda", timesteps=1000,
                     guidance_weight=1.0):
     """Same contract as reference sample.sample_from_npz (sample.py:42-278): returns the path of
@@ -173,13 +213,15 @@ def sample_from_npz(npz_path, ckpt_path, out_dir, device="cuda", timesteps=1000,
     timesteps = int(ck_steps) if ck_steps is not None else timesteps
     diffusion = GaussianDiffusion(unet, timesteps=timesteps, device=device, dataset_mean=mean,
                                   dataset_std=std)
-    motion_rs = match_len(motion, t_len, mode="interp")
-    lyrics_rs = match_len(lyrics, t_len, mode="interp")
     guidance_weight = float(ck.get("guidance_weight", guidance_weight))
 
-    mel_norm, motion_f, text_f = sample_clips(
-        unet, cond_proj, diffusion, motion_rs[None], lyrics_rs[None], t_len, guidance_weight,
-        report=_reporter())
+    # match_len(..., 'interp') (sample.py:124-125), CondProjection (:132) and the K/V cache
+    # build run on the GPU as the clip's prologue; bit-identical to the host resampling
+    mel_norm, ex = sample_clips_raw(
+        unet, cond_proj, diffusion, [np.asarray(motion)], [np.asarray(lyrics)], t_len,
+        guidance_weight, report=_reporter(), want_resampled=True)
+    motion_rs, lyrics_rs = ex["motion_rs"][0].cpu().numpy(), ex["lyrics_rs"][0].cpu().numpy()
+    motion_f, text_f = ex["motion_f"].float(), ex["text_f"].float()
     out = mel_norm[0] * std + mean  # de-normalise (sample.py:230)
 
     base = os.path.splitext(os.path.basename(npz_path))[0]

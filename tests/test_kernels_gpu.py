@@ -418,6 +418,34 @@ def test_conv_transpose_k4s2_as_two_k3_gemms(ops, r, t_lo, cin, cout, skip):
     assert_close(from_slab(z, r, tp_hi, t_hi, cout), refn, 6e-3, "convT stats -> gn_apply")
 
 
+@pytest.mark.parametrize("t_in,t_out,c", [(180, 516, 234), (516, 516, 768), (720, 2064, 234),
+                                          (1, 40, 8), (600, 77, 130), (2, 3, 5)])
+def test_resample_seq_is_bit_exact_vs_numpy_interp(ops, t_in, t_out, c):
+    """lm2a_resample_seq == the reference's interpolate_seq (np.interp per feature on
+    linspace(0, L-1, T), float32 result): bit for bit, including ragged batches."""
+    import numpy as np
+    import lm2a_oracle as orc
+    rng = np.random.default_rng(t_in * 1000 + t_out)
+    rows = 3
+    lens = [t_in, max(1, t_in // 2), max(1, t_in - 1)]
+    x = np.zeros((rows, t_in, c), np.float32)
+    for r_, ln in enumerate(lens):
+        x[r_, :ln] = rng.normal(0, 3.0, size=(ln, c)).astype(np.float32)
+    want = np.stack([orc.match_len_interp(x[r_, :ln], t_out) for r_, ln in enumerate(lens)])
+    xd = torch.from_numpy(x).cuda()
+    ld = (c + 63) // 64 * 64
+    tp = t_out + 2
+    out = torch.full((rows, t_out, c), float("nan"), device="cuda")
+    slab = torch.full((rows * tp, ld), float("nan"), dtype=BF16, device="cuda")
+    ops.resample_seq(xd, torch.tensor(lens, dtype=torch.int32, device="cuda"), out, slab, rows,
+                     t_in, c, t_out, tp, ld)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want.reshape(rows, t_out, c))
+    sv = slab.view(rows, tp, ld)
+    assert torch.equal(sv[:, :t_out, :c], out.to(BF16))
+    assert bool((sv[:, t_out:, :] == 0).all()) and bool((sv[:, :, c:] == 0).all())
+
+
 def test_upsample2x(ops):
     r, t_in, c = 3, 129, 128
     tp_in, tp_out = 130, 260

@@ -170,8 +170,107 @@ def test_sample_from_npz_file_contract(tmp_path, golden_dir):
     assert r["motion_proj"].shape == (1, t_len, 128) and r["lyrics_proj"].shape == (1, t_len, 128)
     assert int(r["sr"]) == 22050 and int(r["hop_length"]) == 256
     assert np.isfinite(r["mel"]).all()
+    # the GPU resampling prologue reproduces the reference's host match_len bit for bit
+    np.testing.assert_array_equal(r["motion"], d["motion_rs"])
+    np.testing.assert_array_equal(r["lyrics"], d["lyrics_rs"])
+    assert _rel(torch.from_numpy(r["motion_proj"]), torch.from_numpy(d["gw21_motion_proj"])) < 1e-2
     with pytest.raises(RuntimeError, match="no CPU"):
         sample.sample_from_npz(str(npz), str(ckpt), str(tmp_path / "out"), device="cpu")
+
+
+def test_raw_condition_prologue_equals_host_resampling():
+    """sample_clips_raw (ragged raw conditions -> GPU match_len -> CondProjection -> K/V build
+    in place) gives the same trajectory, bit for bit, as sample_clips fed with the host-side
+    match_len output (datasetcode/dataset.py:49-87)."""
+    _need_gpu()
+    from lm2a_b200.models import CondProjection, GaussianDiffusion
+    from lm2a_b200.sample import match_len, sample_clips, sample_clips_raw
+    cfg, sd, net = _b64()
+    cp = CondProjection().cuda()
+    cp.load_state_dict(orc.random_cond_proj_state_dict(seed=7))
+    t_len, steps, gw = 100, 5, 2.1
+    clips = [orc.synthetic_clip(i, t_mel=t_len, t_motion=lm, time_varying_lyrics=True)
+             for i, lm in enumerate((37, 100, 61))]
+    clips[2]["lyrics"] = clips[2]["lyrics"][:77]          # ragged lyrics too
+    motions = [c["motion"] for c in clips]
+    lyrics = [c["lyrics"] for c in clips]
+    m_rs = np.stack([match_len(a, t_len, "interp") for a in motions])
+    l_rs = np.stack([match_len(a, t_len, "interp") for a in lyrics])
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(3, 80, t_len, generator=g).cuda()
+    noises = torch.randn(steps - 1, 3, 80, t_len, generator=g).cuda()
+    diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    a, mf_a, _ = sample_clips(net, cp, diff, m_rs, l_rs, t_len, gw, x_init=x0, noises=noises)
+    b, ex = sample_clips_raw(net, cp, diff, motions, lyrics, t_len, gw, x_init=x0, noises=noises,
+                             want_resampled=True)
+    np.testing.assert_array_equal(ex["motion_rs"].cpu().numpy(), m_rs)
+    np.testing.assert_array_equal(ex["lyrics_rs"].cpu().numpy(), l_rs)
+    assert torch.equal(ex["motion_f"].float(), mf_a)
+    np.testing.assert_array_equal(a, b)
+    # unguided plan (no zero slot in front of the condition slabs)
+    a1, _, _ = sample_clips(net, cp, diff, m_rs, l_rs, t_len, 1.0, x_init=x0, noises=noises)
+    b1, _ = sample_clips_raw(net, cp, diff, motions, lyrics, t_len, 1.0, x_init=x0, noises=noises)
+    np.testing.assert_array_equal(a1, b1)
+
+
+def test_ddim_sample_kernel_matches_reference_golden(golden_dir):
+    """GaussianDiffusion.ddim_sample (lm2a_cfg_ddim) vs the reference's ddim_sample outputs:
+    bit-exact (same fp32 scalars, same operation order, no FMA contraction)."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    d = np.load(os.path.join(golden_dir, "ddim.npz"))
+    diff = GaussianDiffusion(None, timesteps=50, device="cuda")
+    x, eps = torch.from_numpy(d["x"]).cuda(), torch.from_numpy(d["eps"]).cuda()
+    for i, (t, tp, eta) in enumerate(d["cases"]):
+        # re-create the reference's CPU draw and inject it through the generator-free path
+        table = diff.ddim_coefficients(int(t), int(tp), float(eta)).contiguous()
+        from lm2a_b200 import ops
+        xp = x.clone()
+        x0 = torch.empty_like(xp)
+        step = torch.zeros(1, dtype=torch.int32, device="cuda")
+        noise = torch.from_numpy(d[f"noise_{i}"]).cuda()
+        ops.cfg_ddim(xp, eps, noise, table, None, step, None, None, x.size(0), x[0].numel(),
+                     1.0, False, False, x0)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(x0.cpu().numpy(), d[f"x0_{i}"])
+        np.testing.assert_array_equal(xp.cpu().numpy(), d[f"x_prev_{i}"])
+    xp, x0 = diff.ddim_sample(x, 0, -1, eps, eta=0.3)   # public signature, no draw at t_prev <= 0
+    np.testing.assert_array_equal(xp.cpu().numpy(), d["x_prev_4"])
+
+
+@pytest.mark.parametrize("eta,gw", [(0.0, 2.1), (0.8, 2.1), (0.0, 1.0)])
+def test_ddim_trajectory_vs_oracle(eta, gw):
+    """Few-step sampler: 6 DDIM steps out of T = 40 under CFG vs the oracle loop,
+    eager with injected noise and graph replay (device-side step index / timestep sequence)."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion
+    cfg, sd, net = _b64()
+    T, S, bsz, t_len, lk = 40, 6, 2, 100, 60
+    g = torch.Generator().manual_seed(55)
+    x0 = torch.randn(bsz, 80, t_len, generator=g)
+    mf = torch.randn(bsz, lk, 128, generator=g)
+    tf = torch.randn(bsz, lk, 128, generator=g)
+    noises = torch.randn(S, bsz, 80, t_len, generator=g)
+    diff = GaussianDiffusion(net, timesteps=T, device="cuda")
+    taus = diff.ddim_timesteps(S)
+    assert len(taus) == S and taus[0] == T - 1 and taus[-1] == 0
+    got = diff.sample_ddim((bsz, 80, t_len), mf.cuda(), tf.cuda(), S, eta, gw, x_init=x0.cuda(),
+                           noises=noises.cuda())
+    with torch.no_grad():
+        ref = orc.ddim_sample_loop(sd, cfg, mf, tf, T, taus, eta, gw, x0, list(noises))
+    for b in range(bsz):
+        mse, cos = orc.mel_metrics(got[b].cpu().numpy(), ref[b].numpy())
+        assert mse / float(ref[b].var()) < 2e-3, f"clip {b}: rel MSE {mse / float(ref[b].var()):.3e}"
+        assert cos > 0.999, f"clip {b}: frame cosine {cos:.6f}"
+    if eta == 0.0:
+        # deterministic sampler: the graph-replayed run must equal the eager injected run
+        rep = diff.sample_ddim((bsz, 80, t_len), mf.cuda(), tf.cuda(), S, eta, gw, x_init=x0.cuda())
+        assert torch.equal(rep, got)
+        rep2 = diff.sample_ddim((bsz, 80, t_len), mf.cuda(), tf.cuda(), S, eta, gw, x_init=x0.cuda())
+        assert torch.equal(rep2, got)   # clock reset between trajectories
+    else:
+        out = diff.sample_ddim((bsz, 80, t_len), mf.cuda(), tf.cuda(), S, eta, gw)
+        assert torch.isfinite(out).all()
 
 
 def test_uncond_shortcut_equals_full_path():
