@@ -10,9 +10,10 @@ Workload (BASELINE.json configs[1]): production UNet1D_ultimate (base 256, mults
 path. A "step" is ONE denoising step of the whole batch = one CUDA Graph replay
 (x ingest -> UNet -> CFG blend + clamps + DDPM posterior, timestep advanced on device).
 `value` = clips/s for the reference's 1000-step trajectory = N*B / (1000 * s_per_step),
-inputs resident in HBM. `e2e` = the same metric through lm2a_b200.sample.sample_clips with
-HOST inputs: pinned H2D of motion/lyrics, CondProjection, K/V cache build, all 1000 steps,
-D2H of the mels (+ one all-gather when N > 1).
+inputs resident in HBM. `e2e` = the same metric through lm2a_b200.sample.sample_clips_raw
+with HOST inputs shaped like the npz files (motion (180, 234), lyrics (516, 768) per clip):
+pinned H2D of the raw conditions, match_len resampling + CondProjection + K/V cache build on
+the GPU, all 1000 steps, D2H of the mels (+ one all-gather when N > 1).
 """
 import argparse
 import json
@@ -114,6 +115,13 @@ def synthetic_conditions(orc, first_clip, count):
     return np.stack(motions), np.stack(lyrics)
 
 
+def synthetic_raw_conditions(orc, first_clip, count):
+    """npz-shaped raw conditions: motion (180, 234), time-varying lyrics (516, 768)."""
+    clips = [orc.synthetic_clip(first_clip + i, t_mel=T_MEL, time_varying_lyrics=True)
+             for i in range(count)]
+    return [c["motion"] for c in clips], [c["lyrics"] for c in clips]
+
+
 def cpu_reference_step(orc, torch, steps, warmup):
     """Times the oracle port of the reference's CFG loop body (sample.py:144-210) on the host
     cores: one clip (2 rows) of the same workload per step. Returns seconds per step."""
@@ -198,7 +206,7 @@ def run_b200(args):
     from lm2a_b200 import distributed as ldist
     from lm2a_b200 import ops
     from lm2a_b200.models import CondProjection, GaussianDiffusion, UNet1D_ultimate
-    from lm2a_b200.sample import sample_clips
+    from lm2a_b200.sample import sample_clips_raw
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the lm2a_b200 path has no CPU fallback")
@@ -265,9 +273,11 @@ def run_b200(args):
             by_kind[k] = by_kind.get(k, 0.0) + s
 
         # ---- end to end through the public API with host buffers (full 1000-step trajectory)
+        raw_m, raw_l = synthetic_raw_conditions(orc, rank * BATCH, BATCH)
+        h2d_bytes = sum(a.nbytes for a in raw_m) + sum(a.nbytes for a in raw_l)
         barrier()
         t0 = time.perf_counter()
-        mel, _, _ = sample_clips(unet, cond_proj, diffusion, motions, lyrics, T_MEL, GW)
+        mel, _ = sample_clips_raw(unet, cond_proj, diffusion, raw_m, raw_l, T_MEL, GW)
         if world > 1:
             mine = torch.from_numpy(mel).to(dev)
             allm = torch.empty((world * BATCH, 80, T_MEL), dtype=torch.float32, device=dev)
@@ -275,6 +285,20 @@ def run_b200(args):
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e_finite = bool(torch.isfinite(torch.from_numpy(mel)).all())
+
+        # ---- few-step sampler, same public path, 50 DDIM steps instead of 1000
+        ddim_steps = 50
+        sampler_d = diffusion.sampler(BATCH, T_MEL, T_MEL, True,
+                                      ddim=(tuple(diffusion.ddim_timesteps(ddim_steps)), 0.0))
+        sampler_d.gw = GW
+        sampler_d._ensure_graph()
+        barrier()
+        t0 = time.perf_counter()
+        mel_d = sampler_d.run(None, None, GW)   # conditions of the e2e run are still in the slabs
+        mel_d = mel_d.cpu()
+        barrier()
+        ddim_s = time.perf_counter() - t0
+        ddim_finite = bool(torch.isfinite(mel_d).all())
 
     tms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,10 +341,16 @@ def run_b200(args):
             "kernel_ms": {k: v * 1e3 for k, v in sorted(by_kind.items())},
             "e2e": {"value": world * BATCH / (e2e_ms * 1e-3), "unit": "clips/s",
                     "seconds": e2e_ms * 1e-3,
-                    "h2d_bytes_per_step": int(motions.nbytes + lyrics.nbytes),
+                    "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(mel.nbytes),
                     "note": "one step of e2e = one full 1000-step trajectory of the batch via "
-                            "lm2a_b200.sample.sample_clips (host in, host out)"},
+                            "lm2a_b200.sample.sample_clips_raw (raw npz-shaped host conditions in, "
+                            "match_len + CondProjection + K/V build on the GPU, host mels out)"},
+            "ddim": {"steps": ddim_steps, "eta": 0.0, "clips_per_s": world * BATCH / ddim_s,
+                     "seconds": ddim_s, "finite": ddim_finite,
+                     "note": "NOT the headline metric: GaussianDiffusion.sample_ddim (reference "
+                             "ddim_sample, diffusion.py:124-165, over a 50-step sub-sequence), "
+                             "device-resident conditions, D2H of the mels included"},
             "gpu_launches": int(launches_per_step * steps),
             "launches_per_step": int(launches_per_step),
             "clocks": clk,

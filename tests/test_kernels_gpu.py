@@ -318,6 +318,9 @@ def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
     # panels), 192, 256, 384 (two V^T boxes, one 512-column TMEM allocation, single-stage rings)
     (384, 4, 50, 60, 1.0), (768, 4, 129, 150, 1.0), (1024, 4, 64, 516, 1.0),
     (1536, 4, 129, 516, 1.0), (1536, 4, 40, 100, 6.0),
+    # tail rows taken over by the producer warps of the full tiles: two per CTA (dh = 32, 64B
+    # swizzle), dh = 96 panels, a peaked softmax on the tail path, rem > 2 * nfull (own tile)
+    (128, 4, 260, 64, 1.0), (384, 4, 129, 60, 1.0), (512, 8, 258, 300, 6.0), (256, 8, 261, 100, 1.0),
 ])
 def test_cross_attention_core(ops, e, heads, t, lk, qgain):
     r, slots, tp = 3, 2, t + 2

@@ -220,10 +220,13 @@ def test_ddim_sample_kernel_matches_reference_golden(golden_dir):
     from lm2a_b200.models import GaussianDiffusion
     d = np.load(os.path.join(golden_dir, "ddim.npz"))
     diff = GaussianDiffusion(None, timesteps=50, device="cuda")
+    # the golden run computed its schedule on the CPU; torch's CUDA cumprod (a parallel scan)
+    # rounds alpha_bars differently in the last bit, so the bit-exact check of the KERNEL takes
+    # the five scalars from a CPU-side schedule, as the reference run did
+    diff_cpu = GaussianDiffusion(None, timesteps=50, device="cpu")
     x, eps = torch.from_numpy(d["x"]).cuda(), torch.from_numpy(d["eps"]).cuda()
     for i, (t, tp, eta) in enumerate(d["cases"]):
-        # re-create the reference's CPU draw and inject it through the generator-free path
-        table = diff.ddim_coefficients(int(t), int(tp), float(eta)).contiguous()
+        table = diff_cpu.ddim_coefficients(int(t), int(tp), float(eta)).cuda().contiguous()
         from lm2a_b200 import ops
         xp = x.clone()
         x0 = torch.empty_like(xp)
@@ -234,8 +237,10 @@ def test_ddim_sample_kernel_matches_reference_golden(golden_dir):
         torch.cuda.synchronize()
         np.testing.assert_array_equal(x0.cpu().numpy(), d[f"x0_{i}"])
         np.testing.assert_array_equal(xp.cpu().numpy(), d[f"x_prev_{i}"])
-    xp, x0 = diff.ddim_sample(x, 0, -1, eps, eta=0.3)   # public signature, no draw at t_prev <= 0
-    np.testing.assert_array_equal(xp.cpu().numpy(), d["x_prev_4"])
+    # public signature with the device-side schedule: last-bit differences of alpha_bars only
+    xp, x0 = diff.ddim_sample(x, 0, -1, eps, eta=0.3)   # no draw at t_prev <= 0
+    np.testing.assert_allclose(xp.cpu().numpy(), d["x_prev_4"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(x0.cpu().numpy(), d["x0_4"], rtol=0, atol=2e-6)
 
 
 @pytest.mark.parametrize("eta,gw", [(0.0, 2.1), (0.8, 2.1), (0.0, 1.0)])
