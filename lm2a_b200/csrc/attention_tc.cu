@@ -16,20 +16,15 @@
 //              max with lazy rescaling (O in TMEM is only corrected when the row max grows
 //              by more than 2^8), exp2, row sum, P -> bf16 -> 128B-swizzled shared tile;
 //              finally O / l -> bf16 slab
-// Query tails: when T is a few rows past a multiple of 128 (516 = 4*128 + 4, 258 = 2*128 + 2,
-// 129 = 128 + 1 — every level of the production clip length), a tile of its own for those rows
-// would stream the whole K/V of its (row, stream, head) again and hold an SM slot for a full
-// key walk. Instead the CTAs of the full tiles share the tail rows (<= 2 each) and their TMA
-// producer warp computes them with warp-level mma.sync from the K / V^T tiles already in shared
-// memory, after issuing each tile's loads (it is the only writer of those stages, so no extra
-// barrier; the arithmetic hides under its wait for the next free stage).
+// Query tails (T = 516 / 258 / 129 leave 4 / 2 / 1 rows in a tile of their own): handing those
+// rows to the producer warps of the full tiles (CUDA-core and mma.sync variants, commit
+// "attention: tail query rows on the producer warp") measured neutral to slower on B200
+// (92 vs 94 / 67 vs 67 / 64 vs 60 us per launch at levels 0 / 1 / 2) and was removed.
 // TMEM: S[0] cols 0-63, S[1] cols 64-127, O in dh further columns; two CTAs per SM for
 // dh <= 128. Head dims: any multiple of 64 up to 384 (64-channel operand panels, 128B
 // swizzle) plus 32 and 96 (32-channel panels, 64B swizzle) — the legacy UNet1D
 // (reference models/unet1d.py:17-29: 4 heads over 256..1536 channels) needs 192, 256 and 384.
 #include "../../include/lm2a_b200.h"
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace lm2a {
@@ -65,10 +60,6 @@ struct AttnSmem {
   static constexpr int kVOff = kKOff + kKStages * kKBytes;
   static constexpr int kBarOff = kVOff + kVStages * kVBytes;
   static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 1;
-  // tail rows on the producer warp (see the header comment): needs >= 2 K stages (the tail lags
-  // the loads by one tile); everything lives in registers (mma.sync fragments)
-  static constexpr bool kTail = DH <= 128;
-  static constexpr int kTQ = 2;   // tail query rows one CTA can take over
   static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
   // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
   // third is never scheduled
@@ -121,8 +112,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmVm,
                      const __grid_constant__ CUtensorMap tmVt, __nv_bfloat16* __restrict__ o,
                      int o_ld, const int* __restrict__ kv_slot, int tp, int t_valid, int lk,
-                     int e, int heads, const __nv_bfloat16* __restrict__ q_rows, int q_ld,
-                     int tail) {
+                     int e, int heads) {
   using L = AttnSmem<DH>;
   constexpr bool kSw64 = L::kSw64;
   constexpr int KS = L::kKStages, VS = L::kVStages, PB = L::kPBufs;
@@ -204,8 +194,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   if (warp == 4) {
     // ------------------------------------------------------------- TMA producer
     // Q, then K_{j+1} before V_j: a K slot frees when S_{j+1-KS} is done, a V slot when
-    // P_{j-VS} V_{j-VS} is done, which happen in this order. Lane 0 issues; all lanes share the
-    // tail rows' arithmetic (see the header comment).
+    // P_{j-VS} V_{j-VS} is done, which happen in this order
     const int slot = kv_slot[r];
     const CUtensorMap* km = stream ? &tmKt : &tmKm;
     const CUtensorMap* vm = stream ? &tmVt : &tmVm;
@@ -235,158 +224,10 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                     r * tp + q0, q_full);
       load_k(0);
     }
-    if constexpr (L::kTail) {
-      // ---- tail rows of this CTA: t = nfull * 128 + blockIdx.x + i * gridDim.x, i < kTQ ----
-      // Row i is row i of an m16n8k16 A fragment (rows >= kTQ stay zero): S = q K^T and
-      // O += P V run as warp-level mma.sync on the K / V^T tiles the tcgen05 pipeline already
-      // holds in shared memory (ldmatrix with the tiles' swizzle applied to the row addresses).
-      constexpr int TQ = L::kTQ;
-      const int g = lane >> 2, t4 = lane & 3;   // fragment row group / thread-in-group
-      const int my_t = (int)gridDim.x * kBQ + (int)blockIdx.x + g * (int)gridDim.x;
-      const bool my_row = tail != 0 && g < TQ && my_t < t_valid;
-      const int first_t = (int)gridDim.x * kBQ + (int)blockIdx.x;
-      const bool any_tail = tail != 0 && first_t < t_valid;   // warp-uniform
-      uint32_t qa[DH / 16][2];
-      {
-        const __nv_bfloat16* qp =
-            q_rows + ((size_t)r * tp + (my_row ? my_t : 0)) * q_ld + stream * e + h * DH;
-#pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks) {
-          qa[ks][0] = my_row ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 2 * t4) : 0u;
-          qa[ks][1] = my_row ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8 + 2 * t4) : 0u;
-        }
-      }
-      float of[DH / 8][2];
-#pragma unroll
-      for (int d = 0; d < DH / 8; ++d) of[d][0] = of[d][1] = 0.f;
-      float m_r = -INFINITY, l_r = 0.f;
-      uint32_t pa[kBK / 16][2];   // P_j as A fragments (a0, a2) per 16-key step
-#pragma unroll
-      for (int kk = 0; kk < kBK / 16; ++kk) pa[kk][0] = pa[kk][1] = 0u;
-      // rows 8-15 of A are zero, so c2 / c3 stay zero: they are fed as constants and their
-      // outputs dropped, only rows 0-7 (c0, c1) are kept in registers across the key walk
-      auto mma16816 = [](float (&c)[2], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-        float d2, d3;
-        asm volatile(
-            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
-            "{%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %10, %10};"
-            : "+f"(c[0]), "+f"(c[1]), "=f"(d2), "=f"(d3)
-            : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1), "f"(0.f));
-      };
-      auto ldsm4 = [](uint32_t addr, uint32_t (&b)[4]) {
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr) : "memory");
-      };
-      // S_j rows of the tail queries, online softmax, P_j -> A fragments
-      auto tail_qk = [&](int j) {
-        const int st = j % KS;
-        mbar_wait(k_full(st), (uint32_t)(j / KS) & 1u);
-        constexpr int kRowBytes = L::kPanelW * 2;
-        constexpr int CPP = L::kPanelW / 8;   // 16-byte chunks per panel row
-        float sf[kBK / 8][2];
-#pragma unroll
-        for (int nb = 0; nb < kBK / 8; ++nb) {
-          sf[nb][0] = sf[nb][1] = 0.f;
-          // key row nb * 8 + (lane & 7): its swizzle phase does not depend on nb
-          const uint32_t krow = (uint32_t)(lane & 7);
-          const uint32_t swz = kSw64 ? ((krow >> 1) & 3u) : krow;
-#pragma unroll
-          for (int ksp = 0; ksp < DH / 32; ++ksp) {
-            const uint32_t chunk = (uint32_t)(ksp * 4 + (lane >> 3));
-            const uint32_t panel = chunk / CPP, cip = chunk % CPP;
-            uint32_t b[4];
-            ldsm4(k_tile(st) + panel * L::kKPanelBytes + krow * kRowBytes + ((cip ^ swz) << 4) +
-                      (uint32_t)(nb * 8 * kRowBytes), b);
-            mma16816(sf[nb], qa[2 * ksp][0], qa[2 * ksp][1], b[0], b[1]);
-            mma16816(sf[nb], qa[2 * ksp + 1][0], qa[2 * ksp + 1][1], b[2], b[3]);
-          }
-        }
-        // row g of the fragment: keys j*64 + nb*8 + 2*t4 (+1) in sf[nb][0], sf[nb][1]
-        const int key0 = j * kBK + 2 * t4;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int nb = 0; nb < kBK / 8; ++nb) {
-          if (key0 + nb * 8 >= lk) sf[nb][0] = -INFINITY;
-          if (key0 + nb * 8 + 1 >= lk) sf[nb][1] = -INFINITY;
-          mx = fmaxf(mx, fmaxf(sf[nb][0], sf[nb][1]));
-        }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float m_new = fmaxf(m_r, mx);
-        const float corr = ex2_approx(m_r - m_new);   // first tile: exp2(-inf) = 0
-        m_r = m_new;
-        float sum = 0.f;
-#pragma unroll
-        for (int nb = 0; nb < kBK / 8; ++nb) {
-          sf[nb][0] = ex2_approx(sf[nb][0] - m_new);
-          sf[nb][1] = ex2_approx(sf[nb][1] - m_new);
-          sum += sf[nb][0] + sf[nb][1];
-        }
-        l_r = fmaf(l_r, corr, sum);   // per-thread partial of the row sum
-#pragma unroll
-        for (int kk = 0; kk < kBK / 16; ++kk) {
-          pa[kk][0] = pack_bf16x2(sf[2 * kk][0], sf[2 * kk][1]);
-          pa[kk][1] = pack_bf16x2(sf[2 * kk + 1][0], sf[2 * kk + 1][1]);
-        }
-#pragma unroll
-        for (int d = 0; d < DH / 8; ++d) {
-          of[d][0] *= corr;
-          of[d][1] *= corr;
-        }
-      };
-      // O rows += P_j V_j (B fragments from the V^T tile: rows = channels, keys contiguous)
-      auto tail_pv = [&](int j) {
-        const int st = j % VS;
-        mbar_wait(v_full(st), (uint32_t)(j / VS) & 1u);
-#pragma unroll
-        for (int db = 0; db < DH / 8; ++db) {
-          // V^T row db * 8 + (lane & 7): swizzle phase independent of db
-          const uint32_t vrow = (uint32_t)(lane & 7);
-#pragma unroll
-          for (int kp = 0; kp < kBK / 32; ++kp) {
-            const uint32_t chunk = (uint32_t)(kp * 4 + (lane >> 3));
-            uint32_t b[4];
-            ldsm4(v_tile(st) + vrow * 128u + ((chunk ^ vrow) << 4) + (uint32_t)(db * 1024), b);
-            mma16816(of[db], pa[2 * kp][0], pa[2 * kp][1], b[0], b[1]);
-            mma16816(of[db], pa[2 * kp + 1][0], pa[2 * kp + 1][1], b[2], b[3]);
-          }
-        }
-      };
-      // Loads first (they gate the MMA pipeline), tail arithmetic after: at iteration j the
-      // stages hold K_j, K_{j+1} and V_{j-1}, V_j; the next iteration overwrites K_j and V_{j-1}
-      // (two-stage rings), so exactly those two are consumed here. Both were issued an iteration
-      // ago, so the waits below normally fall through and the arithmetic hides under the
-      // k_empty / v_empty wait of the next iteration.
+    if (lane == 0) {
       for (int j = 0; j < ntiles; ++j) {
-        if (lane == 0) {
-          if (j + 1 < ntiles) load_k(j + 1);
-          load_v(j);
-        }
-        __syncwarp();
-        if (any_tail) {
-          if (j >= 1) tail_pv(j - 1);
-          tail_qk(j);
-        }
-        __syncwarp();
-      }
-      if (any_tail) {
-        tail_pv(ntiles - 1);
-        float l_tot = l_r + __shfl_xor_sync(0xffffffffu, l_r, 1);
-        l_tot += __shfl_xor_sync(0xffffffffu, l_tot, 2);
-        if (my_row) {
-          const float inv = 1.0f / l_tot;
-          __nv_bfloat16* op = o + ((size_t)r * tp + my_t) * o_ld + stream * e + h * DH + 2 * t4;
-#pragma unroll
-          for (int d = 0; d < DH / 8; ++d)
-            *reinterpret_cast<uint32_t*>(op + d * 8) = pack_bf16x2(of[d][0] * inv, of[d][1] * inv);
-        }
-      }
-    } else {
-      if (lane == 0) {
-        for (int j = 0; j < ntiles; ++j) {
-          if (j + 1 < ntiles) load_k(j + 1);
-          load_v(j);
-        }
+        if (j + 1 < ntiles) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 5) {
@@ -608,19 +449,10 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
       encode_map(&tvt, vt_t, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK,
                  L::kVBoxRows, false))
     return 1;
-  // a few rows past a multiple of 128: the full tiles' CTAs take them over (<= kTQ each)
-  const int nfull = t_valid / kBQ, rem = t_valid % kBQ;
-  static const bool tail_enabled = [] {
-    const char* ev = getenv("LM2A_ATTN_TAIL");
-    return ev == nullptr || ev[0] != '0';
-  }();
-  const int tail = (L::kTail && tail_enabled && nfull >= 1 && rem > 0 &&
-                    rem <= L::kTQ * nfull) ? 1 : 0;
-  dim3 grid(tail ? nfull : (t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
+  dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
   LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, st, tq, tkm, tkt, tvm, tvt,
                                           reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
-                                          t_valid, lk, e, heads,
-                                          reinterpret_cast<const __nv_bfloat16*>(q), q_ld, tail));
+                                          t_valid, lk, e, heads));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -1,0 +1,108 @@
+"""BASELINE.json config 4: dataset-scale sampling — N synthetic npz-shaped clips sharded by clip
+across the GPUs of one box (rank r owns clips r, r+W, ...), each rank sampling its shard in
+batches through the public raw-condition path (lm2a_b200.sample.sample_clips_raw: H2D of the
+raw conditions, match_len + CondProjection + K/V build on the GPU, full CFG trajectory, D2H),
+NO collective inside the loop, one NCCL all-gather of the finished mels at the end.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
+        --master-port 29520 tools/sample_dataset.py [--clips 1868] [--batch 64] [--steps 1000]
+
+Rank 0 prints one JSON line: whole-job clips/s over wall time (barrier + synchronize on both
+sides, max over ranks), the all-gather time, and a checksum of the gathered mels.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import lm2a_oracle as orc  # noqa: E402
+from lm2a_b200 import distributed as ldist  # noqa: E402
+from lm2a_b200.models import CondProjection, GaussianDiffusion, UNet1D_ultimate  # noqa: E402
+from lm2a_b200.sample import sample_clips_raw  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=1868)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--guidance", type=float, default=2.1)
+    a = ap.parse_args()
+    rank, world, local_rank = ldist.init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = orc.UNetConfig.production()
+    unet = UNet1D_ultimate(80, cfg.base_dim, cfg.dim_mults, cfg.cond_dim, cfg.time_emb_dim,
+                           cfg.num_res_blocks, cfg.mid_blocks, cfg.attn_heads)
+    unet.load_state_dict(orc.random_state_dict(cfg, 5))
+    unet = unet.to(dev).eval()
+    cp = CondProjection(234, 768, 128)
+    cp.load_state_dict(orc.random_cond_proj_state_dict(seed=7))
+    cp = cp.to(dev).eval()
+    diff = GaussianDiffusion(unet, timesteps=a.steps, device=dev)
+    t_mel = 516
+    torch.manual_seed(1000 + rank)
+
+    def sample_batch(idx):
+        clips = [orc.synthetic_clip(i, t_mel=t_mel, time_varying_lyrics=True) for i in idx]
+        n = len(clips)
+        # a ragged last batch is padded to the plan's batch size (one graph per batch size)
+        while len(clips) < a.batch:
+            clips.append(clips[-1])
+        mel, _ = sample_clips_raw(unet, cp, diff, [c["motion"] for c in clips],
+                                  [c["lyrics"] for c in clips], t_mel, a.guidance)
+        return torch.from_numpy(mel[:n]).to(dev)
+
+    # warm-up: build the launch plan and capture the step graph outside the timed region
+    smp = diff.sampler(a.batch, t_mel, t_mel, a.guidance > 1.0)
+    smp.gw = a.guidance
+    smp._ensure_graph()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    barrier()
+    t0 = time.perf_counter()
+    local = ldist.sample_sharded(a.clips, a.batch, sample_batch, (80, t_mel), dev, rank, world,
+                                 gather=False)
+    torch.cuda.synchronize(dev)
+    t_local = time.perf_counter() - t0
+    barrier()
+    t1 = time.perf_counter()
+    per = ldist.padded_shard_len(a.clips, world)
+    buf = torch.zeros((per, 80, t_mel), dtype=torch.float32, device=dev)
+    buf[: local.shape[0]] = local
+    if world > 1:
+        full = torch.empty((world * per, 80, t_mel), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, buf)
+    else:
+        full = buf
+    barrier()
+    t2 = time.perf_counter()
+    tm = torch.tensor([t2 - t0, t_local, t2 - t1], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total, loc, gat = (float(v) for v in tm)
+        print(json.dumps({
+            "workload": f"dataset_{a.clips}clips_T{t_mel}_cfg{a.guidance}_steps{a.steps}",
+            "n_gpus": world, "batch_per_gpu": a.batch, "clips": a.clips,
+            "clips_per_s": a.clips / total, "seconds": total, "slowest_rank_sampling_s": loc,
+            "all_gather_s": gat, "all_gather_bytes": int(full.numel() * 4),
+            "finite": bool(torch.isfinite(full).all()),
+            "mel_abs_mean": float(full.abs().mean())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
