@@ -19,12 +19,16 @@
 // Query tails (T = 516 / 258 / 129 leave 4 / 2 / 1 rows in a tile of their own): handing those
 // rows to the producer warps of the full tiles (CUDA-core and mma.sync variants, commit
 // "attention: tail query rows on the producer warp") measured neutral to slower on B200
-// (92 vs 94 / 67 vs 67 / 64 vs 60 us per launch at levels 0 / 1 / 2) and was removed.
+// (92 vs 94 / 67 vs 67 / 64 vs 60 us per launch at levels 0 / 1 / 2) and was removed. Three CTAs
+// per SM at dh = 32 (112-register cap, S walked in two 32-column halves, no spills) measured
+// 112 vs 91 us and was removed as well.
 // TMEM: S[0] cols 0-63, S[1] cols 64-127, O in dh further columns; two CTAs per SM for
 // dh <= 128. Head dims: any multiple of 64 up to 384 (64-channel operand panels, 128B
 // swizzle) plus 32 and 96 (32-channel panels, 64B swizzle) — the legacy UNet1D
 // (reference models/unet1d.py:17-29: 4 heads over 256..1536 channels) needs 192, 256 and 384.
 #include "../../include/lm2a_b200.h"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace lm2a {
@@ -145,6 +149,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   // softmax warps whose 32 query rows are all past t_valid do nothing at all (their P rows
   // stay garbage: MMA rows are independent and those O rows are never stored)
   const int valid_warps = min(4, (t_valid - q0 + 31) >> 5);
+  // a last key tile of <= 16 keys (Lk = 516 = 8 * 64 + 4) is computed 16 keys wide: S with
+  // N = 16, softmax over 16 columns, one K = 16 step of P.V
+  const bool short_last = lk - (ntiles - 1) * kBK <= 16;
 
   if (warp == 4 && lane == 0) {
     if ((smem_base & 1023u) != 0) {
@@ -234,6 +241,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
+      constexpr uint32_t idesc_s16 = umma_idesc_bf16(kBQ, 16);   // short last key tile
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, L::kVBoxRows);
       auto issue_pv = [&](int jj) {
         const int pb = jj % PB, st = jj % VS;
@@ -267,7 +275,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
               umma_desc_kmajor(q_base + panel * L::kQPanelBytes + kk * 32, kSw64);
           const uint64_t bdesc =
               umma_desc_kmajor(k_tile(st) + panel * L::kKPanelBytes + kk * 32, kSw64);
-          umma_bf16_ss(tmem_base + b * kBK, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + b * kBK, adesc, bdesc,
+                       (short_last && j == ntiles - 1) ? idesc_s16 : idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(k_empty(st));
         umma_commit(s_full(b));
@@ -284,29 +293,38 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const uint32_t p_row = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
 
-    for (int j = 0; j < ntiles; ++j) {
+    auto softmax_tile = [&](auto nc_tag, int j) {
+      constexpr int NC = decltype(nc_tag)::value;   // S columns (keys) of this tile: 64 or 16
       const int b = j & 1, pb = j % PB;
       mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
       tc_fence_after_sync();
-      uint32_t v0[32], v1[32];
-      tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
-      tmem_ld_32x32(tmem_base + lane_off + b * kBK + 32, v1);
-      tmem_ld_wait();
-      float s[64];
+      float s[NC];
+      if constexpr (NC == 64) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(tmem_base + lane_off + b * kBK, v0);
+        tmem_ld_32x32(tmem_base + lane_off + b * kBK + 32, v1);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        s[c] = __uint_as_float(v0[c]);
-        s[32 + c] = __uint_as_float(v1[c]);
+        for (int c = 0; c < 32; ++c) {
+          s[c] = __uint_as_float(v0[c]);
+          s[32 + c] = __uint_as_float(v1[c]);
+        }
+      } else {
+        uint32_t v0[16];
+        tmem_ld_32x16(tmem_base + lane_off + b * kBK, v0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) s[c] = __uint_as_float(v0[c]);
       }
       const int keys = lk - j * kBK;
-      if (keys < kBK) {
+      if (keys < NC) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
+        for (int c = 0; c < NC; ++c)
           if (c >= keys) s[c] = -INFINITY;
       }
       float mxa[4] = {s[0], s[1], s[2], s[3]};  // four independent chains
 #pragma unroll
-      for (int c = 4; c < 64; c += 4) {
+      for (int c = 4; c < NC; c += 4) {
         mxa[0] = fmaxf(mxa[0], s[c]);
         mxa[1] = fmaxf(mxa[1], s[c + 1]);
         mxa[2] = fmaxf(mxa[2], s[c + 2]);
@@ -342,7 +360,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       const uint32_t pbase = p_tile(pb) + p_row;
       float suma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < NC / 8; ++c) {
         uint32_t pk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -360,7 +378,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_full(pb));
-    }
+    };
+    const int wide_tiles = short_last ? ntiles - 1 : ntiles;
+#pragma unroll 1
+    for (int j = 0; j < wide_tiles; ++j) softmax_tile(std::integral_constant<int, kBK>{}, j);
+    if (short_last) softmax_tile(std::integral_constant<int, 16>{}, ntiles - 1);
 
     // ---- finalise: O / l -> bf16 slab
     mbar_wait(o_full, 0);
@@ -429,10 +451,11 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
   using L = AttnSmem<DH>;
   constexpr bool sw64 = L::kSw64;
   auto kern = cross_attn_tc_kernel<DH>;
+  constexpr int smem_bytes = L::kBytes;
   static bool configured = false;
   if (!configured) {
     LM2A_CUDA_OK(
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   CUtensorMap tq, tkm, tkt, tvm, tvt;
@@ -450,7 +473,7 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
                  L::kVBoxRows, false))
     return 1;
   dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
-  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), L::kBytes, st, tq, tkm, tkt, tvm, tvt,
+  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), smem_bytes, st, tq, tkm, tkt, tvm, tvt,
                                           reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
                                           t_valid, lk, e, heads));
   LM2A_CUDA_OK(cudaGetLastError());

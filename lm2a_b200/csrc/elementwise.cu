@@ -571,11 +571,11 @@ __device__ __forceinline__ float block_minmax(float v, bool is_max, float* red) 
   return t;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 mel_metrics_kernel(const float* __restrict__ gen, const float* __restrict__ real,
                    double* __restrict__ out, int n_mels, int T, float g_scale, float g_shift) {
-  __shared__ double red[8];
-  __shared__ float redf[8];
+  __shared__ double red[32];
+  __shared__ float redf[32];
   const int b = blockIdx.x;
   const float* g = gen + (size_t)b * n_mels * T;
   const float* r = real + (size_t)b * n_mels * T;
@@ -891,7 +891,7 @@ extern "C" int lm2a_mel_metrics(void* stream, const float* gen, const float* rea
   LM2A_REQUIRE(gen && real && out, "mel_metrics: null pointer");
   LM2A_REQUIRE(batch > 0 && n_mels > 0 && t > 0, "mel_metrics: bad geometry");
   LM2A_REQUIRE(t >= 11, "mel_metrics: SSIM window (11 frames) exceeds the clip length %d", t);
-  LM2A_CUDA_OK(launch_kernel(mel_metrics_kernel, dim3(batch), dim3(256), 0,
+  LM2A_CUDA_OK(launch_kernel(mel_metrics_kernel, dim3(batch), dim3(1024), 0,
                              reinterpret_cast<cudaStream_t>(stream), gen, real, out, n_mels, t,
                              gen_scale, gen_shift));
   LM2A_CUDA_OK(cudaGetLastError());

@@ -26,7 +26,11 @@ s.set_conditions(torch.randn(B, T, 128, generator=g).to(dev), torch.randn(B, T, 
 s.plan.x_in.normal_()
 s.plan.t_in.fill_(999)
 torch.cuda.synchronize()
+from lm2a_b200 import ops  # noqa: E402
+before = ops.launch_count()
 for i in range(STEPS):
     s._step(True)
 torch.cuda.synchronize()
-print("ok", float(s.plan.x_in.std()))
+per_step = (ops.launch_count() - before) // STEPS
+# launches of OUR kernels before the last step / in one step (ncu -s / -c for a one-step capture)
+print("ok", float(s.plan.x_in.std()), "skip", before + (STEPS - 1) * per_step, "per_step", per_step)
