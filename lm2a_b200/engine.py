@@ -716,6 +716,55 @@ class UNetPlan:
             main.wait_stream(side)
         return self.eps
 
+    def _time_op(self, fn, args, iters):
+        """Device time of one launch: `iters` back-to-back launches captured in a CUDA Graph,
+        replayed once untimed and once between CUDA events on the launching stream."""
+        fn(*args)  # warm (first-launch attribute setup must not happen under capture)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn(*args)
+        g.replay()
+        stream = torch.cuda.current_stream(self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(self.dev)
+        del g
+        return e0.elapsed_time(e1) * 1e-3 / iters
+
+    def autotune(self, iters=5, margin=0.97):
+        """Picks the tile shape of every implicit-GEMM launch by measurement instead of the wave
+        model: (block_n, cta_group) in {auto, 128x1, 256x1, 128x2 (CTA pair), 256x2}, each timed
+        on this plan's own operands; a non-default shape is kept only if it is > 3 % faster. The
+        K order of the accumulation and the GroupNorm partial-sum slices do not depend on the tile
+        shape, so the results are unchanged. Returns [(launch index, block_n, cta_group, us)]."""
+        if getattr(self, "_tuned", False):
+            return []
+        self._tuned = True
+        picked = []
+        for idx, (fn, args, meta) in enumerate(self.ops):
+            if meta["kind"] != "conv_gemm":
+                continue
+            desc = args[0]
+            best = None
+            for bn, cg in ((0, 0), (128, 1), (256, 1), (128, 2), (256, 2)):
+                if bn and desc.n_pad % bn != 0:
+                    continue
+                desc.block_n, desc.cta_group = bn, cg
+                try:
+                    t = self._time_op(fn, args, iters)
+                except RuntimeError:   # shape not admissible for this launch (fused GroupNorm)
+                    continue
+                if best is None or t < best[0] * margin:
+                    best = (t, bn, cg)
+            desc.block_n, desc.cta_group = best[1], best[2]
+            if best[1] or best[2]:
+                picked.append((idx, best[1], best[2], best[0] * 1e6))
+        return picked
+
     def flops(self):
         """Algorithmic FLOPs of one forward over all rows (K/V hoisted, out_proj.fuse folded)."""
         return sum(meta["flops"] for _, _, meta in self.ops)
@@ -727,24 +776,7 @@ class UNetPlan:
         rate. Repeats of one launch re-read the same operands (L2-warm; the slabs of the big
         layers exceed what stays resident next to the weights). Returns [(kind, meta, seconds)]
         in launch order."""
-        out = []
-        for fn, args, meta in self.ops:
-            fn(*args)  # warm (first-launch attribute setup must not happen under capture)
-            torch.cuda.synchronize(self.dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _ in range(iters):
-                    fn(*args)
-            g.replay()
-            stream = torch.cuda.current_stream(self.dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            g.replay()
-            e1.record(stream)
-            torch.cuda.synchronize(self.dev)
-            out.append((meta["kind"], meta, e0.elapsed_time(e1) * 1e-3 / iters))
-            del g
-        return out
+        return [(meta["kind"], meta, self._time_op(fn, args, iters)) for fn, args, meta in self.ops]
 
 
 class UNetEngine:

@@ -10,6 +10,8 @@ Every tensor op on the path is a C-ABI kernel (lm2a_cfg_posterior + the UNet pla
 torch is used for memory, RNG draws (torch.randn — the same generator stream the
 reference consumes) and stream / graph plumbing.
 """
+import os
+
 import torch
 
 from .. import ops
@@ -238,6 +240,11 @@ class CfgSampler:
             return
         p = self.plan
         keep_x = p.x_in.clone()
+        if os.environ.get("LM2A_AUTOTUNE", "0") == "1":
+            # measured tile shape per GEMM launch instead of the wave model: opt-in — it raises
+            # the isolated conv throughput (59.7 -> 61.4 % of peak) but not the in-graph step
+            # (2.116 vs 2.103 ms), see DESIGN.md
+            p.autotune()
         draw = self.ddim is None or self.eta > 0
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))

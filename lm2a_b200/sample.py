@@ -144,13 +144,26 @@ def sample_clips(unet, cond_proj, diffusion, motions, lyrics, t_len, guidance_we
     return out.numpy(), motion_f, text_f
 
 
-def _pad_batch(seqs, pinned):
-    """List of (L_i, D) host arrays -> pinned fp32 (B, L_max, D) tensor + int32 lengths."""
+_PINNED = {}   # (tag, shape) -> pinned staging buffer, reused across batches
+
+
+def _staging(tag, shape, pinned):
+    """Host staging buffer; pinned ones are cached (cudaHostAlloc of tens of MB per batch would
+    cost more than the copy it speeds up)."""
+    if not pinned:
+        return torch.empty(shape, dtype=torch.float32)
+    key = (tag, tuple(shape))
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    return _PINNED[key]
+
+
+def _pad_batch(seqs, pinned, tag="cond"):
+    """List of (L_i, D) host arrays -> (pinned) fp32 (B, L_max, D) tensor + int32 lengths. The
+    rows past a clip's length are never read by the resampling kernel."""
     lens = [int(a.shape[0]) for a in seqs]
     d = int(seqs[0].shape[1])
-    buf = torch.zeros(len(seqs), max(lens), d, dtype=torch.float32)
-    if pinned:
-        buf = buf.pin_memory()
+    buf = _staging(tag, (len(seqs), max(lens), d), pinned)
     for i, a in enumerate(seqs):
         buf[i, : lens[i]] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     return buf, torch.tensor(lens, dtype=torch.int32)
@@ -167,8 +180,8 @@ def sample_clips_raw(unet, cond_proj, diffusion, motions, lyrics, t_len, guidanc
     PCIe. Returns (mel_norm (B, 80, T) host fp32, extras) where extras holds the projected
     conditions and, if `want_resampled`, the resampled fp32 sequences (device tensors)."""
     dev = next(unet.parameters()).device
-    m, m_lens = _pad_batch(motions, pinned)
-    ly, l_lens = _pad_batch(lyrics, pinned)
+    m, m_lens = _pad_batch(motions, pinned, "motion")
+    ly, l_lens = _pad_batch(lyrics, pinned, "lyrics")
     m, ly = m.to(dev, non_blocking=True), ly.to(dev, non_blocking=True)
     m_lens, l_lens = m_lens.to(dev, non_blocking=True), l_lens.to(dev, non_blocking=True)
     bsz = m.shape[0]
@@ -177,8 +190,9 @@ def sample_clips_raw(unet, cond_proj, diffusion, motions, lyrics, t_len, guidanc
     mf, tf, m_rs, l_rs = cond_proj.project_raw(m, m_lens, ly, l_lens, t_len, dst_m, dst_t,
                                                want_resampled)
     x = s.run(None, None, guidance_weight, x_init, noises, use_graph, report)
-    out = torch.empty(x.shape, dtype=torch.float32, pin_memory=pinned)
-    out.copy_(x, non_blocking=False)
+    out = _staging("mel", tuple(x.shape), pinned)
+    out.copy_(x, non_blocking=False)   # synchronous: also orders the staging buffers' reuse
+    out = out.clone()                  # the caller owns its result; the staging buffer is reused
     extras = {"motion_f": mf.view(bsz, t_len, -1), "text_f": tf.view(bsz, t_len, -1),
               "motion_rs": m_rs, "lyrics_rs": l_rs}
     return out.numpy(), extras
