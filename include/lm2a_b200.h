@@ -33,6 +33,7 @@
  *   lm2a_cfg_ddim      models/diffusion.py:124-165 (ddim_sample)
  *   lm2a_resample_seq  datasetcode/dataset.py:49-87 (match_len 'interp')
  *   lm2a_mel_metrics   val.py:25-113 (compute_metrics)
+ *   lm2a_adan_step     models/adan.py:34-114 + EMA update train.py:177-180
  */
 #ifndef LM2A_B200_H
 #define LM2A_B200_H
@@ -253,6 +254,30 @@ int lm2a_cfg_ddim(void* stream, float* x, const float* eps, const float* noise,
 int lm2a_mel_metrics(void* stream, const float* gen, const float* real,
                      double* out, int32_t batch, int32_t n_mels, int32_t t,
                      float gen_scale, float gen_shift);
+
+/* ---- fused Adan step (+ EMA shadow weights), all tensors in one launch ------ */
+/* Reference models/adan.py:34-114 (restart_cond = None) and the EMA update of
+ * train.py:177-180. `tensors`: DEVICE array of per-parameter pointers (ema may be
+ * NULL); chunk_tensor / chunk_index: DEVICE int32 [n_chunks] mapping CTA b onto
+ * elements [chunk_index[b] * chunk_elems, ...) of tensor chunk_tensor[b].
+ * scalars: HOST float[14] = {1-b1, b1, 1-b2, b2, 1-b3, b3, correct_m, correct_v,
+ * correct_n (for the step count AFTER the increment), lr, eps, 1 + wd * lr,
+ * ema_decay, 1 - ema_decay}, each rounded to fp32 from the double the reference
+ * computes. first_step != 0: state["step"] was 0 (moments are not updated).   */
+typedef struct lm2a_adan_tensor {
+  float* p;
+  const float* g;
+  float* prev_g;
+  float* m;
+  float* v;
+  float* n;
+  float* ema;
+  int64_t numel;
+} lm2a_adan_tensor;
+int lm2a_adan_step(void* stream, const lm2a_adan_tensor* tensors,
+                   const int32_t* chunk_tensor, const int32_t* chunk_index,
+                   int32_t n_chunks, int32_t chunk_elems, int32_t first_step,
+                   const float* scalars);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,8 @@ SIGNATURES = {
                                 c_int32, c_int32, c_void_p]),
     "lm2a_mel_metrics": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                    c_int32, c_float, c_float]),
+    "lm2a_adan_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                 c_int32, c_void_p]),
 }
 
 _lib = None

@@ -668,6 +668,88 @@ mel_metrics_kernel(const float* __restrict__ gen, const float* __restrict__ real
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused Adan step for every parameter tensor of the model in ONE launch (reference
+// models/adan.py:34-114, restart_cond = None; train.py:99-100 builds it over all UNet +
+// CondProjection parameters) with the EMA shadow update of train.py:177-180 folded in. The
+// reference runs ~20 elementwise launches per tensor (306 + 4 tensors); here a chunk table
+// maps CTAs onto (tensor, 64 K-element chunk) pairs. 13 fp32 streams per element with EMA
+// (p, g, prev_g, m, v, n, ema read; p, prev_g, m, v, n, ema written) = 52 B, 44 B without.
+// Operation order and roundings follow the reference's torch calls (mul_ then add_(alpha) =
+// one FMA, scalar operands pre-rounded to fp32 by the caller, reciprocal * lr for `lr / t`,
+// addcmul_ = fma(value * t1, t2, self), IEEE sqrt, true division by the weight-decay
+// denominator). Moments are bit-identical to torch on CPU and CUDA; p agrees within a few ulp
+// (torch's CPU sqrt is not correctly rounded, torch's CUDA div_ by a scalar multiplies by the
+// reciprocal: the two torch back ends do not agree bit for bit with each other either).
+struct AdanScalars {
+  float om_b1, b1, om_b2, b2, om_b3, b3;   // (1 - beta_i), beta_i
+  float cm, cv, cn;                         // bias corrections 1 / (1 - (1 - beta_i)^step)
+  float lr, eps, denom;                     // denom = 1 + weight_decay * lr
+  float ema_decay, om_ema_decay;
+  int first_step;                           // state["step"] == 0: moments are not updated
+};
+
+__device__ __forceinline__ void adan_elem(float& p, float g, float& prev, float& m, float& v,
+                                          float& n, float* ema, const AdanScalars& s) {
+  if (!s.first_step) {
+    m = fmaf(s.b1, g, __fmul_rn(m, s.om_b1));
+    const float diff = __fsub_rn(g, prev);
+    v = fmaf(s.b2, diff, __fmul_rn(v, s.om_b2));
+    const float u = __fadd_rn(g, __fmul_rn(diff, s.om_b2));
+    n = fmaf(s.b3, __fmul_rn(u, u), __fmul_rn(n, s.om_b3));
+  }
+  const float t = __fadd_rn(__fsqrt_rn(__fmul_rn(n, s.cn)), s.eps);
+  const float wss = __fmul_rn(__frcp_rn(t), s.lr);
+  const float upd = __fadd_rn(__fmul_rn(m, s.cm), __fmul_rn(__fmul_rn(v, s.om_b2), s.cv));
+  p = __fdiv_rn(fmaf(__fmul_rn(-1.0f, wss), upd, p), s.denom);
+  prev = g;
+  if (ema != nullptr) *ema = __fadd_rn(__fmul_rn(*ema, s.ema_decay), __fmul_rn(p, s.om_ema_decay));
+}
+
+__global__ void __launch_bounds__(256)
+adan_step_kernel(const lm2a_adan_tensor* __restrict__ tensors,
+                 const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index,
+                 int chunk_elems, AdanScalars s) {
+  const lm2a_adan_tensor t = tensors[chunk_tensor[blockIdx.x]];
+  const long long begin = (long long)chunk_index[blockIdx.x] * chunk_elems;
+  const long long end = begin + chunk_elems < t.numel ? begin + chunk_elems : t.numel;
+  const bool vec = ((reinterpret_cast<uintptr_t>(t.p) | reinterpret_cast<uintptr_t>(t.g) |
+                     reinterpret_cast<uintptr_t>(t.prev_g) | reinterpret_cast<uintptr_t>(t.m) |
+                     reinterpret_cast<uintptr_t>(t.v) | reinterpret_cast<uintptr_t>(t.n) |
+                     reinterpret_cast<uintptr_t>(t.ema)) & 15) == 0;
+  long long i = begin + (long long)threadIdx.x * 4;
+  if (vec) {
+    for (; i + 3 < end; i += 256 * 4) {
+      float4 p = *reinterpret_cast<float4*>(t.p + i);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(t.g + i));
+      float4 pr = *reinterpret_cast<float4*>(t.prev_g + i);
+      float4 m = *reinterpret_cast<float4*>(t.m + i);
+      float4 v = *reinterpret_cast<float4*>(t.v + i);
+      float4 n = *reinterpret_cast<float4*>(t.n + i);
+      float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t.ema != nullptr) e = *reinterpret_cast<float4*>(t.ema + i);
+      adan_elem(p.x, g.x, pr.x, m.x, v.x, n.x, t.ema ? &e.x : nullptr, s);
+      adan_elem(p.y, g.y, pr.y, m.y, v.y, n.y, t.ema ? &e.y : nullptr, s);
+      adan_elem(p.z, g.z, pr.z, m.z, v.z, n.z, t.ema ? &e.z : nullptr, s);
+      adan_elem(p.w, g.w, pr.w, m.w, v.w, n.w, t.ema ? &e.w : nullptr, s);
+      *reinterpret_cast<float4*>(t.p + i) = p;
+      *reinterpret_cast<float4*>(t.prev_g + i) = pr;
+      *reinterpret_cast<float4*>(t.m + i) = m;
+      *reinterpret_cast<float4*>(t.v + i) = v;
+      *reinterpret_cast<float4*>(t.n + i) = n;
+      if (t.ema != nullptr) *reinterpret_cast<float4*>(t.ema + i) = e;
+    }
+    // ragged tail of the tensor (< 4 elements): the thread whose vector straddles `end`
+    for (long long k = i; k < end && k < i + 4; ++k)
+      adan_elem(t.p[k], t.g[k], t.prev_g[k], t.m[k], t.v[k], t.n[k],
+                t.ema ? t.ema + k : nullptr, s);
+  } else {
+    for (long long k = begin + threadIdx.x; k < end; k += 256)
+      adan_elem(t.p[k], t.g[k], t.prev_g[k], t.m[k], t.v[k], t.n[k],
+                t.ema ? t.ema + k : nullptr, s);
+  }
+}
+
 }  // namespace
 }  // namespace lm2a
 
@@ -894,6 +976,28 @@ extern "C" int lm2a_mel_metrics(void* stream, const float* gen, const float* rea
   LM2A_CUDA_OK(launch_kernel(mel_metrics_kernel, dim3(batch), dim3(1024), 0,
                              reinterpret_cast<cudaStream_t>(stream), gen, real, out, n_mels, t,
                              gen_scale, gen_shift));
+  LM2A_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int lm2a_adan_step(void* stream, const lm2a_adan_tensor* tensors,
+                              const int32_t* chunk_tensor, const int32_t* chunk_index,
+                              int32_t n_chunks, int32_t chunk_elems, int32_t first_step,
+                              const float* scalars) {
+  using namespace lm2a;
+  LM2A_REQUIRE(tensors && chunk_tensor && chunk_index && scalars, "adan_step: null pointer");
+  LM2A_REQUIRE(n_chunks > 0 && chunk_elems > 0 && chunk_elems % 1024 == 0,
+               "adan_step: chunk_elems must be a positive multiple of 1024");
+  AdanScalars s;
+  s.om_b1 = scalars[0]; s.b1 = scalars[1]; s.om_b2 = scalars[2]; s.b2 = scalars[3];
+  s.om_b3 = scalars[4]; s.b3 = scalars[5]; s.cm = scalars[6]; s.cv = scalars[7];
+  s.cn = scalars[8]; s.lr = scalars[9]; s.eps = scalars[10]; s.denom = scalars[11];
+  s.ema_decay = scalars[12]; s.om_ema_decay = scalars[13];
+  s.first_step = first_step != 0 ? 1 : 0;
+  LM2A_CUDA_OK(launch_kernel(adan_step_kernel, dim3(n_chunks), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), tensors, chunk_tensor,
+                             chunk_index, chunk_elems, s));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

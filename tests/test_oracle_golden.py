@@ -143,6 +143,27 @@ def test_compute_metrics_restatement_properties():
     assert flat["snr"] == 0.0   # real_var < 1e-8 guard (val.py:100-101)
 
 
+def test_adan_restatement_matches_reference(golden_dir):
+    """oracle.adan_step / ema_update == reference models/adan.py + train.py:177-180 over four
+    steps (first step included), bit for bit on CPU."""
+    from make_golden_adan import EMA_DECAY, HP, SHAPES, STEPS
+    d = np.load(os.path.join(golden_dir, "adan.npz"))
+    params = [torch.from_numpy(d[f"p0_{i}"].copy()) for i in range(len(SHAPES))]
+    shadow = [p.clone() for p in params]
+    states = [{"step": 0, "prev_grad": torch.zeros_like(p), "m": torch.zeros_like(p),
+               "v": torch.zeros_like(p), "n": torch.zeros_like(p)} for p in params]
+    for step in range(STEPS):
+        for i, p in enumerate(params):
+            orc.adan_step(p, torch.from_numpy(d[f"g{step}_{i}"]), states[i], HP["lr"], HP["betas"],
+                          HP["eps"], HP["weight_decay"])
+            orc.ema_update(shadow[i], p, EMA_DECAY)
+            np.testing.assert_array_equal(p.numpy(), d[f"p{step + 1}_{i}"])
+            np.testing.assert_array_equal(shadow[i].numpy(), d[f"ema{step + 1}_{i}"])
+    for i in range(len(SHAPES)):
+        for k in ("m", "v", "n", "prev_grad"):
+            np.testing.assert_array_equal(states[i][k].numpy(), d[f"{k}_{i}"])
+
+
 def test_match_len_interp(golden_dir):
     d = np.load(os.path.join(golden_dir, "sample_from_npz.npz"))
     t = d["mel"].shape[1]

@@ -85,3 +85,26 @@ def test_assess_batch_persistent_model(tmp_path):
     random.seed(42)
     random.shuffle(files)
     assert val.select_files(str(npz_dir), 2, True, 42) == files[:2]
+
+
+def test_assess_single_sample_contract(tmp_path):
+    """val.assess_single_sample (val.py:164-245): samples through sample_from_npz (schedule length
+    from the checkpoint), returns (metrics, temp_dir) and writes the per-sample files."""
+    _need_gpu()
+    from lm2a_b200 import val
+    clip = orc.synthetic_clip(3, t_mel=48, t_motion=20)
+    npz = tmp_path / "clipx.npz"
+    np.savez(npz, **clip)
+    ck = {"unet": orc.random_state_dict(orc.UNetConfig.production(), 5),
+          "cond_proj": orc.random_cond_proj_state_dict(seed=7), "timesteps": 3,
+          "guidance_weight": 2.1, "dataset_mean": -4.5, "dataset_std": 2.0}
+    ckpt = tmp_path / "ck.pt"
+    torch.save(ck, ckpt)
+    out_dir = tmp_path / "out"
+    metrics, temp_dir = val.assess_single_sample(str(npz), str(ckpt), str(out_dir), device="cuda")
+    assert set(metrics) == set(val.METRIC_KEYS)
+    assert os.path.isdir(temp_dir) and os.path.exists(out_dir / "clipx_metrics.txt")
+    g = np.load(out_dir / "clipx_gen_mel.npz")
+    want = orc.compute_metrics(clip["mel"], g["mel"])
+    for k in val.METRIC_KEYS:
+        _close(metrics[k], round(want[k], 6), k)

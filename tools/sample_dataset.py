@@ -49,6 +49,11 @@ def main():
     diff = GaussianDiffusion(unet, timesteps=a.steps, device=dev)
     t_mel = 516
     torch.manual_seed(1000 + rank)
+    # same number of batches as --batch would need, but evenly sized: no padded clips in the last
+    # batch (1868 clips / 8 ranks = 234 = 4 x 59 instead of 3 x 64 + 42 padded to 64)
+    n_local = len(ldist.shard_indices(a.clips, 0, world))
+    n_batches = (n_local + a.batch - 1) // a.batch
+    a.batch = (n_local + n_batches - 1) // n_batches
 
     def sample_batch(idx):
         clips = [orc.synthetic_clip(i, t_mel=t_mel, time_varying_lyrics=True) for i in idx]
