@@ -324,6 +324,11 @@ def run_b200(args):
         # ---- end to end through the public API with host buffers (full 1000-step trajectory)
         raw_m, raw_l = synthetic_raw_conditions(orc, rank * BATCH, BATCH)
         h2d_bytes = sum(a.nbytes for a in raw_m) + sum(a.nbytes for a in raw_l)
+        # warm-up call of the same public path on a 2-step schedule: pinned staging buffers and
+        # every first-call allocation happen here, as they would once in a long-running sampler
+        warm = GaussianDiffusion(unet, timesteps=2, device=dev)
+        sample_clips_raw(unet, cond_proj, warm, raw_m, raw_l, T_MEL, GW)
+        del warm
         barrier()
         t0 = time.perf_counter()
         mel, _ = sample_clips_raw(unet, cond_proj, diffusion, raw_m, raw_l, T_MEL, GW)
@@ -432,6 +437,10 @@ def run_b200(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to
+    # stdout at NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + [
+        "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     subprocess.check_call(cmd)
     return LIB
 
