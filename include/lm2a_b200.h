@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 5
+#define LM2A_ABI_VERSION 6
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -155,6 +155,20 @@ int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
                          const int32_t* kv_slot, int32_t slots, int32_t rows,
                          int32_t tp, int32_t t_valid, int32_t lk, int32_t e,
                          int32_t heads);
+/* Same, for the first n_streams (1 or 2) condition streams only: n_streams = 1
+ * runs the motion stream alone (q / o use their first e channels). Used when the
+ * lyrics stream is constant in time — the reference's preprocessing tiles ONE
+ * sentence embedding over all frames (preprocess.py:64-71), every key of that
+ * stream is then identical, its softmax uniform and its attention output the
+ * stream's single V row, which the caller keeps in the o slab.               */
+int lm2a_cross_attn_streams_bf16(void* stream, const void* q, int32_t q_ld,
+                                 void* o, int32_t o_ld, const void* k_motion,
+                                 const void* vt_motion, const void* k_text,
+                                 const void* vt_text, int32_t k_ld,
+                                 int32_t vt_ld, const int32_t* kv_slot,
+                                 int32_t slots, int32_t rows, int32_t tp,
+                                 int32_t t_valid, int32_t lk, int32_t e,
+                                 int32_t heads, int32_t n_streams);
 /* per-clip V cache transpose: src [slots*lk, src_ld] (c channels) ->
  * dst [slots*c, dst_ld] (lk keys); c multiple of 32.                        */
 int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src_ld,

@@ -30,7 +30,7 @@ class ConvDesc(ctypes.Structure):
                 ("gn_eps", c_float), ("_pad3", c_int32)]
 
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -50,6 +50,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
                                        c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_int32]),
+    "lm2a_cross_attn_streams_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                               c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                               c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lm2a_transpose_kv_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                          c_int32, c_int32]),
     "lm2a_time_mlp": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

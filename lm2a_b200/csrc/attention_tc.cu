@@ -447,7 +447,7 @@ template <int DH>
 int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, const void* k_m,
                 const void* vt_m, const void* k_t, const void* vt_t, int k_ld, int vt_ld,
                 const int32_t* kv_slot, int slots, int rows, int tp, int t_valid, int lk, int e,
-                int heads) {
+                int heads, int n_streams) {
   using L = AttnSmem<DH>;
   constexpr bool sw64 = L::kSw64;
   auto kern = cross_attn_tc_kernel<DH>;
@@ -459,8 +459,8 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
     configured = true;
   }
   CUtensorMap tq, tkm, tkt, tvm, tvt;
-  if (encode_map(&tq, q, (uint64_t)2 * e, (uint64_t)rows * tp, (uint64_t)q_ld, L::kPanelW, kBQ,
-                 sw64))
+  if (encode_map(&tq, q, (uint64_t)n_streams * e, (uint64_t)rows * tp, (uint64_t)q_ld,
+                 L::kPanelW, kBQ, sw64))
     return 1;
   if (encode_map(&tkm, k_m, (uint64_t)e, (uint64_t)slots * lk, (uint64_t)k_ld, L::kPanelW, kBK,
                  sw64) ||
@@ -472,7 +472,7 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
       encode_map(&tvt, vt_t, (uint64_t)lk, (uint64_t)slots * e, (uint64_t)vt_ld, kBK,
                  L::kVBoxRows, false))
     return 1;
-  dim3 grid((t_valid + kBQ - 1) / kBQ, 2 * heads, rows);
+  dim3 grid((t_valid + kBQ - 1) / kBQ, n_streams * heads, rows);
   LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), smem_bytes, st, tq, tkm, tkt, tvm, tvt,
                                           reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
                                           t_valid, lk, e, heads));
@@ -484,13 +484,15 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
 }  // namespace
 }  // namespace lm2a
 
-extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
-                                    int32_t o_ld, const void* k_motion, const void* vt_motion,
-                                    const void* k_text, const void* vt_text, int32_t k_ld,
-                                    int32_t vt_ld, const int32_t* kv_slot, int32_t slots,
-                                    int32_t rows, int32_t tp, int32_t t_valid, int32_t lk,
-                                    int32_t e, int32_t heads) {
+extern "C" int lm2a_cross_attn_streams_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                                            int32_t o_ld, const void* k_motion,
+                                            const void* vt_motion, const void* k_text,
+                                            const void* vt_text, int32_t k_ld, int32_t vt_ld,
+                                            const int32_t* kv_slot, int32_t slots, int32_t rows,
+                                            int32_t tp, int32_t t_valid, int32_t lk, int32_t e,
+                                            int32_t heads, int32_t n_streams) {
   using namespace lm2a;
+  LM2A_REQUIRE(n_streams == 1 || n_streams == 2, "cross_attn: n_streams=%d (1 or 2)", n_streams);
   LM2A_REQUIRE(q && o && k_motion && vt_motion && k_text && vt_text && kv_slot,
                "cross_attn: null pointer");
   LM2A_REQUIRE(rows > 0 && rows <= 65535 && slots > 0 && tp > 0 && t_valid > 0 &&
@@ -499,7 +501,7 @@ extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, v
   LM2A_REQUIRE(heads > 0 && e % heads == 0, "cross_attn: e=%d not divisible by heads=%d", e,
                heads);
   LM2A_REQUIRE(q_ld % 8 == 0 && o_ld % 8 == 0 && k_ld % 8 == 0 && vt_ld % 8 == 0 &&
-                   q_ld >= 2 * e && o_ld >= 2 * e && k_ld >= e && vt_ld >= lk,
+                   q_ld >= n_streams * e && o_ld >= n_streams * e && k_ld >= e && vt_ld >= lk,
                "cross_attn: bad pitches (q_ld=%d o_ld=%d k_ld=%d vt_ld=%d e=%d lk=%d)", q_ld,
                o_ld, k_ld, vt_ld, e, lk);
   LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(o) |
@@ -512,7 +514,7 @@ extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, v
 #define LM2A_ATTN_CASE(D)                                                                     \
   case D:                                                                                     \
     return launch_attn<D>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,   \
-                          vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads)
+                          vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e, heads, n_streams)
   switch (dh) {
     LM2A_ATTN_CASE(32);
     LM2A_ATTN_CASE(64);
@@ -527,4 +529,15 @@ extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, v
   }
 #undef LM2A_ATTN_CASE
   return 0;
+}
+
+extern "C" int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                                    int32_t o_ld, const void* k_motion, const void* vt_motion,
+                                    const void* k_text, const void* vt_text, int32_t k_ld,
+                                    int32_t vt_ld, const int32_t* kv_slot, int32_t slots,
+                                    int32_t rows, int32_t tp, int32_t t_valid, int32_t lk,
+                                    int32_t e, int32_t heads) {
+  return lm2a_cross_attn_streams_bf16(stream, q, q_ld, o, o_ld, k_motion, vt_motion, k_text,
+                                      vt_text, k_ld, vt_ld, kv_slot, slots, rows, tp, t_valid, lk,
+                                      e, heads, 2);
 }

@@ -148,6 +148,8 @@ def pack_block(blk, heads, dev, film_col):
         # output replaces it, unet1d_ultimate.py:152-159): q = Wq (W2 * n + b2) + bq
         wq_all, bq_all = torch.cat(wq, dim=0), torch.cat(bq, dim=0)
         p.wq2, p.bq2 = _finish(wq_all @ w2, wq_all @ b2 + bq_all, dev)
+        # motion stream alone (the lyrics stream is constant in time: see UNetPlan.const_text)
+        p.wq2_m, p.bq2_m = _finish(wq[0] @ w2, wq[0] @ b2 + bq[0], dev)
         p.wkv_m, p.bkv_m = _finish(wkv[0], bkv[0], dev)
         p.wkv_t, p.bkv_t = _finish(wkv[1], bkv[1], dev)
         wf, bf = _f64(ca.fuse_proj.weight), _f64(ca.fuse_proj.bias)
@@ -351,16 +353,39 @@ class UNetPlan:
             for b in pm.attn_blocks:
                 self.kv.append((z(nslots * lk, 2 * b.e), z(nslots * lk, 2 * b.e)))
                 self.vt.append((z(nslots * b.e, self.lk_pad), z(nslots * b.e, self.lk_pad)))
-        self.ops = []
+        # two launch lists over the same buffers: the full one, and the variant used when the
+        # lyrics stream is constant in time for every clip of the batch (what the reference's
+        # preprocessing produces: ONE sentence embedding tiled over all frames,
+        # preprocess.py:64-71). Every key of that stream is then identical, its softmax uniform
+        # and its attention output the stream's single V row: that row is written once per batch
+        # into the text half of a per-block O slab, the per-step attention launch computes the
+        # motion stream only and the Q projection produces motion queries only.
+        self._ops_by_mode = {False: [], True: []}
+        self.const_text = False
+        self._building_ct = False
+        self.allow_const_text = os.environ.get("LM2A_CONST_STREAM", "1") != "0"
+        # per attention block (slab, tp, t_valid, E); allocated in _resblock_rows
+        self.o_ct = [None] * (len(pm.attn_blocks) if use_cond else 0)
         self.kv_ops = []
         self.use_side_stream = True
         self.fuse_gn = fuse_gn and os.environ.get("LM2A_FUSE_GN", "1") != "0"
         self._side = None
         self._side_op = self._side_pending = self._partial_rows = False
-        if pm.kind == "legacy":
-            self._build_legacy()
-        else:
-            self._build()
+        for mode in ((False, True) if use_cond else (False,)):
+            self._building_ct = mode
+            self.kv_ops = []
+            self._attn_i = 0
+            self._side_op = self._side_pending = self._partial_rows = False
+            if pm.kind == "legacy":
+                self._build_legacy()
+            else:
+                self._build()
+        self._building_ct = False
+
+    @property
+    def ops(self):
+        """The launch list in effect (full, or the constant-lyrics-stream variant)."""
+        return self._ops_by_mode[self.const_text]
 
     # -- helpers -------------------------------------------------------------------------
     def _view(self, flat, m, c):
@@ -374,7 +399,7 @@ class UNetPlan:
         elif self._side_pending and not self._partial_rows:
             meta["join"] = True   # first main op that reads rows written on the side stream
             self._side_pending = False
-        self.ops.append((fn, args, meta))
+        self._ops_by_mode[self._building_ct].append((fn, args, meta))
 
     def _conv(self, segs, w, bias, n_valid, m, tp, t_valid, *a, **k):
         """Queues one implicit-GEMM launch; meta carries its ALGORITHMIC flops
@@ -463,9 +488,28 @@ class UNetPlan:
                        tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
             return
         e = p.e
+        (kv_m, kv_t), (vt_m, vt_t) = kv
+        ai = self._attn_i
+        self._attn_i += 1
+        if self._building_ct:
+            # per-block O slab: text half = the stream's V row of each clip (filled once per
+            # batch by _fill_const_text), motion half written by the attention launch each step
+            if self.o_ct[ai] is None:
+                self.o_ct[ai] = (torch.zeros(self.rows * tp, 2 * e, dtype=BF16, device=self.dev),
+                                 tp, tv, e)
+            o_full = self.o_ct[ai][0]
+            o_off = r0 * tp * 2 * e
+            q = self._view(self._q, m, e)
+            self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2_m, p.bq2_m, e, m, tp, tv, q, e)
+            self._add(ops.cross_attn, q, e, o_full, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
+                      ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad,
+                      ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads, 1,
+                      0, o_off, meta={"kind": "cross_attn", "flops": 4 * nr * tv * self.lk * e})
+            self._conv([Seg(o_full, 2 * e, 2 * e, TAPS_K1, m, o_off)] + skip_seg, p.wof, p.bof,
+                       cout, m, tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
+            return
         q = self._view(self._q, m, 2 * e)
         o = self._view(self._o, m, 2 * e)
-        (kv_m, kv_t), (vt_m, vt_t) = kv
         self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2, p.bq2, 2 * e, m, tp, tv, q, 2 * e)
         self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
                   ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad, ops._ptr(self.kv_slot, r0),
@@ -671,6 +715,25 @@ class UNetPlan:
         for fn, args in self.kv_ops:
             fn(*args)
         self.kv_slot.copy_(kv_slot.to(torch.int32))
+        self._fill_const_text()
+
+    def _fill_const_text(self):
+        """Selects the launch list for this batch. The lyrics stream counts as constant in time
+        when, for every cache slot, all Lk rows of the projected condition are bit-identical (a
+        host-side decision, once per batch). Then each block's text-stream attention output is
+        the V row of the clip (softmax over identical keys is uniform): it is broadcast into the
+        text half of the block's O slab here, and the per-step launches skip that stream."""
+        self.const_text = False
+        if not (self.use_cond and self.allow_const_text and self.lk > 1):
+            return
+        c = self.cond_t.view(self.nslots, self.lk, -1)
+        if not bool((c[:, 1:] == c[:, :1]).all()):
+            return
+        slot = self.kv_slot.long()
+        for (kv_m, kv_t), (o_full, tp, tv, e) in zip(self.kv, self.o_ct):
+            v_row = kv_t.view(self.nslots, self.lk, 2 * e)[:, 0, e:]          # [nslots, E] bf16
+            o_full.view(self.rows, tp, 2 * e)[:, :tv, e:] = v_row[slot].unsqueeze(1)
+        self.const_text = True
 
     def cond_slabs(self, first_slot=0):
         """bf16 views [ (nslots - first_slot) * lk, cond_dim ] of the motion / lyrics condition
@@ -686,6 +749,7 @@ class UNetPlan:
         for fn, args in self.kv_ops:
             fn(*args)
         self.kv_slot.copy_(kv_slot.to(torch.int32))
+        self._fill_const_text()
 
     def run(self):
         """Launches the plan on torch's current stream. Ops tagged `side` (the uncond rows'

@@ -185,8 +185,8 @@ class CfgSampler:
         self.noise = torch.zeros(batch, eng.pm.in_dim, t_len, dtype=torch.float32, device=self.dev)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.gw = 1.0
-        self.graph = None
-        self.graph_gw = None
+        self.graph = None          # the captured step in effect
+        self._graphs = {}          # (guidance weight, plan launch-list variant) -> graph
         if ddim is not None:
             taus, eta = ddim
             prevs = list(taus[1:]) + [-1]
@@ -236,9 +236,13 @@ class CfgSampler:
             self.step_idx.zero_()
 
     def _ensure_graph(self):
-        if self.graph is not None and self.graph_gw == self.gw:
-            return
+        """One captured step per (guidance weight, launch-list variant of the plan: full, or
+        constant lyrics stream — chosen per batch when the conditions are set)."""
         p = self.plan
+        key = (self.gw, p.const_text)
+        if key in self._graphs:
+            self.graph = self._graphs[key]
+            return
         keep_x = p.x_in.clone()
         if os.environ.get("LM2A_AUTOTUNE", "0") == "1":
             # measured tile shape per GEMM launch instead of the wave model: opt-in — it raises
@@ -258,7 +262,7 @@ class CfgSampler:
             self._step(draw)
         p.x_in.copy_(keep_x)
         self.ticket.zero_()
-        self.graph, self.graph_gw = g, self.gw
+        self._graphs[key] = self.graph = g
 
     @torch.no_grad()
     def run(self, motion_f, text_f, guidance_weight=1.0, x_init=None, noises=None,

@@ -132,11 +132,12 @@ def gn_silu(x, x_ld, y, y_ld, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-
 
 
 def cross_attn(q, q_ld, o, o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, kv_slot, slots, rows, tp,
-               t_valid, lk, e, heads):
-    _lib.check(_lib.load().lm2a_cross_attn_bf16(
-        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld,
+               t_valid, lk, e, heads, n_streams=2, q_off=0, o_off=0):
+    """q_off / o_off: element offsets into the q / o slabs (row sub-range of a shared slab)."""
+    _lib.check(_lib.load().lm2a_cross_attn_streams_bf16(
+        _stream(), _ptr(q, q_off), q_ld, _ptr(o, o_off), o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld,
         kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows,
-        tp, t_valid, lk, e, heads), "lm2a_cross_attn_bf16")
+        tp, t_valid, lk, e, heads, n_streams), "lm2a_cross_attn_bf16")
 
 
 def transpose_kv(src, src_ld, src_off, dst, dst_ld, slots, lk, c):

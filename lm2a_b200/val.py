@@ -100,7 +100,7 @@ def assess_batch(npz_dir, ckpt_path, out_dir, device="cuda", max_samples=None, r
     length are sampled `batch_size` at a time (raw conditions resampled / projected on the GPU)
     and their metrics come from one lm2a_mel_metrics launch on the device-resident mels. Writes
     `<base>_metrics.txt`, `<base>_gen_mel.npz` (same keys as sample.py:250-256) and
-    `average_metrics.txt`; returns the averaged metrics."""
+    `average_metrics.txt`; returns (averaged metrics, {clip name: metrics})."""
     os.makedirs(out_dir, exist_ok=True)
     device = torch.device(device)
     if device.type != "cuda":

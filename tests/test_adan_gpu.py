@@ -76,4 +76,4 @@ def test_adan_large_ragged_tensors_vs_oracle():
             assert torch.equal(opt.state[p]["v"], st["v"])
             np.testing.assert_allclose(p.detach().cpu().numpy(), c.cpu().numpy(), rtol=5e-7,
                                        atol=1e-9, err_msg=f"step {step}")
-    assert float(params[3].abs().sum()) == 0.0 and len(opt.state[params[3]]) == 0
+    assert float(params[3].detach().abs().sum()) == 0.0 and len(opt.state[params[3]]) == 0

@@ -50,6 +50,31 @@ def test_legacy_forward_matches_reference_golden(golden_dir, name):
     assert torch.equal(net(x, t, mf, tf), eps)
 
 
+def test_legacy_full_length_vs_oracle():
+    """The width the reference trains (base 256: head dims 64..384, decoder widths 1536 / 768 /
+    512) at the canonical clip length T = Lk = 516 with CFG-style rows (uncond = zeroed
+    conditions) against the fp32 oracle: multi-tile attention at every head dim, fused
+    GroupNorm epilogues, transposed convs at 64 -> 128 (+pad) / 129 -> 258 / 258 -> 516."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = orc.LegacyConfig(80, 256, (1, 2, 4), 128, 256)
+    sd = orc.legacy_random_state_dict(cfg, 22)
+    net = _model(cfg, sd)
+    g = torch.Generator().manual_seed(177)
+    x1 = torch.randn(1, 80, 516, generator=g)
+    mf1 = torch.randn(1, 516, 128, generator=g)
+    tf1 = torch.randn(1, 516, 128, generator=g)
+    x = torch.cat([x1, x1])
+    mf, tf = torch.cat([mf1 * 0, mf1]), torch.cat([tf1 * 0, tf1])
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        ref = orc.legacy_unet_forward(sd, cfg, x, t, mf, tf)
+    eps = net(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
+    assert torch.isfinite(eps).all()
+    err = _rel(eps, ref)
+    assert err < TOL_BF16, f"eps rel-L2 {err:.3e}"
+
+
 def test_legacy_guided_trajectory_vs_oracle():
     """CFG loop (sample.py:144-210) around the legacy model: [uncond, cond] rows, uncond rows on
     the attention-constant shortcut, posterior update; 6 steps with injected noise."""
