@@ -375,6 +375,7 @@ class UNetPlan:
             self._building_ct = mode
             self.kv_ops = []
             self._attn_i = 0
+            self._shared_rows = 0
             self._side_op = self._side_pending = self._partial_rows = False
             if pm.kind == "legacy":
                 self._build_legacy()
@@ -422,16 +423,26 @@ class UNetPlan:
         u = self.uncond_rows if (p.attn and self.use_cond) else 0
         if u > 0:
             # rows [0, u) only need skip(x) + const: one small launch, independent of the cond
-            # rows' pipeline below -> side stream; the block's own main ops touch rows >= u only
+            # rows' pipeline below -> side stream; the block's own main ops touch rows >= u only.
+            # While the CFG copies are still identical (_shared_rows: nothing has attended yet)
+            # the uncond rows' input is read from the cond copy of the same clip.
             self._side_op = True
-            self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u)
+            self._uncond_block(p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u,
+                               self._shared_rows)
             self._side_op = False
             self._partial_rows = True
+            self._shared_rows = 0
+        elif self._shared_rows:
+            # no attention yet: uncond row b == cond row B + b, compute the cond copy only
+            self._resblock_rows(p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st,
+                                kv, self._shared_rows, self.rows - self._shared_rows)
+            return
         self._resblock_rows(p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st, kv,
                             u, self.rows - u)
         self._partial_rows = False
 
-    def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u):
+    def _uncond_block(self, p, lvl, xin, xin_ld, xin_off, out, out_ld, out_off, out_st, u,
+                      src_row0=0):
         """Rows whose conditions are all-zero (sample.py:155-157): every key of a stream is the
         same vector, softmax is exactly uniform, the attention output is the constant
         fuse(out_proj(v_row)) and replaces h (unet1d_ultimate.py:152-159) -> out = skip(x) + c."""
@@ -439,6 +450,7 @@ class UNetPlan:
         tp, tv = g.Tp[lvl], g.T[lvl]
         m = u * tp
         st = out_st.view(0, out_off)
+        xin_off = xin_off + src_row0 * tp * xin_ld   # element offset of the source row range
         if p.has_skip:
             self._conv([Seg(xin, xin_ld, p.cin, TAPS_K1, m, xin_off)], p.wsk, p.bsk_c, p.cout, m,
                        tp, tv, out, out_ld, out_chan_off=out_off, stats=st)
@@ -551,8 +563,16 @@ class UNetPlan:
                   self.t, g.Tp[0], pm.in_pad)
         cur = self._view(self._pp[0], g.M[0], pm.base)
         cur_st = self._stats(rows, 0, pm.base, 8)
-        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
-                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim, stats=cur_st)
+        # CFG copies are identical up to the first (attention) block: input_proj runs on the cond
+        # copies only, the first block's uncond rows read from there (see _build)
+        if (self.copies == 2 and self.uncond_rows == self.batch and self.uniform_t
+                and os.environ.get("LM2A_SHARE_CFG_ROWS", "1") != "0"):
+            self._shared_rows = self.batch
+        r0 = self._shared_rows
+        m0 = (rows - r0) * g.Tp[0]
+        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, m0, r0 * g.Tp[0] * pm.in_pad)],
+                   pm.w_in, pm.b_in, pm.base, m0, g.Tp[0], g.T[0], cur, pm.base,
+                   out_chan_off=r0 * g.Tp[0] * pm.base, k_real=pm.in_dim, stats=cur_st.view(r0, 0))
         cur_c, pp = pm.base, 1
         # concat slab of level l: [transposed-conv output (dims[l]) | skip (c_l)], normalised as
         # a whole by the decoder block. The transposed conv writes it as two launches (even / odd
@@ -620,8 +640,20 @@ class UNetPlan:
         cur = self._view(self._pp[0], g.M[0], pm.base)
         first = pm.downs[0][0][0]
         cur_st = self._stats(rows, 0, pm.base, groups_of(first.gn1))
-        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, g.M[0])], pm.w_in, pm.b_in,
-                   pm.base, g.M[0], g.Tp[0], g.T[0], cur, pm.base, k_real=pm.in_dim, stats=cur_st)
+        # CFG: the uncond and cond copies of a clip are identical until the first attention block
+        # (nothing depends on the conditions before it). With the uncond shortcut on, in_proj and
+        # the leading attention-free ResBlocks run on the cond copies (rows >= B) only and the
+        # first attention block's uncond rows read their input from there.
+        self._shared_rows = 0
+        if (self.copies == 2 and self.use_cond and self.uncond_rows == self.batch
+                and self.uniform_t and not first.attn
+                and os.environ.get("LM2A_SHARE_CFG_ROWS", "1") != "0"):
+            self._shared_rows = self.batch
+        r0 = self._shared_rows
+        m0 = (rows - r0) * g.Tp[0]
+        self._conv([Seg(self.x_slab, pm.in_pad, pm.in_pad, TAPS_K1, m0, r0 * g.Tp[0] * pm.in_pad)],
+                   pm.w_in, pm.b_in, pm.base, m0, g.Tp[0], g.T[0], cur, pm.base,
+                   out_chan_off=r0 * g.Tp[0] * pm.base, k_real=pm.in_dim, stats=cur_st.view(r0, 0))
         cur_c, pp = pm.base, 1
 
         # the concat slab of level l is normalised as a whole by the first up block of that
