@@ -377,6 +377,7 @@ class UNetPlan:
             self._attn_i = 0
             self._shared_rows = 0
             self._side_op = self._side_pending = self._partial_rows = False
+            self._hold_join = self._force_join = False
             if pm.kind == "legacy":
                 self._build_legacy()
             else:
@@ -397,7 +398,11 @@ class UNetPlan:
         if self._side_op:
             meta["side"] = True
             self._side_pending = True
-        elif self._side_pending and not self._partial_rows:
+        elif self._force_join:
+            # first launch of the first ResBlock: the FiLM tables of the side branch must be there
+            meta["join"] = True
+            self._force_join = self._side_pending = False
+        elif self._side_pending and not self._partial_rows and not self._hold_join:
             meta["join"] = True   # first main op that reads rows written on the side stream
             self._side_pending = False
         self._ops_by_mode[self._building_ct].append((fn, args, meta))
@@ -555,10 +560,13 @@ class UNetPlan:
         kv_iter = iter(zip(self.kv, self.vt))
         self._build_kv_ops()
         # TimestepEmbedding output itself (one SiLU): time_proj has no activation in front
+        self._side_op = True
         self._add(ops.time_embed, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,
                   pm.time_dim, False, meta={"kind": "time_mlp", "flops": 0})
         self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, self.t_rows,
                   pm.time_dim, pm.film_cols)
+        self._side_op = False
+        self._hold_join = True
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
                   self.t, g.Tp[0], pm.in_pad)
         cur = self._view(self._pp[0], g.M[0], pm.base)
@@ -574,6 +582,7 @@ class UNetPlan:
                    pm.w_in, pm.b_in, pm.base, m0, g.Tp[0], g.T[0], cur, pm.base,
                    out_chan_off=r0 * g.Tp[0] * pm.base, k_real=pm.in_dim, stats=cur_st.view(r0, 0))
         cur_c, pp = pm.base, 1
+        self._hold_join, self._force_join = False, True
         # concat slab of level l: [transposed-conv output (dims[l]) | skip (c_l)], normalised as
         # a whole by the decoder block. The transposed conv writes it as two launches (even / odd
         # slots) in the geometry of level l+1, so its statistics need two slice ranges.
@@ -628,11 +637,15 @@ class UNetPlan:
 
         self._build_kv_ops()
 
-        # timestep embedding + all FiLM tables, once per step
+        # timestep embedding + all FiLM tables, once per step: a parallel branch (side stream)
+        # next to x ingest + in_proj; the first ResBlock joins it
+        self._side_op = True
         self._add(ops.time_mlp, self.t_in, pm.time_w, pm.time_b, self.silu_temb, self.t_rows,
                   pm.time_dim)
         self._add(ops.film, self.silu_temb, pm.film_w, pm.film_b, self.film, self.t_rows,
                   pm.time_dim, pm.film_cols)
+        self._side_op = False
+        self._hold_join = True
         # x -> bf16 slab (CFG row duplication happens here), in_proj
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
                   self.t, g.Tp[0], pm.in_pad)
@@ -655,6 +668,7 @@ class UNetPlan:
                    pm.w_in, pm.b_in, pm.base, m0, g.Tp[0], g.T[0], cur, pm.base,
                    out_chan_off=r0 * g.Tp[0] * pm.base, k_real=pm.in_dim, stats=cur_st.view(r0, 0))
         cur_c, pp = pm.base, 1
+        self._hold_join, self._force_join = False, True
 
         # the concat slab of level l is normalised as a whole by the first up block of that
         # level; its two halves are written by different kernels into one Stats buffer
