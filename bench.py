@@ -254,9 +254,23 @@ def run_b200(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the lm2a_b200 path has no CPU fallback")
-    rank, world, local_rank = ldist.init_from_env("nccl")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: NCCL prints its "NCCL version ..." banner to stdout
+    # when the communicator is created (NCCL_DEBUG=VERSION / WARN), so fd 1 points at stderr until
+    # the first collective has run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local_rank = ldist.init_from_env("nccl")
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     steps, warmup = args.steps, max(3, args.warmup)
 
     cfg = orc.UNetConfig.production()
@@ -467,16 +481,12 @@ def run_b200(args):
                 "ms_per_step": s * 1e3,
                 "sample": f"{n} CFG denoising steps of 1 clip (2 rows) after 2 warm-up, fp32 torch "
                           "CPU oracle port of sample.py:144-210; x1000-step extrapolation"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
-    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to
-    # stdout at NCCL_DEBUG=VERSION) out of it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

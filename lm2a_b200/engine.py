@@ -165,6 +165,13 @@ def pack_block(blk, heads, dev, film_col):
             p.wsk, p.bsk_c = _finish(wskip, bskip + c_unc, dev)
         p.c_uncond = c_unc.to(dev, torch.float32).contiguous()
         p.wof, p.bof = _finish(wof, bof, dev)
+        # constant lyrics stream: out = [O_m (| x)] [Wf1 Wo_m (| Wskip)]^T + b + (Wf2 Wo_t) v_t,
+        # the last term a per-clip vector computed once per batch from the clip's V row
+        wof_m = wf[:, :e] @ wo[0]
+        if has_skip:
+            wof_m = torch.cat([wof_m, wskip], dim=1)
+        p.wof_m, p.bof_m = _finish(wof_m, bof, dev)
+        p.wof_t, p.zero_b = _finish(wf[:, e:] @ wo[1], torch.zeros_like(bof), dev)
     return p
 
 
@@ -357,15 +364,18 @@ class UNetPlan:
         # lyrics stream is constant in time for every clip of the batch (what the reference's
         # preprocessing produces: ONE sentence embedding tiled over all frames,
         # preprocess.py:64-71). Every key of that stream is then identical, its softmax uniform
-        # and its attention output the stream's single V row: that row is written once per batch
-        # into the text half of a per-block O slab, the per-step attention launch computes the
-        # motion stream only and the Q projection produces motion queries only.
+        # and its attention output the stream's single V row: its image under the folded output
+        # projection is computed once per batch as a per-clip shift of the block's output GEMM,
+        # the per-step attention launch computes the motion stream only and the Q projection
+        # produces motion queries only.
         self._ops_by_mode = {False: [], True: []}
         self.const_text = False
         self._building_ct = False
         self.allow_const_text = os.environ.get("LM2A_CONST_STREAM", "1") != "0"
-        # per attention block (slab, tp, t_valid, E); allocated in _resblock_rows
-        self.o_ct = [None] * (len(pm.attn_blocks) if use_cond else 0)
+        # per attention block: fp32 [rows, 2 * cout] table (zero scale | per-clip shift), built by
+        # ct_ops once per batch
+        self.ct_tab = [None] * (len(pm.attn_blocks) if use_cond else 0)
+        self.ct_ops = []
         self.kv_ops = []
         self.use_side_stream = True
         self.fuse_gn = fuse_gn and os.environ.get("LM2A_FUSE_GN", "1") != "0"
@@ -463,6 +473,24 @@ class UNetPlan:
             self._add(ops.bias_add, xin, xin_ld, xin_off, out, out_ld, out_off, p.c_uncond, m, tp,
                       tv, p.cout, st, meta={"kind": "bias_add", "flops": 0})
 
+    def _make_ct_table(self, ai, p, kv_t):
+        """Per-batch setup of attention block `ai` for the constant-lyrics launch list: the clip's
+        V row (all Lk rows of the text V cache are identical) -> c = (Wf2 Wo_t) v as one small
+        implicit-GEMM launch with fp32 output -> shift half of the block's per-row table."""
+        e, cout, n = p.e, p.cout, self.nslots
+        tab = torch.zeros(self.rows, 2 * cout, dtype=torch.float32, device=self.dev)
+        v_rows = torch.zeros(n, e, dtype=BF16, device=self.dev)
+        c_t = torch.zeros(1, cout, n, dtype=torch.float32, device=self.dev)
+        desc = ops.make_conv_desc([Seg(v_rows, e, e, TAPS_K1, n)], p.wof_t, p.zero_b, cout, n, n, n,
+                                  c_t, 0, out_mode=OUT_F32_NCT, block_n=128)
+        self.ct_tab[ai] = tab
+
+        def fill():
+            v_rows.copy_(kv_t.view(n, self.lk, 2 * e)[:, 0, e:])
+            ops.conv1d(desc)
+            tab[:, cout:] = c_t[0].t()[self.kv_slot.long()]
+        self.ct_ops.append(fill)
+
     def _resblock_rows(self, p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st,
                        kv, r0, nr):
         g = self.geo
@@ -509,21 +537,20 @@ class UNetPlan:
         ai = self._attn_i
         self._attn_i += 1
         if self._building_ct:
-            # per-block O slab: text half = the stream's V row of each clip (filled once per
-            # batch by _fill_const_text), motion half written by the attention launch each step
-            if self.o_ct[ai] is None:
-                self.o_ct[ai] = (torch.zeros(self.rows * tp, 2 * e, dtype=BF16, device=self.dev),
-                                 tp, tv, e)
-            o_full = self.o_ct[ai][0]
-            o_off = r0 * tp * 2 * e
+            # motion stream only; the lyrics stream's contribution (Wf2 Wo_t) v_t is a per-clip
+            # vector: a per-row epilogue shift of the output GEMM, read from the block's table
+            if self.ct_tab[ai] is None:
+                self._make_ct_table(ai, p, kv_t)
             q = self._view(self._q, m, e)
+            o = self._view(self._o, m, e)
             self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2_m, p.bq2_m, e, m, tp, tv, q, e)
-            self._add(ops.cross_attn, q, e, o_full, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
+            self._add(ops.cross_attn, q, e, o, e, ops._ptr(kv_m), ops._ptr(vt_m),
                       ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad,
                       ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads, 1,
-                      0, o_off, meta={"kind": "cross_attn", "flops": 4 * nr * tv * self.lk * e})
-            self._conv([Seg(o_full, 2 * e, 2 * e, TAPS_K1, m, o_off)] + skip_seg, p.wof, p.bof,
-                       cout, m, tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
+                      meta={"kind": "cross_attn", "flops": 4 * nr * tv * self.lk * e})
+            self._conv([Seg(o, e, e, TAPS_K1, m)] + skip_seg, p.wof_m, p.bof_m, cout, m, tp, tv,
+                       out, out_ld, out_chan_off=oo, stats=ost, film=self.ct_tab[ai], film_col=0,
+                       film_shift_off=cout, film_bcast=False, film_row=r0, **res)
             return
         q = self._view(self._q, m, 2 * e)
         o = self._view(self._o, m, 2 * e)
@@ -767,18 +794,17 @@ class UNetPlan:
         """Selects the launch list for this batch. The lyrics stream counts as constant in time
         when, for every cache slot, all Lk rows of the projected condition are bit-identical (a
         host-side decision, once per batch). Then each block's text-stream attention output is
-        the V row of the clip (softmax over identical keys is uniform): it is broadcast into the
-        text half of the block's O slab here, and the per-step launches skip that stream."""
+        the V row of the clip (softmax over identical keys is uniform): its image under the folded
+        output projection becomes a per-clip shift of the block's output GEMM (_make_ct_table),
+        and the per-step launches skip that stream."""
         self.const_text = False
         if not (self.use_cond and self.allow_const_text and self.lk > 1):
             return
         c = self.cond_t.view(self.nslots, self.lk, -1)
         if not bool((c[:, 1:] == c[:, :1]).all()):
             return
-        slot = self.kv_slot.long()
-        for (kv_m, kv_t), (o_full, tp, tv, e) in zip(self.kv, self.o_ct):
-            v_row = kv_t.view(self.nslots, self.lk, 2 * e)[:, 0, e:]          # [nslots, E] bf16
-            o_full.view(self.rows, tp, 2 * e)[:, :tv, e:] = v_row[slot].unsqueeze(1)
+        for fill in self.ct_ops:
+            fill()
         self.const_text = True
 
     def cond_slabs(self, first_slot=0):
