@@ -75,9 +75,11 @@ def test_legacy_full_length_vs_oracle():
     assert err < TOL_BF16, f"eps rel-L2 {err:.3e}"
 
 
-def test_legacy_guided_trajectory_vs_oracle():
+@pytest.mark.parametrize("tiled_lyrics", [False, True])
+def test_legacy_guided_trajectory_vs_oracle(tiled_lyrics):
     """CFG loop (sample.py:144-210) around the legacy model: [uncond, cond] rows, uncond rows on
-    the attention-constant shortcut, posterior update; 6 steps with injected noise."""
+    the attention-constant shortcut, posterior update; 6 steps with injected noise. With a lyrics
+    condition tiled over time (the reference's real data) the one-stream launch list is used."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from lm2a_b200.models import GaussianDiffusion
@@ -89,10 +91,13 @@ def test_legacy_guided_trajectory_vs_oracle():
     x0 = torch.randn(bsz, 80, t_len, generator=g)
     mf = torch.randn(bsz, lk, 128, generator=g)
     tf = torch.randn(bsz, lk, 128, generator=g)
+    if tiled_lyrics:
+        tf = tf[:, :1].expand(bsz, lk, 128).contiguous()
     noises = torch.randn(steps - 1, bsz, 80, t_len, generator=g)
     diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
     got = diff.sample_cfg((bsz, 80, t_len), mf.cuda(), tf.cuda(), gw, x_init=x0.cuda(),
                           noises=noises.cuda())
+    assert diff.sampler(bsz, t_len, lk, True).plan.const_text is tiled_lyrics
     with torch.no_grad():
         ref = orc.sample_loop(sd, cfg, mf, tf, (bsz, 80, t_len), steps, gw, x0, list(noises))
     assert torch.isfinite(got).all()
