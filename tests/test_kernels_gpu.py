@@ -449,6 +449,26 @@ def test_resample_seq_is_bit_exact_vs_numpy_interp(ops, t_in, t_out, c):
     assert bool((sv[:, t_out:, :] == 0).all()) and bool((sv[:, :, c:] == 0).all())
 
 
+def test_loop_side_entry_points_reject_bad_arguments(ops):
+    """Argument violations return an error BEFORE any launch (C ABI convention)."""
+    x = torch.zeros(2, 10, 8, device="cuda")
+    with pytest.raises(RuntimeError, match="resample_seq"):
+        ops.resample_seq(x, None, None, None, 2, 10, 8, 20, 20, 8)          # no output at all
+    with pytest.raises(RuntimeError, match="resample_seq"):
+        ops.resample_seq(x, None, torch.zeros(2, 20, 8, device="cuda"), None, 2, 10, 8, 20, 19, 8)
+    with pytest.raises(RuntimeError, match="mel_metrics"):
+        ops.mel_metrics(torch.zeros(1, 80, 8, device="cuda"), torch.zeros(1, 80, 8, device="cuda"),
+                        torch.zeros(1, 8, dtype=torch.float64, device="cuda"), 1, 80, 8)
+    with pytest.raises(RuntimeError, match="cfg_ddim"):
+        ops.cfg_ddim(torch.zeros(1, 80, 7, device="cuda"), torch.zeros(1, 80, 7, device="cuda"), None,
+                     torch.zeros(8, device="cuda"), None, torch.zeros(1, dtype=torch.int32, device="cuda"),
+                     None, None, 1, 80 * 7 + 1, 1.0, False, False)
+    q = torch.zeros(4 * 66, 256, dtype=BF16, device="cuda")
+    with pytest.raises(RuntimeError, match="n_streams"):
+        ops.cross_attn(q, 256, q, 256, ops._ptr(q), ops._ptr(q), ops._ptr(q), ops._ptr(q), 256, 64,
+                       torch.zeros(4, dtype=torch.int32, device="cuda"), 1, 4, 66, 64, 64, 128, 4, 3)
+
+
 def test_upsample2x(ops):
     r, t_in, c = 3, 129, 128
     tp_in, tp_out = 130, 260

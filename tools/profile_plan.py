@@ -1,5 +1,6 @@
 """Per-launch device times of one CFG denoising step (B clips, production net), CUDA events.
-    python tools/profile_plan.py [B] > profiles/plan_Bxx.csv
+    python tools/profile_plan.py [B] [T] [tiled] > profiles/plan_Bxx.csv
+`tiled`: lyrics condition tiled over time (the reference's real data) -> one-stream launch list.
 """
 import os
 import sys
@@ -22,7 +23,13 @@ diff = GaussianDiffusion(net, timesteps=1000, device=dev)
 s = diff.sampler(B, T, T, guided=True)
 s.gw = 2.1
 g = torch.Generator().manual_seed(0)
-s.set_conditions(torch.randn(B, T, 128, generator=g).to(dev), torch.randn(B, T, 128, generator=g).to(dev))
+tiled = len(sys.argv) > 3 and sys.argv[3] == "tiled"
+mf = torch.randn(B, T, 128, generator=g)
+tf = torch.randn(B, T, 128, generator=g)
+if tiled:
+    tf = tf[:, :1].expand(B, T, 128).contiguous()
+s.set_conditions(mf.to(dev), tf.to(dev))
+assert s.plan.const_text is tiled
 s.plan.x_in.normal_()
 s.plan.t_in.fill_(500)
 prof = s.plan.profile(iters=10)
