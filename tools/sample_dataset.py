@@ -55,8 +55,24 @@ def main():
     n_batches = (n_local + a.batch - 1) // a.batch
     a.batch = (n_local + n_batches - 1) // n_batches
 
+    # host-side clip preparation (stands in for np.load of the npz files) runs one batch ahead on
+    # a thread, under the GPU's sampling of the current batch
+    import concurrent.futures
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+    mine = ldist.shard_indices(a.clips, rank, world)
+    todo = list(ldist.batches(mine, a.batch))
+    make = lambda idx: [orc.synthetic_clip(i, t_mel=t_mel, time_varying_lyrics=True)  # noqa: E731
+                        for i in idx]
+    pending = {0: pool.submit(make, todo[0])} if todo else {}
+    cursor = [0]
+
     def sample_batch(idx):
-        clips = [orc.synthetic_clip(i, t_mel=t_mel, time_varying_lyrics=True) for i in idx]
+        k = cursor[0]
+        assert list(idx) == list(todo[k])
+        clips = pending.pop(k).result()
+        if k + 1 < len(todo):
+            pending[k + 1] = pool.submit(make, todo[k + 1])
+        cursor[0] += 1
         n = len(clips)
         # a ragged last batch is padded to the plan's batch size (one graph per batch size)
         while len(clips) < a.batch:
@@ -77,6 +93,8 @@ def main():
 
     barrier()
     t0 = time.perf_counter()
+    if todo:   # the clock starts with nothing prepared: re-issue the first batch's preparation
+        pending[0] = pool.submit(make, todo[0])
     local = ldist.sample_sharded(a.clips, a.batch, sample_batch, (80, t_mel), dev, rank, world,
                                  gather=False)
     torch.cuda.synchronize(dev)
