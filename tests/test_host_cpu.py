@@ -52,6 +52,16 @@ def test_state_dict_layout_matches_reference_inventory():
     assert len(res.missing_keys) == 305
 
 
+def test_torch_custom_ops_are_cuda_only():
+    """torch.ops.lm2a.* (lm2a_b200/torch_ops.py) exist with CUDA kernels only: a CPU tensor finds no
+    implementation (no fallback was registered)."""
+    import lm2a_b200.torch_ops  # noqa: F401
+    for name in ("cfg_posterior", "cfg_ddim", "resample_seq", "mel_metrics", "gn_silu", "upsample2x"):
+        assert hasattr(torch.ops.lm2a, name)
+    with pytest.raises(NotImplementedError):
+        torch.ops.lm2a.resample_seq(torch.zeros(1, 4, 3), None, 8)
+
+
 def test_cpu_tensors_are_refused():
     from lm2a_b200.models import UNet1D_ultimate
     net = UNet1D_ultimate(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)

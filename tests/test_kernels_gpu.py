@@ -469,6 +469,28 @@ def test_loop_side_entry_points_reject_bad_arguments(ops):
                        torch.zeros(4, dtype=torch.int32, device="cuda"), 1, 4, 66, 64, 64, 128, 4, 3)
 
 
+def test_torch_custom_op_layer(ops):
+    """torch.ops.lm2a.* dispatch to the same C-ABI kernels as lm2a_b200.ops."""
+    import numpy as np
+    import lm2a_oracle as orc
+    import lm2a_b200.torch_ops  # noqa: F401
+    x = rnd(2, 37, 10, seed=90)
+    got = torch.ops.lm2a.resample_seq(x, None, 64)
+    want = np.stack([orc.match_len_interp(x[i].cpu().numpy(), 64) for i in range(2)])
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    # in-place posterior update through the op == through ops.cfg_posterior
+    xa, eps, nz = rnd(2, 80, 64, seed=91), rnd(4, 80, 64, seed=92), rnd(2, 80, 64, seed=93)
+    sched = torch.rand(10, 4, device="cuda")
+    xb = xa.clone()
+    t1 = torch.full((2,), 7, dtype=torch.int64, device="cuda")
+    t2 = t1.clone()
+    torch.ops.lm2a.cfg_posterior(xa, eps, nz, sched, t1, None, 2.1, True, False)
+    ops.cfg_posterior(xb, eps, nz, sched, t2, None, 2, 80 * 64, 2.1, True, False)
+    assert torch.equal(xa, xb)
+    m = torch.ops.lm2a.mel_metrics(rnd(1, 80, 40, seed=94), rnd(1, 80, 40, seed=95), 1.0, 0.0)
+    assert m.shape == (1, 8) and torch.isfinite(m).all()
+
+
 def test_upsample2x(ops):
     r, t_in, c = 3, 129, 128
     tp_in, tp_out = 130, 260
