@@ -30,10 +30,11 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
+    extra = os.environ.get("LM2A_NVCC_DEFS", "").split()   # e.g. -DLM2A_CONV_TIMING (probe builds)
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
+               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", *extra,
                "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
         objs.append(obj)

@@ -25,6 +25,14 @@
 
 namespace lm2a {
 
+#ifdef LM2A_CONV_TIMING
+// Instrumented build (python -m lm2a_b200.build with LM2A_NVCC_DEFS=-DLM2A_CONV_TIMING, see
+// tools/conv_stall_probe.py): cycles the MMA-issuing thread waits for operands (full barriers) /
+// for a free accumulator, cycles the TMA producer waits for a free stage, and the CTA lifetime,
+// summed over all CTAs. Not part of the product build.
+__device__ unsigned long long g_conv_timing[8];
+#endif
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -169,6 +177,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+#ifdef LM2A_CONV_TIMING
+      long long t_prod_wait = 0;
+#endif
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int m0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
         const int n0 = (tile % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
@@ -195,7 +206,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             for (int cb = 0; cb < cblk; ++cb, ++kb) {
               // first tile: the W box of the first stages is already in flight (see above)
               const bool w_done = tile == unit && kb < w_prefetched;
+#ifdef LM2A_CONV_TIMING
+              const long long tw0 = clock64();
+#endif
               if (!w_done) mbar_wait(empty_bar(stage), phase ^ 1u);
+#ifdef LM2A_CONV_TIMING
+              t_prod_wait += clock64() - tw0;
+#endif
               if (CG == 2) {
                 // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
                 const uint32_t fb = mapa_shared(full_bar(stage), 0);
@@ -216,21 +233,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
       }
+#ifdef LM2A_CONV_TIMING
+      atomicAdd(&g_conv_timing[2], (unsigned long long)t_prod_wait);
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer (pair: the leader CTA only)
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+#ifdef LM2A_CONV_TIMING
+      long long t_full_wait = 0, t_acc_wait = 0;
+      const long long t_begin = clock64();
+#endif
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         if (!fuse_gn) {
+#ifdef LM2A_CONV_TIMING
+          const long long ta0 = clock64();
+#endif
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+#ifdef LM2A_CONV_TIMING
+          t_acc_wait += clock64() - ta0;
+#endif
           tc_fence_after_sync();
         }
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
 #pragma unroll 1
         for (int kb = 0; kb < p.num_kb; ++kb) {
+#ifdef LM2A_CONV_TIMING
+          const long long tf0 = clock64();
+#endif
           mbar_wait(full_bar(stage), phase);
+#ifdef LM2A_CONV_TIMING
+          t_full_wait += clock64() - tf0;
+#endif
           tc_fence_after_sync();
           const uint64_t adesc = umma_desc_sw128_kmajor(a_tile(stage));
           const uint64_t bdesc = umma_desc_sw128_kmajor(b_tile(stage));
@@ -258,6 +294,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           if (acc == 0) acc_phase ^= 1u;
         }
       }
+#ifdef LM2A_CONV_TIMING
+      atomicAdd(&g_conv_timing[0], (unsigned long long)t_full_wait);
+      atomicAdd(&g_conv_timing[1], (unsigned long long)t_acc_wait);
+      atomicAdd(&g_conv_timing[3], (unsigned long long)(clock64() - t_begin));
+      atomicAdd(&g_conv_timing[4], 1ull);
+#endif
     }
   } else {
     // ----------------------------------------------------------------- epilogue
@@ -901,3 +943,14 @@ extern "C" int lm2a_conv_gn_fusable(int64_t m, int32_t n_pad) {
   if (m <= 0 || n_pad <= 0 || n_pad % 128 != 0) return 0;
   return lm2a::choose_tile(m, n_pad, true).block_n != 0 ? 1 : 0;
 }
+
+#ifdef LM2A_CONV_TIMING
+// instrumented build only: read (and clear) the counters of g_conv_timing into out[8]
+extern "C" int lm2a_conv_timing_read(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, lm2a::g_conv_timing, 8 * sizeof(unsigned long long)) != cudaSuccess)
+    return 1;
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  return cudaMemcpyToSymbol(lm2a::g_conv_timing, zero, sizeof(zero)) == cudaSuccess ? 0 : 1;
+}
+#endif
