@@ -88,6 +88,17 @@ class ClockSampler:
                 pass
             time.sleep(0.004)
 
+    def sample_now(self):
+        """One synchronous sample (called right after the timed launches are enqueued, while the
+        GPU is still executing them): even a 2-step timed region gets a reading."""
+        if self.nvml is None:
+            return
+        try:
+            h = self.nvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(h, self.nvml.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+
     def start(self):
         try:
             import pynvml
@@ -320,6 +331,8 @@ def run_b200(args):
         for _ in range(steps):
             sampler.graph.replay()
         e1.record(stream)
+        if rank == 0:
+            clocks.sample_now()
         barrier()
         ms = e0.elapsed_time(e1)
         clk = clocks.stop() if rank == 0 else None
