@@ -16,7 +16,8 @@
  * a k=3 conv is three shifted 2-D TMA boxes over the flattened slab.
  *
  * Reference symbols replaced (paths relative to the reference repo):
- *   lm2a_conv1d_bf16   nn.Conv1d k1/k3/k4s2 + bias (+FiLM, +skip conv, +residual)
+ *   lm2a_conv1d_bf16   nn.Conv1d k1/k3/k4s2 + bias (+GroupNorm/SiLU of its input,
+ *                      +FiLM, +skip conv, +residual, +GroupNorm sums of its output)
  *                      models/unet1d_ultimate.py:87-88,115,138-148,159,216-221,
  *                      255-261,295,364 and every nn.Linear / MHA in/out
  *                      projection of models/cross_attention.py:19-36,46-65
@@ -44,7 +45,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 6
+#define LM2A_ABI_VERSION 7
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -88,41 +89,40 @@ typedef struct lm2a_conv_desc {
   void* out;              /* bf16 slab [m, out_ld] or fp32 [R, n_valid, t_valid] */
   int32_t out_ld;
   int32_t block_n;        /* 0 = auto, else 128 or 256                        */
-  /* Optional partial GroupNorm statistics of the OUTPUT (bf16 slab mode only),
-   * consumed by lm2a_gn_apply_bf16. float2 {sum, sum of squares} at
-   *   stats[((r*stats_sub + c/stats_gran) * stats_ns) + slice]
-   * for clip-row r (relative to this launch), output channel c (relative to
-   * `out`), slice = ceil(t_first/32) of the 32-slot warp segment that starts at
-   * slot t_first of the clip. Every slice is written by exactly one warp
-   * (plain store): allocate zeroed, never clear. stats_ns >= tp/32 + 2.       */
+  /* Optional exact GroupNorm sums of the OUTPUT (bf16 slab mode only), consumed by
+   * the next conv's in_gn_* transform or by lm2a_gn_apply_bf16: two int64 per
+   * (clip-row r relative to this launch, group g = (stats_c0 + c) / stats_cg of
+   * output channel c relative to `out`) at stats[(r * stats_pitch + g) * 2 + {0, 1}] =
+   * {sum * 2^24, sum of squares * 2^20} in fixed point. Each lane converts the fp32
+   * sums of its own slot and the rest is integer addition (shuffle tree + one
+   * atomic per (clip-row, group) and warp), so the totals are exact and do not
+   * depend on tile shape, batch position or sharding. The buffer must be ZERO when
+   * the first producer of a step runs (lm2a_ingest_x clears a region for this). */
   void* stats;
-  int32_t stats_sub;      /* row pitch of the stats buffer in sub-blocks      */
-  int32_t stats_ns;       /* slices per (row, sub-block)                      */
-  int32_t stats_gran;     /* channels per sub-block: 8, 16 or 32              */
+  int32_t stats_pitch;    /* groups per clip-row in the stats buffer            */
+  int32_t stats_cg;       /* channels per group (multiple of 8)                 */
   int32_t cta_group;      /* 0 = auto, 1 = one CTA per 128-row tile, 2 = CTA
                              pair (cluster of 2, cta_group::2 UMMA) per 256 rows */
-  /* Optional fused GroupNorm + SiLU of the output (unet1d_ultimate.py:146-147):
-   * gn_out = SiLU(GroupNorm(out)) is written as a second bf16 slab by the same
-   * launch. Every CTA keeps its tiles in TMEM, the partial sums go to `stats`
-   * (required, stats_gran = 32), all CTAs meet at a grid barrier, then the tiles
-   * are normalised straight out of TMEM. `out` may be NULL (raw output not
-   * needed). Needs (n_valid/gn_groups) % 32 == 0, tp >= 32, a uniform FiLM table
-   * (film_ld == 0) and lm2a_conv_gn_fusable(m, n_pad) != 0. gn_barrier: two
-   * zero-initialised uint32 owned by this launch site.                        */
-  const float* gn_gamma;  /* NULL = no fusion                                  */
-  const float* gn_beta;
-  void* gn_out;
-  void* gn_barrier;
-  int32_t gn_out_ld;
-  int32_t gn_groups;
-  float gn_eps;
-  int32_t _pad3;
+  int32_t stats_c0;       /* channel of the normalised tensor that `out` channel 0
+                             is (two producers of one concat slab share a buffer) */
+  /* Optional GroupNorm + SiLU of the INPUT of seg[0] (unet1d_ultimate.py:136-137,
+   * 146-147, 362-363), applied to the operand tile in shared memory between its
+   * TMA landing and the MMA: y = SiLU((x - mean) * rstd * gamma + beta) with
+   * mean / rstd per (clip-row, group) from in_gn_stats (layout as `stats` above,
+   * written by the kernel that produced the slab; in_gn_pitch groups per clip-row,
+   * in_gn_groups groups over seg[0].cin channels). k1 / k3 segments only; seg[1]
+   * (skip conv) always reads raw. cin <= 2048; clips must be long enough that a
+   * 130-slot tile touches at most 512 / in_gn_groups of them.                   */
+  const void* in_gn_stats;  /* NULL = raw operand                               */
+  const float* in_gn_gamma; /* [cin]                                            */
+  const float* in_gn_beta;  /* [cin]                                            */
+  int32_t in_gn_pitch;
+  int32_t in_gn_groups;
+  float in_gn_eps;
+  int32_t in_gn_silu;       /* 0: GroupNorm only                                */
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);
-/* 1 if an [m, n_pad] output can stay resident in the TMEM accumulators of one
- * wave of CTAs (precondition of the fused GroupNorm), else 0.                 */
-int lm2a_conv_gn_fusable(int64_t m, int32_t n_pad);
 
 /* ---- GroupNorm + SiLU over a slab -------------------------------------- */
 /* x,y: bf16 slabs [R, tp, ld*]; stats over t < t_valid and c/groups channels */
@@ -131,16 +131,16 @@ int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                       int32_t rows, int32_t tp, int32_t t_valid, int32_t c,
                       int32_t groups, float eps, int32_t apply_silu);
 
-/* GroupNorm + SiLU as one streaming pass over a slab whose partial sums were
- * produced by the kernel that wrote it (lm2a_conv_desc.stats / lm2a_bias_add_bf16):
- * adds the slices in a fixed order (fp64), y = SiLU((x - mean) * rstd * gamma + beta).
- * c % 8 == 0; (c/groups) % stats_gran == 0.                                  */
+/* GroupNorm + SiLU as one streaming pass over a slab whose exact sums were
+ * produced by the kernel that wrote it (lm2a_conv_desc.stats / lm2a_bias_add_bf16;
+ * stats_pitch groups per clip-row): y = SiLU((x - mean) * rstd * gamma + beta),
+ * bit-identical to the in_gn_* transform of lm2a_conv1d_bf16. c % 8 == 0,
+ * (c/groups) % 8 == 0, groups <= 64.                                          */
 int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
-                       int32_t y_ld, const void* stats, int32_t stats_sub,
-                       int32_t stats_ns, int32_t stats_gran, const float* gamma,
-                       const float* beta, int32_t rows, int32_t tp,
-                       int32_t t_valid, int32_t c, int32_t groups, float eps,
-                       int32_t apply_silu);
+                       int32_t y_ld, const void* stats, int32_t stats_pitch,
+                       const float* gamma, const float* beta, int32_t rows,
+                       int32_t tp, int32_t t_valid, int32_t c, int32_t groups,
+                       float eps, int32_t apply_silu);
 
 /* ---- cross-attention core (tcgen05 + TMEM) -------------------------------- */
 /* q,o: bf16 slabs [R*tp, ld]; stream s, head h live at channel s*e + h*dh.
@@ -195,9 +195,12 @@ int lm2a_film(void* stream, const float* silu_temb, const float* w,
 
 /* ---- layout / resampling helpers ---------------------------------------- */
 /* x fp32 [B, c, T] -> bf16 slab rows [copies*B, tp, ld] (channels >= c and
- * slots >= T zero); copy k of clip b lands in row k*B + b.                  */
+ * slots >= T zero); copy k of clip b lands in row k*B + b. As the first kernel
+ * of a UNet step it also clears `zero_bytes` (multiple of 16, may be 0) at
+ * `zero`: the GroupNorm statistics arena the step's epilogues accumulate into. */
 int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t batch,
-                  int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld);
+                  int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld,
+                  void* zero, int64_t zero_bytes);
 /* fp32 [rows, t, c] -> bf16 slab [rows, tp, ld] (channels >= c zero)        */
 int lm2a_ingest_seq(void* stream, const float* x, void* slab, int32_t rows,
                     int32_t t, int32_t c, int32_t tp, int32_t ld);
@@ -221,12 +224,12 @@ int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, void* y,
 /* y[slot,:c] = x[slot,:c] + bias[:c] for slots with t < t_valid, zero otherwise
  * (identity-skip ResBlock of an all-zero-condition row: its attention output is
  * a constant vector — the classifier-free-guidance uncond shortcut). `stats`
- * (optional) receives the partial GroupNorm sums of y, layout as in
+ * (optional) accumulates the exact GroupNorm sums of y, layout as in
  * lm2a_conv_desc.                                                            */
 int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                        int32_t y_ld, const float* bias, int64_t slots,
                        int32_t tp, int32_t t_valid, int32_t c, void* stats,
-                       int32_t stats_sub, int32_t stats_ns, int32_t stats_gran);
+                       int32_t stats_pitch, int32_t stats_cg, int32_t stats_c0);
 
 /* ---- CFG blend + clamps + DDPM posterior update -------------------------- */
 /* x [B,c,T] fp32 updated in place. eps: fp32 [2B,c,T] (uncond rows first)

@@ -23,14 +23,14 @@ class ConvDesc(ctypes.Structure):
                 ("film", c_void_p), ("film_ld", c_int32), ("film_shift_off", c_int32),
                 ("residual", c_void_p), ("res_ld", c_int32), ("out_mode", c_int32),
                 ("out", c_void_p), ("out_ld", c_int32), ("block_n", c_int32),
-                ("stats", c_void_p), ("stats_sub", c_int32), ("stats_ns", c_int32),
-                ("stats_gran", c_int32), ("cta_group", c_int32),
-                ("gn_gamma", c_void_p), ("gn_beta", c_void_p), ("gn_out", c_void_p),
-                ("gn_barrier", c_void_p), ("gn_out_ld", c_int32), ("gn_groups", c_int32),
-                ("gn_eps", c_float), ("_pad3", c_int32)]
+                ("stats", c_void_p), ("stats_pitch", c_int32), ("stats_cg", c_int32),
+                ("cta_group", c_int32), ("stats_c0", c_int32),
+                ("in_gn_stats", c_void_p), ("in_gn_gamma", c_void_p), ("in_gn_beta", c_void_p),
+                ("in_gn_pitch", c_int32), ("in_gn_groups", c_int32), ("in_gn_eps", c_float),
+                ("in_gn_silu", c_int32)]
 
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -42,7 +42,6 @@ SIGNATURES = {
     "lm2a_launch_count": (c_int64, []),
     "lm2a_reset_launch_count": (None, []),
     "lm2a_conv1d_bf16": (c_int32, [c_void_p, ctypes.POINTER(ConvDesc)]),
-    "lm2a_conv_gn_fusable": (c_int32, [c_int64, c_int32]),
     "lm2a_gn_silu_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_float, c_int32]),
@@ -63,7 +62,7 @@ SIGNATURES = {
     "lm2a_film": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                             c_int32]),
     "lm2a_ingest_x": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
-                                c_int32, c_int32, c_int32]),
+                                c_int32, c_int32, c_int32, c_void_p, c_int64]),
     "lm2a_ingest_seq": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_int32, c_int32]),
     "lm2a_resample_seq": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
@@ -74,8 +73,8 @@ SIGNATURES = {
                                      c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                      c_int32, c_int32]),
     "lm2a_gn_apply_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
-                                     c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
-                                     c_int32, c_int32, c_int32, c_int32, c_float, c_int32]),
+                                     c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_float, c_int32]),
     "lm2a_cfg_posterior": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_int32, c_int64, c_float, c_int32,
                                      c_int32, c_void_p]),

@@ -45,15 +45,32 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+// per device (a process may drive several GPUs)
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  const int slot = (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+  if (sms[slot] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[slot] = n > 0 ? n : 148;
   }
-  return sms;
+  return sms[slot];
+}
+
+// cudaFuncSetAttribute is per device: true exactly once per (call site flag array, device)
+bool first_use_on_device(bool* flags) {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
 }
 
 }  // namespace lm2a

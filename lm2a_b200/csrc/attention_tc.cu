@@ -452,12 +452,10 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
   constexpr bool sw64 = L::kSw64;
   auto kern = cross_attn_tc_kernel<DH>;
   constexpr int smem_bytes = L::kBytes;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
     LM2A_CUDA_OK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    configured = true;
-  }
   CUtensorMap tq, tkm, tkt, tvm, tvt;
   if (encode_map(&tq, q, (uint64_t)n_streams * e, (uint64_t)rows * tp, (uint64_t)q_ld,
                  L::kPanelW, kBQ, sw64))

@@ -13,7 +13,10 @@ namespace lm2a {
 // ---------------------------------------------------------------- host side
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-int num_sms();
+constexpr int kMaxDevices = 64;
+int current_device();
+int num_sms();                          // of the current device
+bool first_use_on_device(bool* flags);  // flags: a static bool[kMaxDevices] of the call site
 
 // cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,

@@ -1,51 +1,61 @@
 // Implicit-GEMM Conv1d / Linear for channels-last bf16 slabs on sm_100a.
 //
-//   out[m, n] = sum_{seg, tap, c} A_seg[m + shift(tap), c] * W[n, k(seg,tap,c)] + bias[n]
+//   out[m, n] = sum_{seg, tap, c} f_seg(A_seg)[m + shift(tap), c] * W[n, k(seg,tap,c)] + bias[n]
 //
-// Replaces nn.Conv1d (k=1, k=3 p=1, k=4 s=2 p=1) and every nn.Linear / MHA
-// projection on the sampling path (reference models/unet1d_ultimate.py:87-88,
-// 115,216-221,255-261,295,364; models/cross_attention.py:19-36). The FiLM
-// modulation h*(1+scale)+shift (:141-143), the ResBlock skip 1x1 conv (second K
-// segment accumulating into the same TMEM tile) and the residual add (:159) are
-// fused into the epilogue.
+// Replaces nn.Conv1d (k=1, k=3 p=1, k=4 s=2 p=1) and every nn.Linear / MHA projection on the
+// sampling path (reference models/unet1d_ultimate.py:87-88,115,216-221,255-261,295,364;
+// models/cross_attention.py:19-36). Fused around the contraction:
+//   * consumer side: the GroupNorm + SiLU in front of a conv (unet1d_ultimate.py:136-137,
+//     146-147, 362-363) is applied to the operand tile in shared memory between its TMA
+//     landing and the MMA (f_seg above; per-(clip-row, group) mean / rstd from the producer's
+//     exact integer sums), so the normalised tensor never exists in HBM;
+//   * producer side (epilogue): bias, FiLM h*(1+scale)+shift (:141-143), the ResBlock skip 1x1
+//     conv (second K segment accumulating into the same TMEM tile), the residual add (:159),
+//     and the GroupNorm sums of the OUTPUT for the next consumer.
 //
-// Structure (one CTA per SM, persistent over 128 x BLOCK_N output tiles):
-//   warp 0     TMA producer: per K-block one 128x64 A box (a tap is a row shift of
-//              the flattened slab; the zero slot between clips and TMA's
-//              out-of-bounds zero fill are the conv padding) and one BLOCK_Nx64 W box
-//   warp 1     tcgen05.mma issuer (single thread), accumulators in TMEM,
-//              double-buffered so tile i+1's MMAs overlap tile i's epilogue
-//   warps 2-9  epilogue: tcgen05.ld -> bias/FiLM/residual (+ partial GroupNorm sums of the
-//              output) -> bf16 slab (or the final fp32 [R, C, T] eps tensor); warp w reads
-//              TMEM lane quadrant w % 4 and the column half (w - 2) / 4
+// One CTA per SM, persistent over 128 x BLOCK_N output tiles (CG = 2: a CTA pair per
+// 256 x BLOCK_N tile, cta_group::2 UMMA):
+//   warp 0      TMA producer. An "A block" is ONE box of 128 (+ halo) slots x 64 channels that
+//               serves every tap of the conv: a tap is a row shift, and a row-shifted view of a
+//               128B-swizzled tile is expressed in the UMMA descriptor (start address + 128 B
+//               per row, matrix base offset = row phase). Operand bytes per output tile drop by
+//               the tap count versus one box per tap. W boxes ride in a ring of their own.
+//   warp 1      tcgen05.mma issuer (one thread), fp32 accumulators double-buffered in TMEM
+//   warps 2-5   operand transform: wait for the A block, normalise + SiLU in place (or pass it
+//               through untouched), fence to the async proxy, hand it to the MMA warp
+//   warps 6-13  epilogue: tcgen05.ld -> bias / FiLM / residual -> GroupNorm sums -> bf16 slab via
+//               TMA store (or the final fp32 [R, C, T] eps tensor)
+//
+// GroupNorm sums are exact: every lane's per-slot channel sums (a fixed-order fp32 sum that does
+// not depend on where the slot sits in the batch) are converted to 40.24 / 44.20 fixed point and
+// accumulated with 64-bit integer adds (warp shuffle tree, then one atomic per (clip-row,
+// group)). Integer addition is associative, so the statistics - and with them every output bit -
+// are independent of tile shape, batch position and sharding.
 #include "../../include/lm2a_b200.h"
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace lm2a {
-
-#ifdef LM2A_CONV_TIMING
-// Instrumented build (python -m lm2a_b200.build with LM2A_NVCC_DEFS=-DLM2A_CONV_TIMING, see
-// tools/conv_stall_probe.py): cycles the MMA-issuing thread waits for operands (full barriers) /
-// for a free accumulator, cycles the TMA producer waits for a free stage, and the CTA lifetime,
-// summed over all CTAs. Not part of the product build.
-__device__ unsigned long long g_conv_timing[8];
-#endif
-
 namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kATileBytes = kBlockM * kBlockK * 2;
+constexpr int kASlotRows = 136;                      // 128 + 2 halo rows, rounded to 8-row atoms
+constexpr int kASlotBytes = kASlotRows * kBlockK * 2;  // 17408 = 17 * 1024
+constexpr int kXformWarps = 4;
 constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes half of the columns
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kFirstEpiWarp = 2 + kXformWarps;
+constexpr int kThreads = 32 * (2 + kXformWarps + kEpiWarps);
+constexpr int kMaxGnChannels = 2048;   // gamma / beta of the input GroupNorm staged in smem
+constexpr int kMaxGnEntries = 512;     // (clip-rows touched by a tile) x groups
+constexpr float kStatScale1 = 16777216.0f;   // 2^24: sum
+constexpr float kStatScale2 = 1048576.0f;    // 2^20: sum of squares
 
 struct ConvArgs {
   int seg_cblk[2];   // cin / 64 per segment
   int seg_taps[2];   // LM2A_TAPS_*
   int seg_half[2];   // K4S2: channel offset of the odd slot inside a slot pair
-  int num_kb;
   int m_tiles, n_tiles;
   long long m;
   int tp, t_valid, n_valid;
@@ -57,63 +67,147 @@ struct ConvArgs {
   void* out;
   int out_ld;
   int out_mode;
-  float2* stats;     // partial GroupNorm sums of the output (or null), see lm2a_conv_desc
-  int stats_sub;     // sub-blocks per clip-row in the stats buffer (= its row pitch)
-  int stats_ns;      // slices per (clip-row, sub-block)
-  int stats_gran;    // channels per sub-block: 8, 16 or 32
-  // fused GroupNorm + SiLU of the output (see lm2a_conv_desc.gn_*): the CTA keeps its tiles in
-  // TMEM, all CTAs meet at a grid barrier once the partial sums are written, then the tiles
-  // are normalised straight out of TMEM
+  unsigned long long* stats;  // exact GroupNorm sums of the output (or null): [R][stats_pitch][2]
+  int stats_pitch;            // groups per clip-row in the stats buffer
+  int stats_cg;               // channels per group
+  int stats_c0;               // channel of the normalised tensor that output column 0 maps to
+  // GroupNorm (+ SiLU) applied to segment 0 on the fly
+  const long long* gn_stats;  // null = raw operand
   const float* gn_gamma;
   const float* gn_beta;
-  int gn_groups;
+  int gn_pitch, gn_groups, gn_cg, gn_silu;
   float gn_eps;
-  unsigned int* gn_barrier;  // {arrival count, generation}
+  int desc_base_offset;       // 1: row-shifted tap views carry the matrix base offset
 };
 
-template <int BLOCK_N, int STAGES, int CG>
+template <int BLOCK_N, int CG>
 struct SmemLayout {
-  static constexpr int kBTileBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits B along N
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kBSlotBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits W along N
+  static constexpr int kAStages = (BLOCK_N == 256 && CG == 1) ? 3 : 4;
+  static constexpr int kBStages = (BLOCK_N == 256 && CG == 1) ? 4 : (kBSlotBytes == 16384 ? 6 : 8);
+  static constexpr int kAOffset = 0;
+  static constexpr int kBOffset = kAStages * kASlotBytes;
   // epilogue: per warp a [32 rows][32 cols] bf16 staging tile (TMA store source, 64B swizzle)
   // and a table of per-column (scale, offset) pairs for its BLOCK_N / 2 columns
-  static constexpr int kOutOffset = STAGES * kStageBytes;
+  static constexpr int kOutOffset = kBOffset + kBStages * kBSlotBytes;
   static constexpr int kOutBytesPerWarp = 32 * 32 * 2;
   static constexpr int kTabOffset = kOutOffset + kEpiWarps * kOutBytesPerWarp;
-  static constexpr int kTabBytesPerWarp = 2 * (BLOCK_N / 2) * 8;  // x2: one table per clip-row
-  static constexpr int kBarOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
-  static constexpr int kBytes = kBarOffset + 256 + 1024;  // + barriers + align slack
+  static constexpr int kTabBytesPerWarp = (BLOCK_N / 2) * 8;
+  // operand transform: gamma | beta of the input GroupNorm, (mean, rstd) per (clip-row, group)
+  // of the current tile, clip-row index of every slot of the A block
+  static constexpr int kGammaOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
+  static constexpr int kMrOffset = kGammaOffset + 2 * kMaxGnChannels * 4;
+  static constexpr int kRowInfoOffset = kMrOffset + kMaxGnEntries * 8;
+  static constexpr int kBarOffset = kRowInfoOffset + kASlotRows * 4;
+  static constexpr int kNumBars = 3 * kAStages + 2 * kBStages + 4;
+  static constexpr int kBytes = kBarOffset + 8 * kNumBars + 16 + 1024;  // + tmem slot + align
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
-  // fused GroupNorm pass 1 stages every output box of the CTA in the (then idle) pipeline area
-  static_assert(kEpiWarps * (512 / BLOCK_N) * (BLOCK_N / 2 / 32) * kOutBytesPerWarp <=
-                    STAGES * kStageBytes, "pass-1 staging must fit the operand pipeline");
 };
 
-// CG = 1: one CTA per 128 x BLOCK_N tile. CG = 2: a CTA pair (cluster of 2) per 256 x BLOCK_N
-// tile with cta_group::2 UMMA: each CTA stages its own 128 rows of A and half of the W rows,
-// so the operand bytes an SM pulls from L2 per MMA cycle drop from 96 to 64 (BLOCK_N = 256).
-template <int BLOCK_N, int STAGES, int CG>
+// 128B-swizzled K-major operand descriptor of a tile that starts `row_shift` (< 8) rows into a
+// 1024-byte aligned slot: start address advanced by whole 128-byte rows, the swizzle phase of
+// the first row in the matrix-base-offset field (bits 49-51).
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t slot_addr, uint32_t row_shift,
+                                                        uint32_t use_base_offset) {
+  uint64_t d = umma_desc_sw128_kmajor(slot_addr + row_shift * 128u);
+  if (use_base_offset) d |= static_cast<uint64_t>(row_shift & 7u) << 49;
+  return d;
+}
+
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+      printf("lm2a: mbarrier (cluster) wait timeout (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The K loop of one output tile as a sequence of A blocks, each followed by the W blocks of
+// the taps it serves. on_a(seg, cb, row0, chan): box at slot m0 + row0, channel `chan` of the
+// segment's tensor map. on_b(shift, kb): tap view `shift` rows into the A block, W K-block kb.
+template <typename FA, typename FB>
+__device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_b) {
+  int kb_base = 0;
+#pragma unroll 1
+  for (int seg = 0; seg < 2; ++seg) {
+    const int cblk = p.seg_cblk[seg];
+    if (cblk == 0) continue;
+    const int mode = p.seg_taps[seg];
+    const int nhalf = mode == LM2A_TAPS_K4S2 ? 2 : 1;
+    const int ntap = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 2);
+#pragma unroll 1
+    for (int cb = 0; cb < cblk; ++cb) {
+#pragma unroll 1
+      for (int hf = 0; hf < nhalf; ++hf) {
+        // K3: slots m-1, m, m+1 -> one box from m0 - 1, tap j = view shifted by j rows.
+        // K4S2 over slot pairs: x[2t-1+tap]; hf = 0 is the odd half of a pair (taps 0, 2 =
+        // pairs t-1, t -> box from m0 - 1), hf = 1 the even half (taps 1, 3 = pairs t, t+1).
+        const int row0 = (mode == LM2A_TAPS_K3 || (mode == LM2A_TAPS_K4S2 && hf == 0)) ? -1 : 0;
+        const int chan = ((mode == LM2A_TAPS_K4S2 && hf == 0) ? p.seg_half[seg] : 0) + cb * kBlockK;
+        on_a(seg, cb, row0, chan);
+#pragma unroll 1
+        for (int j = 0; j < ntap; ++j) {
+          const int tap = mode == LM2A_TAPS_K4S2 ? 2 * j + hf : j;
+          on_b(j, kb_base + tap * cblk + cb);
+        }
+      }
+    }
+    kb_base += cblk * (mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4));
+  }
+}
+
+__device__ __forceinline__ uint32_t a_box_bytes(int mode) {
+  const int rows = mode == LM2A_TAPS_K1 ? 128 : (mode == LM2A_TAPS_K3 ? 130 : 129);
+  return (uint32_t)rows * kBlockK * 2;
+}
+
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmOut,
-                 const __grid_constant__ CUtensorMap tmOut2, const ConvArgs p) {
-  using L = SmemLayout<BLOCK_N, STAGES, CG>;
+                 const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
+  using L = SmemLayout<BLOCK_N, CG>;
+  constexpr int NA = L::kAStages, NB = L::kBStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
   const uint32_t bar_base = smem_base + L::kBarOffset;
-  // barrier slots (8 B each): full[STAGES], empty[STAGES], tfull[4], tempty[2], tmem ptr
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 6);
-  // fused GroupNorm: every tile of this CTA keeps its own accumulator (512 / BLOCK_N of them)
-  const bool fuse_gn = p.gn_gamma != nullptr;
-  constexpr int kMaxAcc = 512 / BLOCK_N;
-  auto a_tile = [&](int s) { return smem_base + s * L::kStageBytes; };
-  auto b_tile = [&](int s) { return smem_base + s * L::kStageBytes + kATileBytes; };
+  // barrier slots (8 B each)
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_ready = [&](int s) { return bar_base + 8u * (NA + s); };
+  auto a_empty = [&](int s) { return bar_base + 8u * (2 * NA + s); };
+  auto b_full = [&](int s) { return bar_base + 8u * (3 * NA + s); };
+  auto b_empty = [&](int s) { return bar_base + 8u * (3 * NA + NB + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
+  auto a_slot = [&](int s) { return smem_base + L::kAOffset + s * kASlotBytes; };
+  auto b_slot = [&](int s) { return smem_base + L::kBOffset + s * L::kBSlotBytes; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -121,23 +215,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;       // tile-walking unit
   const int num_units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const bool xform = p.gn_stats != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
-    tma_prefetch_desc(&tmOut2);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_ready(s), kXformWarps * CG);  // pair: the leader collects both CTAs' blocks
+      mbar_init(a_empty(s), 1);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(tfull_bar(s), 1);
-    for (int s = 0; s < 2; ++s)
-      mbar_init(tempty_bar(s), 32 * kEpiWarps * CG);  // pair: the leader collects both CTAs
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 32 * kEpiWarps * CG);
+    }
     mbar_fence_init();
   }
-  const uint32_t tmem_cols = fuse_gn ? 512u : 2u * BLOCK_N;
+  constexpr uint32_t tmem_cols = 2u * BLOCK_N;
   if (warp == 1) {
     if (CG == 2) {
       tmem_alloc_cg2(tmem_slot, tmem_cols);
@@ -145,6 +245,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     } else {
       tmem_alloc(tmem_slot, tmem_cols);
       tmem_relinquish();
+    }
+  }
+  if (warp >= 2 && warp < kFirstEpiWarp && xform) {
+    // gamma / beta of the input GroupNorm (parameters: never written by a kernel of the stream)
+    float* sg = reinterpret_cast<float*>(smem_gen + L::kGammaOffset);
+    const int gn_c = p.gn_groups * p.gn_cg;
+    for (int i = threadIdx.x - 64; i < gn_c; i += 32 * kXformWarps) {
+      sg[i] = __ldg(p.gn_gamma + i);
+      sg[kMaxGnChannels + i] = __ldg(p.gn_beta + i);
     }
   }
   tc_fence_before_sync();
@@ -155,20 +264,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   // Everything above overlapped the previous kernel's tail. The weights are never written by
   // a kernel, so the producer also starts the W boxes of the first pipeline stages before
   // waiting for the previous kernel (their HBM latency hides under its tail); activations
-  // (A boxes, residual, FiLM table) are only touched after griddepcontrol.wait.
+  // (A boxes, residual, FiLM table, statistics) are only touched after griddepcontrol.wait.
   int w_prefetched = 0;
   if (warp == 0 && lane == 0 && unit < total_tiles) {
     const int n0 = (unit % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
-    w_prefetched = p.num_kb < STAGES ? p.num_kb : STAGES;
-    for (int kb = 0; kb < w_prefetched; ++kb) {
-      if (CG == 2) {
-        if (cta_rank == 0) mbar_expect_tx(full_bar(kb), 2 * L::kStageBytes);
-        tma_load_2d_cg2(b_tile(kb), &tmB, kb * kBlockK, n0, mapa_shared(full_bar(kb), 0));
-      } else {
-        mbar_expect_tx(full_bar(kb), L::kStageBytes);
-        tma_load_2d(b_tile(kb), &tmB, kb * kBlockK, n0, full_bar(kb));
-      }
-    }
+    walk_tile(p, [](int, int, int, int) {},
+              [&](int, int kb) {
+                if (w_prefetched >= NB) return;
+                const int s = w_prefetched++;
+                if (CG == 2) {
+                  if (cta_rank == 0) mbar_expect_tx(b_full(s), 2 * L::kBSlotBytes);
+                  tma_load_2d_cg2(b_slot(s), &tmB, kb * kBlockK, n0, mapa_shared(b_full(s), 0));
+                } else {
+                  mbar_expect_tx(b_full(s), L::kBSlotBytes);
+                  tma_load_2d(b_slot(s), &tmB, kb * kBlockK, n0, b_full(s));
+                }
+              });
   }
   pdl_wait();
   pdl_launch_dependents();
@@ -176,148 +287,241 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-#ifdef LM2A_CONV_TIMING
-      long long t_prod_wait = 0;
-#endif
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      int b_issued = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int m0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
         const int n0 = (tile % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
-        int kb = 0;
-#pragma unroll 1
-        for (int seg = 0; seg < 2; ++seg) {
-          const int cblk = p.seg_cblk[seg];
-          if (cblk == 0) continue;
-          const CUtensorMap* tm = seg ? &tmA1 : &tmA0;
-          const int mode = p.seg_taps[seg];
-          const int ntaps = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4);
-#pragma unroll 1
-          for (int tap = 0; tap < ntaps; ++tap) {
-            int shift = 0, choff = 0;
-            if (mode == LM2A_TAPS_K3) {
-              shift = tap - 1;
-            } else if (mode == LM2A_TAPS_K4S2) {
-              // x[2t-1+tap] over slot pairs: tap0 -> pair t-1 odd half, tap1 -> pair t
-              // even half, tap2 -> pair t odd half, tap3 -> pair t+1 even half
-              shift = tap == 0 ? -1 : (tap == 3 ? 1 : 0);
-              choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
-            }
-#pragma unroll 1
-            for (int cb = 0; cb < cblk; ++cb, ++kb) {
-              // first tile: the W box of the first stages is already in flight (see above)
-              const bool w_done = tile == unit && kb < w_prefetched;
-#ifdef LM2A_CONV_TIMING
-              const long long tw0 = clock64();
-#endif
-              if (!w_done) mbar_wait(empty_bar(stage), phase ^ 1u);
-#ifdef LM2A_CONV_TIMING
-              t_prod_wait += clock64() - tw0;
-#endif
-              if (CG == 2) {
-                // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
-                const uint32_t fb = mapa_shared(full_bar(stage), 0);
-                if (cta_rank == 0 && !w_done) mbar_expect_tx(full_bar(stage), 2 * L::kStageBytes);
-                tma_load_2d_cg2(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift, fb);
-                if (!w_done) tma_load_2d_cg2(b_tile(stage), &tmB, kb * kBlockK, n0, fb);
-              } else {
-                if (!w_done) mbar_expect_tx(full_bar(stage), L::kStageBytes);
-                tma_load_2d(a_tile(stage), tm, choff + cb * kBlockK, m0 + shift,
-                            full_bar(stage));
-                if (!w_done) tma_load_2d(b_tile(stage), &tmB, kb * kBlockK, n0, full_bar(stage));
+        walk_tile(
+            p,
+            [&](int seg, int, int row0, int chan) {
+              mbar_wait(a_empty(sa), pa ^ 1u);
+              mbar_expect_tx(a_full(sa), a_box_bytes(p.seg_taps[seg]));
+              tma_load_2d(a_slot(sa), seg ? &tmA1 : &tmA0, chan, m0 + row0, a_full(sa));
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1u;
               }
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1u;
+            },
+            [&](int, int kb) {
+              // first tile: the W boxes of the first stages are already in flight (see above)
+              if (b_issued >= w_prefetched) {
+                mbar_wait(b_empty(sb), pb ^ 1u);
+                if (CG == 2) {
+                  // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
+                  if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::kBSlotBytes);
+                  tma_load_2d_cg2(b_slot(sb), &tmB, kb * kBlockK, n0, mapa_shared(b_full(sb), 0));
+                } else {
+                  mbar_expect_tx(b_full(sb), L::kBSlotBytes);
+                  tma_load_2d(b_slot(sb), &tmB, kb * kBlockK, n0, b_full(sb));
+                }
               }
-            }
-          }
-        }
+              ++b_issued;
+              if (++sb == NB) {
+                sb = 0;
+                pb ^= 1u;
+              }
+            });
       }
-#ifdef LM2A_CONV_TIMING
-      atomicAdd(&g_conv_timing[2], (unsigned long long)t_prod_wait);
-#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer (pair: the leader CTA only)
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CG, BLOCK_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-#ifdef LM2A_CONV_TIMING
-      long long t_full_wait = 0, t_acc_wait = 0;
-      const long long t_begin = clock64();
-#endif
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
-        if (!fuse_gn) {
-#ifdef LM2A_CONV_TIMING
-          const long long ta0 = clock64();
-#endif
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-#ifdef LM2A_CONV_TIMING
-          t_acc_wait += clock64() - ta0;
-#endif
-          tc_fence_after_sync();
-        }
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-#pragma unroll 1
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-#ifdef LM2A_CONV_TIMING
-          const long long tf0 = clock64();
-#endif
-          mbar_wait(full_bar(stage), phase);
-#ifdef LM2A_CONV_TIMING
-          t_full_wait += clock64() - tf0;
-#endif
-          tc_fence_after_sync();
-          const uint64_t adesc = umma_desc_sw128_kmajor(a_tile(stage));
-          const uint64_t bdesc = umma_desc_sw128_kmajor(b_tile(stage));
+        uint32_t started = 0;   // 0 until the first MMA of the tile (which overwrites D)
+        uint32_t cur_a = 0;
+        bool a_open = false;
+        walk_tile(
+            p,
+            [&](int, int, int, int) {
+              if (a_open) {  // every tap of the previous A block has been issued: free its slot
+                if (CG == 2) umma_commit_cg2(a_empty(cur_a)); else umma_commit(a_empty(cur_a));
+              }
+              if (CG == 2) mbar_wait_cluster(a_ready(sa), pa); else mbar_wait(a_ready(sa), pa);
+              tc_fence_after_sync();
+              cur_a = sa;
+              a_open = true;
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1u;
+              }
+            },
+            [&](int shift, int) {
+              mbar_wait(b_full(sb), pb);
+              tc_fence_after_sync();
+              const uint64_t adesc =
+                  umma_desc_sw128_rows(a_slot(cur_a), (uint32_t)shift, (uint32_t)p.desc_base_offset);
+              const uint64_t bdesc = umma_desc_sw128_kmajor(b_slot(sb));
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
-            if (CG == 2)
-              umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
-                               (kb | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc,
-                           (kb | k) != 0 ? 1u : 0u);
-          }
-          if (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 B per K=16 step inside the 128 B swizzle row (address field is >>4)
+                if (CG == 2)
+                  umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, started);
+                else
+                  umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, started);
+                started = 1u;
+              }
+              if (CG == 2) umma_commit_cg2(b_empty(sb)); else umma_commit(b_empty(sb));
+              if (++sb == NB) {
+                sb = 0;
+                pb ^= 1u;
+              }
+            });
+        if (a_open) {
+          if (CG == 2) umma_commit_cg2(a_empty(cur_a)); else umma_commit(a_empty(cur_a));
         }
         if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-        if (fuse_gn) {
-          ++acc;  // one accumulator per tile, kept until the normalisation pass
-        } else {
-          acc ^= 1u;
-          if (acc == 0) acc_phase ^= 1u;
-        }
+        acc ^= 1u;
+        if (acc == 0) acc_phase ^= 1u;
       }
-#ifdef LM2A_CONV_TIMING
-      atomicAdd(&g_conv_timing[0], (unsigned long long)t_full_wait);
-      atomicAdd(&g_conv_timing[1], (unsigned long long)t_acc_wait);
-      atomicAdd(&g_conv_timing[3], (unsigned long long)(clock64() - t_begin));
-      atomicAdd(&g_conv_timing[4], 1ull);
-#endif
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // ------------------------------------------------- operand transform (128 threads)
+    const int xt = threadIdx.x - 64;
+    const int chunk = xt & 7;    // 16-byte chunk (8 channels) of a 128-byte operand row
+    const int rl = xt >> 3;      // row lane: rows rl, rl + 16, ...
+    const float* sg = reinterpret_cast<const float*>(smem_gen + L::kGammaOffset);
+    float2* mr = reinterpret_cast<float2*>(smem_gen + L::kMrOffset);
+    int* row_info = reinterpret_cast<int*>(smem_gen + L::kRowInfoOffset);
+    const int mode0 = p.seg_taps[0];
+    const int rows0 = mode0 == LM2A_TAPS_K3 ? 130 : 128;   // slots per A block of segment 0
+    const int roff0 = mode0 == LM2A_TAPS_K3 ? -1 : 0;
+    uint32_t sa = 0, pa = 0;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
+      const int m_base = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM + roff0;
+      bool single_clip = false;
+      if (xform) {
+        // clip-row of every slot of the block and (mean, rstd) of every (clip-row, group) it
+        // touches, from the producer's exact integer sums
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
+        const int m_lo = m_base > 0 ? m_base : 0;
+        const long long m_hi_ll = (long long)m_base + rows0 - 1;
+        const int m_hi = m_hi_ll < p.m - 1 ? (int)m_hi_ll : (int)(p.m - 1);
+        const int r_first = m_lo / p.tp;
+        const int r_last = m_hi >= m_lo ? m_hi / p.tp : r_first - 1;
+        single_clip = r_last == r_first;
+        for (int i = xt; i < rows0; i += 32 * kXformWarps) {
+          const long long m = (long long)m_base + i;
+          int info = -1;
+          if (m >= 0 && m < p.m) {
+            const int r = (int)m / p.tp;
+            const int t = (int)m - r * p.tp;
+            if (t < p.t_valid) info = r - r_first;
+          }
+          row_info[i] = info;
+        }
+        const int nent = (r_last - r_first + 1) * p.gn_groups;
+        const double inv_n = 1.0 / ((double)p.gn_cg * (double)p.t_valid);
+        for (int e = xt; e < nent; e += 32 * kXformWarps) {
+          const int rr = r_first + e / p.gn_groups, g = e % p.gn_groups;
+          const long long* sp = p.gn_stats + ((size_t)rr * p.gn_pitch + g) * 2;
+          const long long s1 = __ldcg(sp), s2 = __ldcg(sp + 1);
+          const double mean = (double)s1 * (1.0 / 16777216.0) * inv_n;
+          double var = (double)s2 * (1.0 / 1048576.0) * inv_n - mean * mean;
+          var = var > 0.0 ? var : 0.0;
+          mr[e] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)p.gn_eps)));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
+      }
+      walk_tile(
+          p,
+          [&](int seg, int cb, int, int) {
+            mbar_wait(a_full(sa), pa);
+            if (seg == 0 && xform) {
+              const uint32_t slot = a_slot(sa);
+              const int c0 = cb * kBlockK + chunk * 8;
+              const int g = c0 / p.gn_cg;
+              float ga[8], be[8];
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + e);
+                const float4 b4 = *reinterpret_cast<const float4*>(sg + kMaxGnChannels + c0 + e);
+                ga[e] = g4.x; ga[e + 1] = g4.y; ga[e + 2] = g4.z; ga[e + 3] = g4.w;
+                be[e] = b4.x; be[e + 1] = b4.y; be[e + 2] = b4.z; be[e + 3] = b4.w;
+              }
+              if (single_clip) {
+                const float2 s = mr[g];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  ga[e] *= s.y;
+                  be[e] = fmaf(-s.x, ga[e], be[e]);
+                }
+              }
+#pragma unroll 1
+              for (int i = rl; i < rows0; i += 16) {
+                const int info = row_info[i];
+                if (info < 0) continue;   // pad slot / outside the slab: stays zero
+                float a[8], b[8];
+                if (single_clip) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    a[e] = ga[e];
+                    b[e] = be[e];
+                  }
+                } else {
+                  const float2 s = mr[info * p.gn_groups + g];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    a[e] = ga[e] * s.y;
+                    b[e] = fmaf(-s.x, a[e], be[e]);
+                  }
+                }
+                const uint32_t addr = slot + (uint32_t)i * 128u + (((uint32_t)(chunk ^ (i & 7))) << 4);
+                uint32_t w[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                             : "r"(addr));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 x = unpack_bf16x2(w[e]);
+                  float v0 = fmaf(x.x, a[2 * e], b[2 * e]);
+                  float v1 = fmaf(x.y, a[2 * e + 1], b[2 * e + 1]);
+                  if (p.gn_silu) {
+                    v0 = silu_tanh(v0);
+                    v1 = silu_tanh(v1);
+                  }
+                  w[e] = pack_bf16x2(v0, v1);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]),
+                             "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+              }
+              fence_proxy_async_smem();
+            }
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(mapa_shared(a_ready(sa), 0));
+              else mbar_arrive(a_ready(sa));
+            }
+            if (++sa == NA) {
+              sa = 0;
+              pa ^= 1u;
+            }
+          },
+          [](int, int) {});
     }
   } else {
     // ----------------------------------------------------------------- epilogue
+    const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;
+    const int half = ew >> 2;
     const int row = quad * 32 + lane;
-    const uint32_t stg_base = smem_base + L::kOutOffset + (warp - 2) * L::kOutBytesPerWarp;
-    const uint32_t tab_base = smem_base + L::kTabOffset + (warp - 2) * L::kTabBytesPerWarp;
+    const uint32_t stg = smem_base + L::kOutOffset + ew * L::kOutBytesPerWarp;
+    const uint32_t tab_base = smem_base + L::kTabOffset + ew * L::kTabBytesPerWarp;
     const bool film_tab = p.film != nullptr && p.film_ld == 0;
     const bool film_row = p.film != nullptr && p.film_ld != 0;
     constexpr int kHalfN = BLOCK_N / 2;  // columns handled by this warp
+    // channel granularity of the GroupNorm sums inside a 32-column chunk
+    const int gmask = p.stats_cg | p.stats_c0;
+    const int gran = gmask % 32 == 0 ? 32 : (gmask % 16 == 0 ? 16 : 8);
 
-    // One output tile. pass 0: out = acc * a + b (bias / FiLM folded per column) + residual,
-    // partial GroupNorm sums, raw output. pass 1 (fused GroupNorm only): the same accumulator
-    // again, now with the per-(clip-row, column) normalisation folded into the table, SiLU, and
-    // the normalised tile goes out through tmOut2.
-    uint32_t box_ord = 0;  // pass 1: running index of this warp's output boxes
-    auto run_tile = [&](int tile, uint32_t acc, uint32_t wait_parity, int pass) {
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
       const long long m = (long long)m_tile0 + row;
       const int n0 = (tile % p.n_tiles) * BLOCK_N;
@@ -325,7 +529,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       const int r = in_range ? (int)((int)m / p.tp) : 0;
       const int t = in_range ? (int)m - r * p.tp : 0;
       const bool valid = in_range && t < p.t_valid;
-      // clip-rows touched by this warp's 32 slots (GroupNorm partial sums are per clip-row)
+      // clip-rows touched by this warp's 32 slots (GroupNorm sums are per clip-row)
       const int m_first = m_tile0 + quad * 32;
       const int m_last = m_first + 31 < (int)p.m - 1 ? m_first + 31 : (int)p.m - 1;
       const int r_lo = m_first / p.tp;
@@ -336,7 +540,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       // (per-row FiLM tables, film_ld != 0, are applied per lane further down)
       {
         __syncwarp();  // previous tile's table reads are done
-        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
         const int cl = lane * 4;                        // column inside this warp's half
         const int ncol = n0 + half * kHalfN + cl;
         if (cl < kHalfN) {
@@ -346,103 +549,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             s4 = __ldg(reinterpret_cast<const float4*>(p.film + ncol));
             h4 = __ldg(reinterpret_cast<const float4*>(p.film + p.film_shift_off + ncol));
           }
-          lo = make_float4(1.f + s4.x, fmaf(b4.x, 1.f + s4.x, h4.x), 1.f + s4.y,
-                           fmaf(b4.y, 1.f + s4.y, h4.y));
-          hi = make_float4(1.f + s4.z, fmaf(b4.z, 1.f + s4.z, h4.z), 1.f + s4.w,
-                           fmaf(b4.w, 1.f + s4.w, h4.w));
-        }
-        if (pass == 0) {
-          if (cl < kHalfN) {
-            const uint32_t ta = tab_base + (uint32_t)cl * 8u;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(lo.x),
-                         "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(hi.x),
-                         "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
-          }
-        } else {
-          // GroupNorm folded in: y = (v - mean) * rstd * gamma + beta with v = acc * a + b
-          //   => A = a * rstd * gamma, B = (b - mean) * rstd * gamma + beta, one table per clip-row
-          const int cg = p.n_valid / p.gn_groups;          // channels per group (multiple of 32)
-          const int spg = cg >> 5;                         // 32-channel sub-blocks per group
-          const int cnt = spg * p.stats_ns;                // partial sums per (clip-row, group)
-          const int g_first = (n0 + half * kHalfN) / cg;
-          const int g_last = (n0 + half * kHalfN + kHalfN - 1) / cg;
-          const double inv_n = 1.0 / ((double)cg * (double)p.t_valid);
-          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), be4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cl < kHalfN && ncol < p.n_valid) {
-            g4 = __ldg(reinterpret_cast<const float4*>(p.gn_gamma + ncol));
-            be4 = __ldg(reinterpret_cast<const float4*>(p.gn_beta + ncol));
-          }
-          const int my_g = ncol / cg;                      // 4 consecutive columns: one group
-          // all partial-sum loads of the (<= 2 clip-rows) x (<= 4 groups) of this warp are issued
-          // before any reduction, so their L2 latency is paid once
-          constexpr int kMaxG = kHalfN / 32;
-          float2 part[2][kMaxG];
-#pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            const int rr = ci == 0 ? r_lo : r_hi;
-            const bool live = r_hi >= r_lo && (ci == 0 || r_hi != r_lo);
-#pragma unroll
-            for (int gi = 0; gi < kMaxG; ++gi) {
-              part[ci][gi] = make_float2(0.f, 0.f);
-              const int g = g_first + gi;
-              if (live && g <= g_last && g < p.gn_groups) {
-                const float2* sp =
-                    p.stats + ((size_t)rr * p.stats_sub + (size_t)g * spg) * p.stats_ns;
-                for (int i = lane; i < cnt; i += 32) {
-                  const float2 v = __ldcg(sp + i);
-                  part[ci][gi].x += v.x;
-                  part[ci][gi].y += v.y;
-                }
-              }
-            }
-          }
-          for (int ci = 0; ci < 2; ++ci) {
-            float mean_c = 0.f, rstd_c = 0.f;
-#pragma unroll
-            for (int gi = 0; gi < kMaxG; ++gi) {
-              const int g = g_first + gi;
-              if (g > g_last) break;  // warp-uniform
-              double sa = (double)part[ci][gi].x, sb = (double)part[ci][gi].y;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                sb += __shfl_xor_sync(0xffffffffu, sb, o);
-              }
-              const double mean = sa * inv_n;
-              double var = sb * inv_n - mean * mean;
-              var = var > 0.0 ? var : 0.0;
-              if (g == my_g) {
-                mean_c = (float)mean;
-                rstd_c = (float)(1.0 / sqrt(var + (double)p.gn_eps));
-              }
-            }
-            if (cl < kHalfN) {
-              const float ga[4] = {g4.x * rstd_c, g4.y * rstd_c, g4.z * rstd_c, g4.w * rstd_c};
-              const float4 tlo = make_float4(lo.x * ga[0], fmaf(lo.y - mean_c, ga[0], be4.x),
-                                             lo.z * ga[1], fmaf(lo.w - mean_c, ga[1], be4.y));
-              const float4 thi = make_float4(hi.x * ga[2], fmaf(hi.y - mean_c, ga[2], be4.z),
-                                             hi.z * ga[3], fmaf(hi.w - mean_c, ga[3], be4.w));
-              const uint32_t ta = tab_base + (uint32_t)(ci * kHalfN + cl) * 8u;
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(tlo.x),
-                           "f"(tlo.y), "f"(tlo.z), "f"(tlo.w) : "memory");
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u), "f"(thi.x),
-                           "f"(thi.y), "f"(thi.z), "f"(thi.w) : "memory");
-            }
-          }
+          const uint32_t ta = tab_base + (uint32_t)cl * 8u;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta), "f"(1.f + s4.x),
+                       "f"(fmaf(b4.x, 1.f + s4.x, h4.x)), "f"(1.f + s4.y),
+                       "f"(fmaf(b4.y, 1.f + s4.y, h4.y))
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ta + 16u),
+                       "f"(1.f + s4.z), "f"(fmaf(b4.z, 1.f + s4.z, h4.z)), "f"(1.f + s4.w),
+                       "f"(fmaf(b4.w, 1.f + s4.w, h4.w))
+                       : "memory");
         }
         __syncwarp();
       }
-      // pass 1: lanes of the second clip-row of this warp read the second table
-      const uint32_t tab_lane =
-          tab_base + ((pass == 1 && in_range && r != r_lo) ? (uint32_t)kHalfN * 8u : 0u);
 
-      if (pass == 0) {
-        mbar_wait(tfull_bar(acc), wait_parity);
-        tc_fence_after_sync();
-      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
-      const CUtensorMap* tm_out = pass == 0 ? &tmOut : &tmOut2;
 
 #pragma unroll 1
       for (int c0 = half * kHalfN; c0 < (half + 1) * kHalfN; c0 += 32) {
@@ -451,24 +573,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         float f[32];
-        const uint32_t tcol = tab_lane + (uint32_t)(c0 - half * kHalfN) * 8u;
-        float4 ab[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(ab[j].x), "=f"(ab[j].y), "=f"(ab[j].z), "=f"(ab[j].w)
-                       : "r"(tcol + 16u * j));
+        const uint32_t tcol = tab_base + (uint32_t)(c0 - half * kHalfN) * 8u;
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          f[2 * j] = fmaf(__uint_as_float(v[2 * j]), ab[j].x, ab[j].y);
-          f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), ab[j].z, ab[j].w);
+          float4 ab;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(ab.x), "=f"(ab.y), "=f"(ab.z), "=f"(ab.w)
+                       : "r"(tcol + 16u * j));
+          f[2 * j] = fmaf(__uint_as_float(v[2 * j]), ab.x, ab.y);
+          f[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), ab.z, ab.w);
         }
-        if (pass == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = silu_tanh(f[j]);
-        }
-        if (film_row && pass == 0) {
+        if (film_row) {
           const float* sc = p.film + (size_t)r * p.film_ld + n;
           const float* sh = sc + p.film_shift_off;
 #pragma unroll
@@ -481,7 +597,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             f[j + 3] = fmaf(f[j + 3], 1.0f + s4.w, h4.w);
           }
         }
-        if (pass == 0 && p.residual != nullptr && valid) {
+        if (p.residual != nullptr && valid) {
           const uint4* rp =
               reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.res_ld + n);
 #pragma unroll
@@ -496,25 +612,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
           }
         }
-        if (pass == 0 && p.stats != nullptr) {
-          // Partial sum / sum of squares of this warp's 32 slots x 32 channels, per clip-row
-          // and per `gran`-channel sub-block, written (not accumulated) to a slot that only
-          // this warp owns: the consumer (gn_apply) adds the slices in a fixed order, so the
-          // statistics are deterministic and need no zeroing between steps.
+        if (p.stats != nullptr) {
+          // Sum / sum of squares of this lane's slot over each `gran`-channel sub-block (fp32,
+          // fixed order: independent of where the slot sits in the batch), then exact integer
+          // accumulation over the warp's 32 slots and one atomic per (clip-row, group).
           float q1[4], q2[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float v = valid ? f[q * 8 + j] : 0.f;
-              a += v;
-              b = fmaf(v, v, b);
+              const float x = valid ? f[q * 8 + j] : 0.f;
+              a += x;
+              b = fmaf(x, x, b);
             }
             q1[q] = a;
             q2[q] = b;
           }
-          const int nsub = 32 / p.stats_gran;  // sub-blocks inside this 32-channel chunk
+          const int nsub = 32 / gran;  // sub-blocks inside this 32-channel chunk
           if (nsub == 1) {
             q1[0] = (q1[0] + q1[1]) + (q1[2] + q1[3]);
             q2[0] = (q2[0] + q2[1]) + (q2[2] + q2[3]);
@@ -524,19 +639,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             q1[1] = q1[2] + q1[3];
             q2[1] = q2[2] + q2[3];
           }
-          const int sub0 = (n >> 3) / (p.stats_gran >> 3);
-          for (int rr = r_lo; rr <= r_hi; ++rr) {
-            const bool mine = in_range && r == rr;
-            const int t_first = m_first - rr * p.tp;
-            const int slice = t_first > 0 ? (t_first + 31) >> 5 : 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (q < nsub) {
-                const float a = warp_sum(mine ? q1[q] : 0.f);
-                const float b = warp_sum(mine ? q2[q] : 0.f);
-                if (lane == 0)
-                  p.stats[((size_t)rr * p.stats_sub + sub0 + q) * p.stats_ns + slice] =
-                      make_float2(a, b);
+          for (int q = 0; q < 4; ++q) {
+            if (q < nsub) {
+              const long long i1 = __float2ll_rn(q1[q] * kStatScale1);
+              const long long i2 = __float2ll_rn(q2[q] * kStatScale2);
+              const int g = (p.stats_c0 + n + q * gran) / p.stats_cg;
+              for (int rr = r_lo; rr <= r_hi; ++rr) {
+                const bool mine = in_range && r == rr;
+                const long long a = warp_sum_ll(mine ? i1 : 0ll);
+                const long long b = warp_sum_ll(mine ? i2 : 0ll);
+                if (lane == 0) {
+                  unsigned long long* sp = p.stats + ((size_t)rr * p.stats_pitch + g) * 2;
+                  atomicAdd(sp, (unsigned long long)a);
+                  atomicAdd(sp + 1, (unsigned long long)b);
+                }
               }
             }
           }
@@ -545,42 +662,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           // bf16 -> this warp's [32 slots][32 channels] staging tile (64B swizzle) -> one TMA
           // store; rows past the slab and channels past n_valid are clipped by the tensor map,
           // pad slots (t >= t_valid) are written as zeros to keep the conv padding intact.
-          // (fused GroupNorm with no raw output requested: pass 0 stores nothing)
-          if (pass == 1 || p.out != nullptr) {
-            // pass 1 runs after every MMA of the CTA (pair): the operand pipeline's shared
-            // memory is idle, so each box gets a staging tile of its own there and no store
-            // waits for the previous one; pass 0 reuses this warp's single staging tile
-            uint32_t stg = stg_base;
-            if (pass == 1) {
-              stg = smem_base + ((uint32_t)((warp - 2) * kMaxAcc * (kHalfN / 32)) + box_ord) *
-                                    (uint32_t)L::kOutBytesPerWarp;
-              ++box_ord;
-            } else {
-              if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the tile
-              __syncwarp();
-            }
-            const uint32_t srow = stg + (uint32_t)lane * 64u;
-            const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous box has left the tile
+          __syncwarp();
+          const uint32_t srow = stg + (uint32_t)lane * 64u;
+          const uint32_t sx = (uint32_t)(lane >> 1) & 3u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t q0 = 0u, q1w = 0u, q2w = 0u, q3 = 0u;
-              if (valid) {
-                q0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-                q1w = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-                q2w = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-                q3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-              }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                               srow + (((uint32_t)j ^ sx) << 4)),
-                           "r"(q0), "r"(q1w), "r"(q2w), "r"(q3)
-                           : "memory");
+          for (int j = 0; j < 4; ++j) {
+            uint32_t q0 = 0u, q1w = 0u, q2w = 0u, q3 = 0u;
+            if (valid) {
+              q0 = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+              q1w = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+              q2w = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+              q3 = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
             }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0 && m_first < (int)p.m) {
-              tma_store_2d(tm_out, stg, n, m_first);
-              tma_store_commit();
-            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                             srow + (((uint32_t)j ^ sx) << 4)),
+                         "r"(q0), "r"(q1w), "r"(q2w), "r"(q3)
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && m_first < (int)p.m) {
+            tma_store_2d(&tmOut, stg, n, m_first);
+            tma_store_commit();
           }
         } else {
           // fp32 [R, n_valid, t_valid]: lanes are consecutive t -> coalesced per channel
@@ -594,50 +698,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           }
         }
       }
-    };
-
-    if (!fuse_gn) {
-      uint32_t acc = 0, acc_phase = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
-        run_tile(tile, acc, acc_phase, 0);
-        tc_fence_before_sync();
-        if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
-        else mbar_arrive(tempty_bar(acc));
-        acc ^= 1u;
-        if (acc == 0) acc_phase ^= 1u;
-      }
-    } else {
-      // pass 0 over this CTA's tiles (their accumulators stay in TMEM), grid barrier once the
-      // partial GroupNorm sums of every CTA are in global memory, then the normalising pass
-      uint32_t ord = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) run_tile(tile, ord++, 0, 0);
-      __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      if (warp == 2 && lane == 0) {
-        volatile unsigned int* cnt = p.gn_barrier;
-        volatile unsigned int* gen = p.gn_barrier + 1;
-        const unsigned int g0 = *gen;
-        __threadfence();
-        if (atomicAdd(p.gn_barrier, 1u) == gridDim.x - 1) {
-          *cnt = 0u;
-          __threadfence();
-          atomicAdd(p.gn_barrier + 1, 1u);
-        } else {
-          const uint64_t t0 = global_timer_ns();
-          unsigned int spins = 0;
-          while (*gen == g0) {
-            if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 4000000000ull) {
-              printf("lm2a: conv grid barrier timeout (block %d)\n", (int)blockIdx.x);
-              __trap();
-            }
-          }
-        }
-        __threadfence();
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      tc_fence_after_sync();
-      ord = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) run_tile(tile, ord++, 0, 1);
+      tc_fence_before_sync();
+      if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      else mbar_arrive(tempty_bar(acc));
+      acc ^= 1u;
+      if (acc == 0) acc_phase ^= 1u;
     }
     if (lane == 0) tma_store_wait<0>();  // all boxes written before the grid completes
   }
@@ -652,7 +717,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
 }
 
 // ------------------------------------------------------------------ host side
-// 2-D bf16 map: inner = channels (box 64 -> 128 B, SWIZZLE_128B), outer = slots / rows.
 // bf16 output slab as seen by the epilogue's TMA stores: [32 channels x 32 slots] boxes, 64B swizzle
 int encode_2d_out(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
                   uint64_t pitch_elems) {
@@ -672,6 +736,7 @@ int encode_2d_out(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t ou
   return 0;
 }
 
+// 2-D bf16 operand map: inner = channels (box 64 -> 128 B, SWIZZLE_128B), outer = slots / rows.
 int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
               uint64_t pitch_elems, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
@@ -691,23 +756,20 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-template <int BLOCK_N, int STAGES, int CG>
+template <int BLOCK_N, int CG>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
-           const CUtensorMap& b, const CUtensorMap& o, const CUtensorMap& o2,
-           const ConvArgs& args) {
-  using L = SmemLayout<BLOCK_N, STAGES, CG>;
-  auto kern = conv_gemm_kernel<BLOCK_N, STAGES, CG>;
-  static bool configured = false;
-  if (!configured) {
+           const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
+  using L = SmemLayout<BLOCK_N, CG>;
+  auto kern = conv_gemm_kernel<BLOCK_N, CG>;
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
     LM2A_CUDA_OK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
-    configured = true;
-  }
   const int tiles = args.m_tiles * args.n_tiles;
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
   LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kThreads), L::kBytes, stream,
-                                     (unsigned)CG, a0, a1, b, o, o2, args));
+                                     (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
 }
@@ -719,12 +781,9 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
 struct TileChoice {
   int block_n, cg;
 };
-// max_tiles_per_unit > 0 restricts the choice to shapes where no CTA (pair) gets more tiles than
-// it has TMEM accumulators (512 / block_n): the fused GroupNorm keeps every tile resident.
-// Returns block_n = 0 when nothing fits.
-TileChoice choose_tile(long long m, int n_pad, bool keep_tiles_in_tmem = false) {
+TileChoice choose_tile(long long m, int n_pad) {
   const long long sms = num_sms();
-  TileChoice best{keep_tiles_in_tmem ? 0 : 128, 1};
+  TileChoice best{128, 1};
   long long best_cost = -1;
   const int bns[2] = {256, 128};
   for (int cg = 2; cg >= 1; --cg) {
@@ -734,7 +793,6 @@ TileChoice choose_tile(long long m, int n_pad, bool keep_tiles_in_tmem = false) 
       const long long tiles = ((m + 128 * cg - 1) / (128 * cg)) * (n_pad / bn);
       const long long units = sms / cg;
       const long long waves = (tiles + units - 1) / units;
-      if (keep_tiles_in_tmem && waves > 512 / bn) continue;
       const long long per_kb = cg == 2 ? (bn == 256 ? 512 : 384) : (bn == 256 ? 768 : 512);
       const long long cost = waves * per_kb;
       if (best_cost < 0 || cost < best_cost) {
@@ -753,7 +811,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   using namespace lm2a;
   LM2A_REQUIRE(d != nullptr, "conv1d: null descriptor");
   LM2A_REQUIRE(d->seg[0].x != nullptr && d->w != nullptr && d->bias != nullptr &&
-                   (d->out != nullptr || d->gn_gamma != nullptr),
+                   d->out != nullptr,
                "conv1d: null x / w / bias / out pointer");
   LM2A_REQUIRE(d->m > 0 && d->tp > 0 && d->t_valid > 0 && d->t_valid <= d->tp &&
                    d->m % d->tp == 0,
@@ -762,7 +820,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   LM2A_REQUIRE(d->n_pad > 0 && d->n_pad % 128 == 0 && d->n_valid > 0 && d->n_valid <= d->n_pad,
                "conv1d: n_pad=%d must be a positive multiple of 128 (n_valid=%d)", d->n_pad,
                d->n_valid);
-  LM2A_REQUIRE(d->m < (1ll << 31) - 256, "conv1d: too many slots");
+  LM2A_REQUIRE(d->m < (1ll << 31) - 512, "conv1d: too many slots");
 
   ConvArgs a{};
   CUtensorMap tmA[2];
@@ -793,44 +851,23 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
                    (long long)g.rows, (long long)d->m);
       a.seg_half[s] = g.ld;
       ntaps = 4;
+      // slot pairs: one row of the [rows / 2, 2 * ld] view = (even slot | odd slot); a box
+      // covers the pairs t (+1 halo) of one half
       if (encode_2d(&tmA[s], g.x, (uint64_t)g.ld + g.cin, (uint64_t)g.rows / 2,
-                    (uint64_t)g.ld * 2, kBlockM))
+                    (uint64_t)g.ld * 2, kBlockM + 1))
         return 1;
     } else {
       LM2A_REQUIRE(g.rows == d->m, "conv1d: seg %d slots (%lld) != output slots (%lld)", s,
                    (long long)g.rows, (long long)d->m);
       a.seg_half[s] = 0;
       ntaps = g.taps == LM2A_TAPS_K3 ? 3 : 1;
-      if (encode_2d(&tmA[s], g.x, (uint64_t)g.cin, (uint64_t)g.rows, (uint64_t)g.ld, kBlockM))
+      if (encode_2d(&tmA[s], g.x, (uint64_t)g.cin, (uint64_t)g.rows, (uint64_t)g.ld,
+                    g.taps == LM2A_TAPS_K3 ? kBlockM + 2 : kBlockM))
         return 1;
     }
     k_total += ntaps * g.cin;
   }
-  const bool fuse_gn = d->gn_gamma != nullptr;
-  if (fuse_gn) {
-    LM2A_REQUIRE(d->gn_beta != nullptr && d->gn_out != nullptr && d->gn_barrier != nullptr &&
-                     d->stats != nullptr && d->stats_gran == 32,
-                 "conv1d: fused GroupNorm needs gn_beta, gn_out, gn_barrier and 32-channel stats");
-    LM2A_REQUIRE(d->out_mode == LM2A_OUT_BF16_SLAB && d->gn_groups > 0 &&
-                     d->n_valid % d->gn_groups == 0 && (d->n_valid / d->gn_groups) % 32 == 0 &&
-                     d->tp >= 32 && (d->film == nullptr || d->film_ld == 0),
-                 "conv1d: fused GroupNorm needs >= 32-channel groups, tp >= 32 and a uniform "
-                 "FiLM table (n=%d groups=%d tp=%d film_ld=%d)", d->n_valid, d->gn_groups,
-                 d->tp, d->film_ld);
-    LM2A_REQUIRE(d->gn_out_ld % 8 == 0 && d->gn_out_ld >= d->n_valid &&
-                     ((reinterpret_cast<uintptr_t>(d->gn_out) |
-                       reinterpret_cast<uintptr_t>(d->gn_gamma) |
-                       reinterpret_cast<uintptr_t>(d->gn_beta)) & 15) == 0,
-                 "conv1d: gn_out / gn_gamma / gn_beta alignment");
-  }
   int block_n = d->block_n, cg = d->cta_group;
-  if (fuse_gn && (block_n == 0 || cg == 0)) {
-    const TileChoice c = choose_tile(d->m, d->n_pad, true);
-    LM2A_REQUIRE(c.block_n != 0, "conv1d: fused GroupNorm: %lld x %d output does not fit the "
-                 "chip's TMEM accumulators (see lm2a_conv_gn_fusable)", (long long)d->m, d->n_pad);
-    block_n = c.block_n;
-    cg = c.cg;
-  }
   if (cg == 0) {
     // LM2A_CONV_CG=1|2 pins the auto choice (A/B measurements); unset = wave model
     static const int forced = [] {
@@ -865,7 +902,6 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
                 (uint32_t)(block_n / cg)))
     return 1;
 
-  a.num_kb = k_total / 64;
   a.m_tiles = (int)((d->m + kBlockM * cg - 1) / (kBlockM * cg));
   a.n_tiles = d->n_pad / block_n;
   a.m = d->m;
@@ -890,67 +926,70 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   a.out = d->out;
   a.out_ld = d->out_ld;
   a.out_mode = d->out_mode;
-  a.stats = reinterpret_cast<float2*>(d->stats);
-  a.stats_sub = d->stats_sub;
-  a.stats_ns = d->stats_ns;
-  a.stats_gran = d->stats_gran;
+  a.stats = reinterpret_cast<unsigned long long*>(d->stats);
+  a.stats_pitch = d->stats_pitch;
+  a.stats_cg = d->stats_cg > 0 ? d->stats_cg : 32;
+  a.stats_c0 = d->stats_c0;
   if (d->stats != nullptr) {
     LM2A_REQUIRE(d->out_mode == LM2A_OUT_BF16_SLAB, "conv1d: stats need a bf16 slab output");
-    LM2A_REQUIRE((d->stats_gran == 8 || d->stats_gran == 16 || d->stats_gran == 32) &&
-                     d->stats_sub > 0 && d->stats_ns >= d->tp / 32 + 2 &&
-                     (reinterpret_cast<uintptr_t>(d->stats) & 7) == 0,
-                 "conv1d: bad stats layout (gran=%d sub=%d ns=%d, need ns >= tp/32+2 = %d)",
-                 d->stats_gran, d->stats_sub, d->stats_ns, d->tp / 32 + 2);
+    LM2A_REQUIRE(d->stats_cg > 0 && d->stats_cg % 8 == 0 && d->stats_pitch > 0 &&
+                     d->stats_c0 >= 0 && d->stats_c0 % 8 == 0 &&
+                     (d->stats_c0 + d->n_valid + d->stats_cg - 1) / d->stats_cg <= d->stats_pitch &&
+                     (reinterpret_cast<uintptr_t>(d->stats) & 15) == 0,
+                 "conv1d: bad stats layout (channels per group=%d, groups per row=%d, first "
+                 "channel=%d, n=%d)", d->stats_cg, d->stats_pitch, d->stats_c0, d->n_valid);
+  }
+  a.gn_stats = reinterpret_cast<const long long*>(d->in_gn_stats);
+  a.gn_gamma = d->in_gn_gamma;
+  a.gn_beta = d->in_gn_beta;
+  a.gn_pitch = d->in_gn_pitch;
+  a.gn_groups = d->in_gn_groups;
+  a.gn_eps = d->in_gn_eps;
+  a.gn_silu = d->in_gn_silu;
+  if (d->in_gn_stats != nullptr) {
+    const lm2a_conv_seg& g = d->seg[0];
+    LM2A_REQUIRE(d->in_gn_gamma != nullptr && d->in_gn_beta != nullptr && d->in_gn_groups > 0 &&
+                     d->in_gn_pitch >= d->in_gn_groups && g.cin % d->in_gn_groups == 0 &&
+                     (g.cin / d->in_gn_groups) % 8 == 0 && g.cin <= kMaxGnChannels,
+                 "conv1d: input GroupNorm needs gamma / beta, groups dividing cin=%d into "
+                 "multiples of 8 channels, cin <= %d (groups=%d pitch=%d)", g.cin,
+                 kMaxGnChannels, d->in_gn_groups, d->in_gn_pitch);
+    LM2A_REQUIRE(g.taps == LM2A_TAPS_K1 || g.taps == LM2A_TAPS_K3,
+                 "conv1d: input GroupNorm is available for k1 / k3 segments only");
+    LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(d->in_gn_stats) |
+                   reinterpret_cast<uintptr_t>(d->in_gn_gamma) |
+                   reinterpret_cast<uintptr_t>(d->in_gn_beta)) & 15) == 0,
+                 "conv1d: input GroupNorm stats / gamma / beta must be 16-byte aligned");
+    a.gn_cg = g.cin / d->in_gn_groups;
+    const int clip_rows = (kBlockM + 2 - 1) / d->tp + 2;   // clip-rows a 130-slot block can touch
+    LM2A_REQUIRE(clip_rows * d->in_gn_groups <= kMaxGnEntries,
+                 "conv1d: input GroupNorm: %d clip-rows x %d groups per tile exceed %d entries "
+                 "(clips of %d slots are too short for the fused path)", clip_rows,
+                 d->in_gn_groups, kMaxGnEntries, d->tp);
   }
   if (d->out_mode == LM2A_OUT_BF16_SLAB) {
-    LM2A_REQUIRE((d->out == nullptr || (d->out_ld % 8 == 0 && d->out_ld >= d->n_valid)) &&
-                     d->n_valid % 32 == 0,
+    LM2A_REQUIRE(d->out_ld % 8 == 0 && d->out_ld >= d->n_valid && d->n_valid % 32 == 0,
                  "conv1d: bf16 slab output needs ld %% 8 == 0 and n_valid %% 32 == 0 (ld=%d n=%d)",
                  d->out_ld, d->n_valid);
   } else {
     LM2A_REQUIRE(d->out_mode == LM2A_OUT_F32_NCT, "conv1d: bad out_mode %d", d->out_mode);
   }
+  // LM2A_DESC_BASE_OFFSET=0: row-shifted tap views without the matrix-base-offset field
+  static const int base_off = [] {
+    const char* e = getenv("LM2A_DESC_BASE_OFFSET");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  a.desc_base_offset = base_off;
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tmOut = tmB, tmOut2 = tmB;  // unused in the fp32 output mode / without fusion
-  if (d->out_mode == LM2A_OUT_BF16_SLAB && d->out != nullptr &&
+  CUtensorMap tmOut = tmB;  // unused in the fp32 output mode
+  if (d->out_mode == LM2A_OUT_BF16_SLAB &&
       encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
     return 1;
-  a.gn_gamma = d->gn_gamma;
-  a.gn_beta = d->gn_beta;
-  a.gn_groups = d->gn_groups;
-  a.gn_eps = d->gn_eps;
-  a.gn_barrier = reinterpret_cast<unsigned int*>(d->gn_barrier);
-  if (fuse_gn) {
-    const long long tiles = (long long)a.m_tiles * a.n_tiles;
-    const long long units = num_sms() / cg;
-    LM2A_REQUIRE((tiles + units - 1) / units <= 512 / block_n,
-                 "conv1d: fused GroupNorm: %lld tiles over %lld CTA%s exceed the %d TMEM "
-                 "accumulators", tiles, units, cg == 2 ? " pairs" : "s", 512 / block_n);
-    if (encode_2d_out(&tmOut2, d->gn_out, (uint64_t)d->n_valid, (uint64_t)d->m,
-                      (uint64_t)d->gn_out_ld))
-      return 1;
-  }
   if (cg == 2) {
-    if (block_n == 256) return launch<256, 6, 2>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
-    return launch<128, 8, 2>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+    if (block_n == 256) return launch<256, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
+    return launch<128, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
   }
-  if (block_n == 256) return launch<256, 4, 1>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
-  return launch<128, 6, 1>(st, tmA[0], tmA[1], tmB, tmOut, tmOut2, a);
+  if (block_n == 256) return launch<256, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  return launch<128, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
 }
-
-extern "C" int lm2a_conv_gn_fusable(int64_t m, int32_t n_pad) {
-  if (m <= 0 || n_pad <= 0 || n_pad % 128 != 0) return 0;
-  return lm2a::choose_tile(m, n_pad, true).block_n != 0 ? 1 : 0;
-}
-
-#ifdef LM2A_CONV_TIMING
-// instrumented build only: read (and clear) the counters of g_conv_timing into out[8]
-extern "C" int lm2a_conv_timing_read(unsigned long long* out) {
-  cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out, lm2a::g_conv_timing, 8 * sizeof(unsigned long long)) != cudaSuccess)
-    return 1;
-  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  return cudaMemcpyToSymbol(lm2a::g_conv_timing, zero, sizeof(zero)) == cudaSuccess ? 0 : 1;
-}
-#endif

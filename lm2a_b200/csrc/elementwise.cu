@@ -7,15 +7,29 @@
 namespace lm2a {
 namespace {
 
+// torch.clamp semantics: NaN propagates (fminf / fmaxf alone would turn a NaN eps into a bound,
+// and the non-finite early stop of the sampling loop, reference sample.py:216-223, could never
+// trigger)
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) {
+  return v != v ? v : fminf(fmaxf(v, lo), hi);
+}
+
 // ---------------------------------------------------------------------------
 // x fp32 [B, c, T] -> bf16 slab [copies*B, tp, ld]. CFG doubles the batch by
 // feeding the same x to the uncond and cond rows (reference sample.py:162), so
-// one read of x feeds `copies` rows.
+// one read of x feeds `copies` rows. First kernel of a UNet step: it also clears the
+// step's GroupNorm statistics arena (the conv / bias_add epilogues accumulate into it).
 __global__ void __launch_bounds__(256)
 ingest_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ slab, int batch,
-                int copies, int c, int T, int tp, int ld) {
+                int copies, int c, int T, int tp, int ld, uint4* __restrict__ zero,
+                long long zero_vec) {
   pdl_wait();
   pdl_launch_dependents();
+  {
+    const long long nthr = (long long)gridDim.x * gridDim.y * blockDim.x;
+    const long long tid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    for (long long i = tid; i < zero_vec; i += nthr) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __shared__ float tile[32][129];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
@@ -146,100 +160,61 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* 
 // y[slot, :] = x[slot, :] + bias for valid slots (zero for the pad slots): the
 // identity-skip ResBlock of an all-zero-condition row, whose attention output is a
 // constant vector (reference unet1d_ultimate.py:152-159 with cross_attention.py:38-67).
-// One CTA = one 32-slot segment (the same segmentation as the conv epilogue), so it can emit
-// the same partial GroupNorm statistics of y for lm2a_gn_apply_bf16.
+// One CTA = one 32-slot segment; thread = one 8-channel vector column, every `tstep`-th slot.
+// Optionally accumulates the exact GroupNorm sums of y (see lm2a_conv_desc.stats): per (slot,
+// vector) the fp32 sum / sum of squares of its 8 channels in a fixed order, converted to
+// 64-bit fixed point (2^24 / 2^20) and added with integer arithmetic, so the statistics do
+// not depend on how slots are grouped into CTAs.
 __global__ void __launch_bounds__(256)
 bias_add_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
                 int y_ld, const float* __restrict__ bias, long long slots, int tp, int t_valid,
-                int c, float2* __restrict__ stats, int stats_sub, int stats_ns, int stats_gran) {
+                int c, unsigned long long* __restrict__ stats, int stats_pitch, int stats_cg,
+                int stats_c0) {
   pdl_wait();
   pdl_launch_dependents();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m_first = (long long)blockIdx.x * 32;
   const int vpr = c >> 3;
-  const int lanes_per_sub = stats != nullptr ? stats_gran >> 3 : 1;
-  for (int cvb = warp * 32; cvb < vpr; cvb += 256) {
-    const int cv = cvb + lane;
-    const bool active = cv < vpr;
+  const int lanes = vpr < 256 ? vpr : 256;
+  const int tstep = 256 / lanes;
+  const int cvl = threadIdx.x % lanes, ts = threadIdx.x / lanes;
+  if (ts >= tstep) return;   // vector-column counts that do not divide the CTA
+  // lanes of a warp that hold vectors of one group are combined by a shuffle tree first
+  // (only when every warp sees one slot lane and groups are power-of-two runs of lanes)
+  int lg = 1;
+  if (stats != nullptr && lanes % 32 == 0 && vpr % 32 == 0) {
+    const int l = stats_cg >> 3;
+    if (l <= 32 && (l & (l - 1)) == 0 && stats_c0 % stats_cg == 0) lg = l;
+  }
+  for (int cv = cvl; cv < vpr; cv += 256) {
     float bv[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) bv[e] = active ? __ldg(bias + cv * 8 + e) : 0.f;
-    float a = 0.f, b = 0.f;
-    int r_cur = (int)(m_first / tp);
+    for (int e = 0; e < 8; ++e) bv[e] = __ldg(bias + cv * 8 + e);
+    long long s1 = 0, s2 = 0;
+    int r_cur = (int)((m_first + ts) / tp);
     auto flush = [&](int rr) {
       if (stats == nullptr) return;
-      float sa = a, sb = b;
-      for (int o = 1; o < lanes_per_sub; o <<= 1) {
-        sa += __shfl_xor_sync(0xffffffffu, sa, o);
-        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      long long a = s1, b = s2;
+      for (int o = 1; o < lg; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
       }
-      if (active && (cv % lanes_per_sub) == 0) {
-        const long long t_first = m_first - (long long)rr * tp;
-        const int slice = t_first > 0 ? (int)((t_first + 31) >> 5) : 0;
-        stats[((size_t)rr * stats_sub + (size_t)(cv / lanes_per_sub)) * stats_ns + slice] =
-            make_float2(sa, sb);
+      if ((cv & (lg - 1)) == 0 && (a != 0 || b != 0)) {
+        unsigned long long* sp =
+            stats + ((size_t)rr * stats_pitch + (stats_c0 + cv * 8) / stats_cg) * 2;
+        atomicAdd(sp, (unsigned long long)a);
+        atomicAdd(sp + 1, (unsigned long long)b);
       }
+      s1 = s2 = 0;
     };
-    for (int sidx = 0; sidx < 32; ++sidx) {
+    for (int sidx = ts; sidx < 32; sidx += tstep) {
       const long long m = m_first + sidx;
       if (m >= slots) break;
       const int r = (int)(m / tp);
       const int t = (int)(m - (long long)r * tp);
       if (r != r_cur) {
         flush(r_cur);
-        a = b = 0.f;
         r_cur = r;
       }
-      if (!active) continue;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (t < t_valid) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * x_ld + cv * 8));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_bf16x2(w[e]);
-          const float v0 = f.x + bv[2 * e], v1 = f.y + bv[2 * e + 1];
-          a += v0 + v1;
-          b = fmaf(v0, v0, fmaf(v1, v1, b));
-          ow[e] = pack_bf16x2(v0, v1);
-        }
-        o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-      *reinterpret_cast<uint4*>(y + (size_t)m * y_ld + cv * 8) = o;
-    }
-    flush(r_cur);
-  }
-}
-
-// Same contract for tp >= 32 (a 32-slot segment then touches at most two clip-rows): all 256
-// threads stream the segment in parallel (thread = one 8-channel vector column, every
-// `tstep`-th slot); the partial sums are combined through shared memory in a fixed order.
-__global__ void __launch_bounds__(256)
-bias_add_par_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
-                    int y_ld, const float* __restrict__ bias, int slots, int tp, int t_valid,
-                    int c, float2* __restrict__ stats, int stats_sub, int stats_ns,
-                    int stats_gran) {
-  pdl_wait();
-  pdl_launch_dependents();
-  __shared__ float4 red[256];
-  const int m_first = blockIdx.x * 32;
-  const int vpr = c >> 3;
-  const int lanes = vpr < 256 ? vpr : 256;   // host guarantees 256 % lanes == 0
-  const int tstep = 256 / lanes;
-  const int cvl = threadIdx.x % lanes, ts = threadIdx.x / lanes;
-  const int r_lo = m_first / tp;
-  const int lanes_per_sub = stats != nullptr ? stats_gran >> 3 : 1;
-  for (int cv = cvl; cv < vpr; cv += 256) {
-    float bv[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) bv[e] = __ldg(bias + cv * 8 + e);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // {sum, sumsq} of clip r_lo, of clip r_lo + 1
-    for (int sidx = ts; sidx < 32; sidx += tstep) {
-      const int m = m_first + sidx;
-      if (m >= slots) break;
-      const int r = m / tp;
-      const int t = m - r * tp;
       uint4 o = make_uint4(0u, 0u, 0u, 0u);
       if (t < t_valid) {
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (size_t)m * x_ld + cv * 8));
@@ -255,48 +230,12 @@ bias_add_par_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16
           ow[e] = pack_bf16x2(v0, v1);
         }
         o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        if (r == r_lo) {
-          acc.x += a;
-          acc.y += b;
-        } else {
-          acc.z += a;
-          acc.w += b;
-        }
+        s1 += __float2ll_rn(a * 16777216.0f);
+        s2 += __float2ll_rn(b * 1048576.0f);
       }
       *reinterpret_cast<uint4*>(y + (size_t)m * y_ld + cv * 8) = o;
     }
-    if (stats != nullptr) {
-      __syncthreads();
-      red[threadIdx.x] = acc;
-      __syncthreads();
-      if (ts == 0) {
-        float4 tot = red[cvl];
-        for (int k = 1; k < tstep; ++k) {
-          const float4 v = red[k * lanes + cvl];
-          tot.x += v.x;
-          tot.y += v.y;
-          tot.z += v.z;
-          tot.w += v.w;
-        }
-        // lanes_per_sub (1, 2 or 4) adjacent vector columns form one sub-block
-        for (int o = 1; o < lanes_per_sub; o <<= 1) {
-          tot.x += __shfl_xor_sync(0xffffffffu, tot.x, o);
-          tot.y += __shfl_xor_sync(0xffffffffu, tot.y, o);
-          tot.z += __shfl_xor_sync(0xffffffffu, tot.z, o);
-          tot.w += __shfl_xor_sync(0xffffffffu, tot.w, o);
-        }
-        if ((cv % lanes_per_sub) == 0) {
-          const int m_last = m_first + 31 < slots - 1 ? m_first + 31 : slots - 1;
-          const int r_hi = m_last / tp;
-          const int t0 = m_first - r_lo * tp;
-          stats[((size_t)r_lo * stats_sub + cv / lanes_per_sub) * stats_ns +
-                (t0 > 0 ? (t0 + 31) >> 5 : 0)] = make_float2(tot.x, tot.y);
-          if (r_hi > r_lo)
-            stats[((size_t)r_hi * stats_sub + cv / lanes_per_sub) * stats_ns] =
-                make_float2(tot.z, tot.w);
-        }
-      }
-    }
+    flush(r_cur);
   }
 }
 
@@ -419,9 +358,9 @@ cfg_posterior_kernel(float* __restrict__ x, const float* __restrict__ eps,
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float d = __fsub_rn(c[k], u[k]);
-        d = fminf(fmaxf(d, -5.0f), 5.0f);
+        d = clamp_nan(d, -5.0f, 5.0f);
         float g = __fadd_rn(u[k], __fmul_rn(gw, d));
-        o[k] = fminf(fmaxf(g, -10.0f), 10.0f);
+        o[k] = clamp_nan(g, -10.0f, 10.0f);
       }
       e = make_float4(o[0], o[1], o[2], o[3]);
     } else {
@@ -492,9 +431,9 @@ cfg_ddim_kernel(float* __restrict__ x, const float* __restrict__ eps,
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float d = __fsub_rn(c[q], u[q]);
-        d = fminf(fmaxf(d, -5.0f), 5.0f);
+        d = clamp_nan(d, -5.0f, 5.0f);
         const float g = __fadd_rn(u[q], __fmul_rn(gw, d));
-        e[q] = fminf(fmaxf(g, -10.0f), 10.0f);
+        e[q] = clamp_nan(g, -10.0f, 10.0f);
       }
     } else {
       const float4 ev = __ldg(reinterpret_cast<const float4*>(eps) + i);
@@ -508,7 +447,7 @@ cfg_ddim_kernel(float* __restrict__ x, const float* __restrict__ eps,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float p0 = __fdiv_rn(__fsub_rn(xv[q], __fmul_rn(e[q], c0)), c1);
-      p0 = fminf(fmaxf(p0, -2.0f), 2.0f);
+      p0 = clamp_nan(p0, -2.0f, 2.0f);
       x0[q] = p0;
       o[q] = __fadd_rn(__fadd_rn(__fmul_rn(c2, p0), __fmul_rn(c3, e[q])),
                        __fmul_rn(sigma, zv[q]));
@@ -574,6 +513,8 @@ __device__ __forceinline__ float block_minmax(float v, bool is_max, float* red) 
 __global__ void __launch_bounds__(1024)
 mel_metrics_kernel(const float* __restrict__ gen, const float* __restrict__ real,
                    double* __restrict__ out, int n_mels, int T, float g_scale, float g_shift) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ double red[32];
   __shared__ float redf[32];
   const int b = blockIdx.x;
@@ -710,6 +651,8 @@ __global__ void __launch_bounds__(256)
 adan_step_kernel(const lm2a_adan_tensor* __restrict__ tensors,
                  const int* __restrict__ chunk_tensor, const int* __restrict__ chunk_index,
                  int chunk_elems, AdanScalars s) {
+  pdl_wait();
+  pdl_launch_dependents();
   const lm2a_adan_tensor t = tensors[chunk_tensor[blockIdx.x]];
   const long long begin = (long long)chunk_index[blockIdx.x] * chunk_elems;
   const long long end = begin + chunk_elems < t.numel ? begin + chunk_elems : t.numel;
@@ -754,15 +697,22 @@ adan_step_kernel(const lm2a_adan_tensor* __restrict__ tensors,
 }  // namespace lm2a
 
 extern "C" int lm2a_ingest_x(void* stream, const float* x, void* slab, int32_t batch,
-                             int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld) {
+                             int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld,
+                             void* zero, int64_t zero_bytes) {
   using namespace lm2a;
   LM2A_REQUIRE(x && slab, "ingest_x: null pointer");
   LM2A_REQUIRE(batch > 0 && copies > 0 && c > 0 && c <= 128 && ld <= 128 && ld >= c && t > 0 &&
                    tp >= t,
                "ingest_x: bad geometry (c=%d ld=%d t=%d tp=%d; c, ld <= 128)", c, ld, t, tp);
+  LM2A_REQUIRE(zero_bytes >= 0 && zero_bytes % 16 == 0 &&
+                   (zero_bytes == 0 || (zero != nullptr &&
+                                        (reinterpret_cast<uintptr_t>(zero) & 15) == 0)),
+               "ingest_x: the region to clear must be 16-byte aligned and sized");
   dim3 grid((tp + 31) / 32, batch);
-  LM2A_CUDA_OK(launch_kernel(ingest_x_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      x, reinterpret_cast<__nv_bfloat16*>(slab), batch, copies, c, t, tp, ld));
+  LM2A_CUDA_OK(launch_kernel(ingest_x_kernel, dim3(grid), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream), x,
+                             reinterpret_cast<__nv_bfloat16*>(slab), batch, copies, c, t, tp, ld,
+                             reinterpret_cast<uint4*>(zero), (long long)(zero_bytes / 16)));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -838,37 +788,32 @@ extern "C" int lm2a_upsample2x_bf16(void* stream, const void* x, int32_t x_ld, v
 
 extern "C" int lm2a_bias_add_bf16(void* stream, const void* x, int32_t x_ld, void* y,
                                   int32_t y_ld, const float* bias, int64_t slots, int32_t tp,
-                                  int32_t t_valid, int32_t c, void* stats, int32_t stats_sub,
-                                  int32_t stats_ns, int32_t stats_gran) {
+                                  int32_t t_valid, int32_t c, void* stats, int32_t stats_pitch,
+                                  int32_t stats_cg, int32_t stats_c0) {
   using namespace lm2a;
   LM2A_REQUIRE(x && y && bias, "bias_add: null pointer");
   LM2A_REQUIRE(slots > 0 && tp > 0 && t_valid > 0 && t_valid <= tp && slots % tp == 0 &&
-                   c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
+                   c > 0 && c % 8 == 0 && x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
                "bias_add: bad geometry");
   LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                  reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
                "bias_add: tensors must be 16-byte aligned");
   if (stats != nullptr) {
-    LM2A_REQUIRE((stats_gran == 8 || stats_gran == 16 || stats_gran == 32) &&
-                     c % stats_gran == 0 && stats_sub >= c / stats_gran &&
-                     stats_ns >= tp / 32 + 2 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
-                 "bias_add: bad stats layout (gran=%d sub=%d ns=%d)", stats_gran, stats_sub,
-                 stats_ns);
+    LM2A_REQUIRE(stats_cg > 0 && stats_cg % 8 == 0 && stats_pitch > 0 && stats_c0 >= 0 &&
+                     stats_c0 % 8 == 0 &&
+                     (stats_c0 + c + stats_cg - 1) / stats_cg <= stats_pitch &&
+                     (reinterpret_cast<uintptr_t>(stats) & 15) == 0,
+                 "bias_add: bad stats layout (channels per group=%d, groups per row=%d, first "
+                 "channel=%d)", stats_cg, stats_pitch, stats_c0);
   }
   const long long blocks = (slots + 31) / 32;
-  const int vpr = c / 8;
   LM2A_REQUIRE(slots < (1ll << 31) - 64, "bias_add: too many slots");
-  if (tp >= 32 && vpr % 32 == 0 && (vpr >= 256 ? vpr % 256 == 0 : 256 % vpr == 0)) {
-    LM2A_CUDA_OK(launch_kernel(bias_add_par_kernel, dim3((unsigned)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
-        y_ld, bias, (int)slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub,
-        stats_ns, stats_gran));
-  } else {
-    LM2A_CUDA_OK(launch_kernel(bias_add_kernel, dim3((unsigned)blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-        reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y),
-        y_ld, bias, slots, tp, t_valid, c, reinterpret_cast<float2*>(stats), stats_sub, stats_ns,
-        stats_gran));
-  }
+  LM2A_CUDA_OK(launch_kernel(bias_add_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                             reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
+                             reinterpret_cast<__nv_bfloat16*>(y), y_ld, bias, (long long)slots, tp,
+                             t_valid, c, reinterpret_cast<unsigned long long*>(stats), stats_pitch,
+                             stats_cg, stats_c0));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

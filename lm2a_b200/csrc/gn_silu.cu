@@ -124,26 +124,27 @@ gn_silu_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __r
 }
 
 // ---------------------------------------------------------------------------
-// GroupNorm + SiLU as a pure streaming pass: the per-(row, group) sums were already
+// GroupNorm + SiLU as a pure streaming pass: the per-(clip-row, group) sums were already
 // produced by the epilogue of the kernel that wrote x (lm2a_conv1d_bf16 / lm2a_bias_add_bf16
-// `stats`), so this kernel only adds the partial slices (fixed order, fp64), derives
+// `stats`: exact 64-bit fixed-point sums, 2^24 / 2^20 scaled), so this kernel only derives
 // mean / rstd and applies y = SiLU(x * a_c + b_c). One CTA = a few consecutive slots of one
 // clip-row, all channels; every thread owns one 8-channel vector column (4 slots of it).
+// The UNet plan applies the same transform inside the consuming conv (lm2a_conv_desc.in_gn_*);
+// this stand-alone pass serves callers that need the normalised slab itself.
 constexpr int kApplyVec = 4;  // 16-byte vectors per thread and pass
 
 __global__ void __launch_bounds__(kGnThreads)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ y,
-                int y_ld, const float2* __restrict__ stats, int stats_sub, int stats_ns,
-                int stats_gran, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int y_ld, const long long* __restrict__ stats, int stats_pitch,
+                const float* __restrict__ gamma, const float* __restrict__ beta,
                 int tp, int t_valid, int c, int groups, float eps, int apply_silu) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float s_mean[64], s_rstd[64];
   const int r = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cg = c / groups;
   // thread -> (vector column, slot) mapping; the first pass's loads are issued before the
-  // statistics are reduced so their latency overlaps
+  // statistics are read so their latency overlaps
   const int vpr = c >> 3;
   const int lanes = vpr < kGnThreads ? vpr : kGnThreads;
   const int passes = (vpr + kGnThreads - 1) / kGnThreads;
@@ -162,29 +163,15 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
     if (active && t < t_valid)
       q[k] = __ldg(reinterpret_cast<const uint4*>(x + (row_base + t) * x_ld + cvl * 8));
   }
-  const int sub_per_group = cg / stats_gran;
-  const int per_group = sub_per_group * stats_ns;
-  const double inv_n = 1.0 / ((double)cg * (double)t_valid);
-  for (int g = warp; g < groups; g += kGnThreads / 32) {
-    const float2* sp = stats + ((size_t)r * stats_sub + (size_t)g * sub_per_group) * stats_ns;
-    double a = 0.0, b = 0.0;
-    for (int i = lane; i < per_group; i += 32) {
-      const float2 v = __ldg(sp + i);
-      a += (double)v.x;
-      b += (double)v.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) {
-      const double mean = a * inv_n;
-      double var = b * inv_n - mean * mean;
-      var = var > 0.0 ? var : 0.0;
-      s_mean[g] = (float)mean;
-      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    const long long* sp = stats + ((size_t)r * stats_pitch + g) * 2;
+    const double inv_n = 1.0 / ((double)cg * (double)t_valid);
+    const double mean = (double)__ldcg(sp) * (1.0 / 16777216.0) * inv_n;
+    double var = (double)__ldcg(sp + 1) * (1.0 / 1048576.0) * inv_n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
 
@@ -206,7 +193,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
     for (int e = 0; e < 8; ++e) {
       const float gm = __ldg(gamma + cv * 8 + e) * rstd;
       ga[e] = gm;
-      be[e] = __ldg(beta + cv * 8 + e) - mean * gm;
+      be[e] = fmaf(-mean, gm, __ldg(beta + cv * 8 + e));
     }
 #pragma unroll
     for (int k = 0; k < kApplyVec; ++k) {
@@ -238,36 +225,34 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
 }  // namespace lm2a
 
 extern "C" int lm2a_gn_apply_bf16(void* stream, const void* x, int32_t x_ld, void* y,
-                                  int32_t y_ld, const void* stats, int32_t stats_sub,
-                                  int32_t stats_ns, int32_t stats_gran, const float* gamma,
-                                  const float* beta, int32_t rows, int32_t tp, int32_t t_valid,
-                                  int32_t c, int32_t groups, float eps, int32_t apply_silu) {
+                                  int32_t y_ld, const void* stats, int32_t stats_pitch,
+                                  const float* gamma, const float* beta, int32_t rows,
+                                  int32_t tp, int32_t t_valid, int32_t c, int32_t groups,
+                                  float eps, int32_t apply_silu) {
   using namespace lm2a;
   LM2A_REQUIRE(x && y && stats && gamma && beta, "gn_apply: null pointer");
   LM2A_REQUIRE(rows > 0 && rows <= 65535 && tp > 0 && t_valid > 0 && t_valid <= tp,
                "gn_apply: bad geometry");
-  LM2A_REQUIRE(groups > 0 && groups <= 64 && c % groups == 0,
-               "gn_apply: c=%d not divisible by groups=%d (<= 64)", c, groups);
-  const int cg = c / groups;
+  LM2A_REQUIRE(groups > 0 && groups <= 64 && c % groups == 0 && stats_pitch >= groups,
+               "gn_apply: c=%d not divisible by groups=%d (<= 64, stats pitch %d)", c, groups,
+               stats_pitch);
   const int vpr = c / 8;
-  LM2A_REQUIRE(c % 8 == 0 && vpr > 0, "gn_apply: c=%d must be a positive multiple of 8", c);
-  LM2A_REQUIRE((stats_gran == 8 || stats_gran == 16 || stats_gran == 32) &&
-                   cg % stats_gran == 0 && stats_sub >= c / stats_gran &&
-                   stats_ns >= tp / 32 + 2,
-               "gn_apply: stats layout (gran=%d sub=%d ns=%d) does not fit c=%d groups=%d tp=%d",
-               stats_gran, stats_sub, stats_ns, c, groups, tp);
+  LM2A_REQUIRE(c % 8 == 0 && vpr > 0 && (c / groups) % 8 == 0,
+               "gn_apply: c=%d / channels per group must be positive multiples of 8", c);
   LM2A_REQUIRE(x_ld % 8 == 0 && y_ld % 8 == 0 && x_ld >= c && y_ld >= c,
                "gn_apply: ld must be a multiple of 8 and >= c");
-  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
-               "gn_apply: slabs must be 16-byte aligned");
+  LM2A_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                 reinterpret_cast<uintptr_t>(stats)) & 15) == 0,
+               "gn_apply: slabs and statistics must be 16-byte aligned");
   const int lanes = vpr < kGnThreads ? vpr : kGnThreads;
   const int slots_per_cta = kApplyVec * (kGnThreads / lanes);
   dim3 grid((tp + slots_per_cta - 1) / slots_per_cta, rows);
-  LM2A_CUDA_OK(launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0, reinterpret_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(x), x_ld, reinterpret_cast<__nv_bfloat16*>(y), y_ld,
-      reinterpret_cast<const float2*>(stats), stats_sub, stats_ns, stats_gran, gamma, beta, tp,
-      t_valid, c, groups, eps, apply_silu));
+  LM2A_CUDA_OK(launch_kernel(gn_apply_kernel, dim3(grid), dim3(kGnThreads), 0,
+                             reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const __nv_bfloat16*>(x), x_ld,
+                             reinterpret_cast<__nv_bfloat16*>(y), y_ld,
+                             reinterpret_cast<const long long*>(stats), stats_pitch, gamma, beta,
+                             tp, t_valid, c, groups, eps, apply_silu));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -296,13 +281,11 @@ extern "C" int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void
   const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (cache_bytes <= 200 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};
+    if (first_use_on_device(configured))
       LM2A_CUDA_OK(cudaFuncSetAttribute(gn_silu_kernel<true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         200 * 1024));
-      configured = true;
-    }
     LM2A_CUDA_OK(launch_kernel(gn_silu_kernel<true>, dim3(grid), dim3(kGnThreads), cache_bytes, st, 
         xp, x_ld, yp, y_ld, gamma, beta, tp, t_valid, cg, eps, apply_silu));
   } else {

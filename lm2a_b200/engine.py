@@ -47,7 +47,10 @@ class Geometry:
 
 # ------------------------------------------------------------------------ weight packing
 def _f64(p):
-    return p.detach().to(torch.float64)
+    """Parameters are folded on the HOST in fp64 (exact algebra, a few seconds once per
+    checkpoint at production width) and only the packed bf16 / fp32 operands go to the GPU: no
+    library kernel runs on the device on behalf of the weight pack."""
+    return p.detach().to("cpu", torch.float64)
 
 
 def _conv_w(w, cin_pad=None):
@@ -72,23 +75,15 @@ def _finish(w, b, dev):
 
 
 def _gn(gn, dev):
+    if gn.num_channels % gn.num_groups != 0 or (gn.num_channels // gn.num_groups) % 8 != 0:
+        raise RuntimeError(f"GroupNorm over {gn.num_channels} channels in {gn.num_groups} groups: "
+                           "channels per group must be a multiple of 8 on the sm_100a path")
     return (gn.weight.detach().to(dev, torch.float32).contiguous(),
             gn.bias.detach().to(dev, torch.float32).contiguous(), gn.num_groups, float(gn.eps))
 
 
 class PackedBlock:
     pass
-
-
-def _stats_gran(c, groups):
-    """Channel granularity of the partial GroupNorm sums of a slab whose consumer normalises
-    `c` channels in `groups` groups (8, 16 or 32 channels per sub-block)."""
-    cg = c // groups
-    for g in (32, 16, 8):
-        if cg % g == 0:
-            return g
-    raise RuntimeError(f"GroupNorm over {c} channels in {groups} groups: channels per group "
-                       "must be a multiple of 8 on the sm_100a path")
 
 
 def _check_channels(c, what):
@@ -233,6 +228,8 @@ class PackedModel:
         self.attn_blocks = [b for blocks, _, _ in self.downs for b in blocks if b.attn]
         self.attn_blocks += [b for b in self.mid if b.attn]
         self.attn_blocks += [b for _, _, blocks in self.ups for b in blocks if b.attn]
+        gns = [m for m in model.modules() if isinstance(m, torch.nn.GroupNorm)]
+        self.n_groupnorms, self.max_groups = len(gns), max(m.num_groups for m in gns)
 
 
 def _convT_w(w):
@@ -308,6 +305,8 @@ class PackedLegacy:
                                          dev)
         self.attn_blocks = ([b for b, _, _ in self.downs] + [self.mid]
                             + [b for _, _, _, b in self.ups])
+        gns = [m for m in model.modules() if isinstance(m, torch.nn.GroupNorm)]
+        self.n_groupnorms, self.max_groups = len(gns), max(m.num_groups for m in gns)
 
 
 # ------------------------------------------------------------------------------ the plan
@@ -317,7 +316,7 @@ class UNetPlan:
     (CFG: copies=2, rows = 2B, row k*B+b reads clip b)."""
 
     def __init__(self, pm, rows, t, lk, nslots, copies, use_cond, dev, uniform_t=False,
-                 uncond_rows=0, fuse_gn=True):
+                 uncond_rows=0):
         self.pm, self.rows, self.t, self.lk, self.nslots = pm, rows, t, lk, nslots
         # uniform_t: every clip-row is at the same timestep (sampling) -> one FiLM table row
         self.uniform_t = uniform_t
@@ -343,8 +342,12 @@ class UNetPlan:
         # scratch slabs shared by all blocks (sized for the largest level)
         cmax = max(g.M[lvl] * pm.scratch_width(lvl) for lvl in range(n_down + 1))
         flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
-        self._norm, self._h1, self._norm2, self._q, self._o, self._xup = (
-            flat(), flat(), flat(), flat(), flat(), flat())
+        self._h1, self._q, self._o, self._xup = flat(), flat(), flat(), flat()
+        self._flat = flat
+        self._norm = None   # only for clips too short for the conv's operand transform
+        # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
+        # kernel (ingest_x) clears; the epilogues accumulate exact integer sums into it
+        self.arena = ops.StatsArena(dev, (2 * pm.n_groupnorms + 16) * rows * pm.max_groups * 2)
         self._pp = [flat(), flat()]  # block outputs ping-pong
         self.x_slab = z(g.M[0], pm.in_pad)
         self.cat = [z(g.M[lvl], pm.cat_width(lvl)) for lvl in range(n_down)]
@@ -378,11 +381,12 @@ class UNetPlan:
         self.ct_ops = []
         self.kv_ops = []
         self.use_side_stream = True
-        self.fuse_gn = fuse_gn and os.environ.get("LM2A_FUSE_GN", "1") != "0"
         self._side = None
         self._side_op = self._side_pending = self._partial_rows = False
+        self._stats_pool = {}
         for mode in ((False, True) if use_cond else (False,)):
             self._building_ct = mode
+            self._stats_seq = []
             self.kv_ops = []
             self._attn_i = 0
             self._shared_rows = 0
@@ -422,13 +426,39 @@ class UNetPlan:
         (valid slots x real output channels x K, no padding counted)."""
         ntaps = {TAPS_K1: 1, TAPS_K3: 3, TAPS_K4S2: 4}
         k_total = k.pop("k_real", None) or sum(ntaps[s.taps] * s.cin for s in segs)
-        meta = {"kind": "conv_gemm", "flops": 2 * (m // tp) * t_valid * n_valid * k_total,
-                "m": m, "n": n_valid, "k": k_total}
+        executed = 2 * (m // tp) * t_valid * n_valid * k_total
+        flops = min(executed, k.pop("flops_alg", None) or executed)
+        meta = {"kind": "conv_gemm", "flops": flops, "flops_executed": executed,
+                "m": m, "n": n_valid, "k": k_total, "in_gn": k.get("in_gn") is not None}
         self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
                   meta=meta)
 
     def _stats(self, rows, lvl, c, groups):
-        return ops.Stats(rows, self.geo.Tp[lvl], c, _stats_gran(c, groups), self.dev)
+        """Statistics buffer of a [rows, Tp_lvl, c] slab whose consumer normalises it in `groups`
+        groups. Both launch lists (full / constant lyrics) are built over the same buffers, so
+        the n-th request of either build returns the same object."""
+        key = len(self._stats_seq)
+        self._stats_seq.append(key)
+        if key not in self._stats_pool:
+            self._stats_pool[key] = ops.Stats(rows, c, groups, self.dev, arena=self.arena)
+        st = self._stats_pool[key]
+        assert (st.rows, st.c, st.groups) == (rows, c, groups)
+        return st
+
+    def _gn_operand(self, x, x_ld, x_off, x_st, gn, nr, tp, tv, c):
+        """Input of a conv that follows GroupNorm + SiLU: (slab, ld, element offset, in_gn). The
+        normalisation runs inside the conv (operand transform); clips too short for it go
+        through a stand-alone gn_apply into a scratch slab."""
+        gm, bt, groups, eps = gn
+        if ops.in_gn_supported(tp, groups):
+            return x, x_ld, x_off, (x_st, gm, bt, eps, True)
+        if self._norm is None:
+            self._norm = [self._flat(), self._flat()]
+        self._norm_i = getattr(self, "_norm_i", 0) ^ 1
+        norm = self._view(self._norm[self._norm_i], nr * tp, c)
+        self._add(ops.gn_apply, x, x_ld, norm, c, x_st, gm, bt, nr, tp, tv, c, groups, eps, True,
+                  x_off, 0, meta={"kind": "gn_apply", "flops": 0})
+        return norm, c, 0, None
 
     def _resblock(self, p, lvl, xin, xin_ld, xin_off, xin_st, out, out_ld, out_off, out_st, kv):
         """xin/out: (tensor, ld, channel offset, Stats) views of slabs at level `lvl`; the block
@@ -499,43 +529,31 @@ class UNetPlan:
         xo = r0 * tp * xin_ld + xin_off      # element offsets of the row range inside the slabs
         oo = r0 * tp * out_ld + out_off
         cin, cout = p.cin, p.cout
-        norm = self._view(self._norm, m, cin)
+        assert xin_off == 0, "a ResBlock input starts at channel 0 of its slab"
         h1 = self._view(self._h1, m, cout)
-        norm2 = self._view(self._norm2, m, cout)
-        gm, bt, groups, eps = p.gn1
-        self._add(ops.gn_apply, xin, xin_ld, norm, cin, xin_st.view(r0, xin_off), gm, bt, nr, tp,
-                  tv, cin, groups, eps, True, xo, 0, meta={"kind": "gn_apply", "flops": 0})
-        gm, bt, groups, eps = p.gn2
-        h1_st = self._stats(nr, lvl, cout, groups)
-        # gn2 + SiLU fused into conv1: the tiles stay in TMEM across a grid barrier and are
-        # normalised from there (no h1 round trip, no separate launch). Needs one FiLM row for
-        # all clips (sampling), >= 32-channel groups and an output that fits one wave's TMEM.
-        n_pad1 = p.w1.shape[0]
-        fuse = (self.fuse_gn and self.uniform_t and (cout // groups) % 32 == 0 and tp >= 32
-                and h1_st.gran == 32 and ops.conv_gn_fusable(m, n_pad1))
-        if fuse:
-            barrier = torch.zeros(2, dtype=torch.int32, device=self.dev)
-            self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, None, cout,
-                       film=self.film, film_col=p.film_col, film_shift_off=cout,
-                       film_bcast=True, film_row=r0, stats=h1_st,
-                       gn=(gm, bt, groups, eps, norm2, cout, barrier))
-        else:
-            self._conv([Seg(norm, cin, cin, TAPS_K3, m)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
-                       film=self.film, film_col=p.film_col, film_shift_off=cout,
-                       film_bcast=self.uniform_t, film_row=r0, stats=h1_st)
-            self._add(ops.gn_apply, h1, cout, norm2, cout, h1_st, gm, bt, nr, tp, tv, cout, groups,
-                      eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
+        # conv1 reads x through gn1 + SiLU (operand transform), FiLM in its epilogue, and emits
+        # the exact sums gn2 needs; conv2 (or the composed conv2 . Q projection) reads h1 through
+        # gn2 + SiLU the same way: no normalised tensor is ever written
+        a, a_ld, a_off, in_gn = self._gn_operand(xin, xin_ld, xo, xin_st.view(r0, 0), p.gn1, nr,
+                                                 tp, tv, cin)
+        h1_st = self._stats(nr, lvl, cout, p.gn2[2])
+        self._conv([Seg(a, a_ld, cin, TAPS_K3, m, a_off)], p.w1, p.b1, cout, m, tp, tv, h1, cout,
+                   film=self.film, film_col=p.film_col, film_shift_off=cout,
+                   film_bcast=self.uniform_t, film_row=r0, stats=h1_st, in_gn=in_gn)
+        n2, n2_ld, n2_off, in_gn2 = self._gn_operand(h1, cout, 0, h1_st, p.gn2, nr, tp, tv, cout)
+        main = [Seg(n2, n2_ld, cout, TAPS_K3, m, n2_off)]
         skip_seg = [Seg(xin, xin_ld, cin, TAPS_K1, m, xo)] if p.has_skip else []
         res = {} if p.has_skip else dict(residual=xin, res_ld=xin_ld, res_chan_off=xo)
         ost = out_st.view(r0, out_off)
         if not (p.attn and self.use_cond):
-            self._conv([Seg(norm2, cout, cout, TAPS_K3, m)] + skip_seg, p.w2s, p.b2s, cout, m,
-                       tp, tv, out, out_ld, out_chan_off=oo, stats=ost, **res)
+            self._conv(main + skip_seg, p.w2s, p.b2s, cout, m, tp, tv, out, out_ld,
+                       out_chan_off=oo, stats=ost, in_gn=in_gn2, **res)
             return
         e = p.e
         (kv_m, kv_t), (vt_m, vt_t) = kv
         ai = self._attn_i
         self._attn_i += 1
+        rows_valid = nr * tv
         if self._building_ct:
             # motion stream only; the lyrics stream's contribution (Wf2 Wo_t) v_t is a per-clip
             # vector: a per-row epilogue shift of the output GEMM, read from the block's table
@@ -543,7 +561,9 @@ class UNetPlan:
                 self._make_ct_table(ai, p, kv_t)
             q = self._view(self._q, m, e)
             o = self._view(self._o, m, e)
-            self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2_m, p.bq2_m, e, m, tp, tv, q, e)
+            # algorithmic work of conv2 (6 T C^2) + one Q projection (2 T C^2) exceeds what the
+            # composed GEMM executes (6 T C^2): credit the executed FLOPs
+            self._conv(main, p.wq2_m, p.bq2_m, e, m, tp, tv, q, e, in_gn=in_gn2)
             self._add(ops.cross_attn, q, e, o, e, ops._ptr(kv_m), ops._ptr(vt_m),
                       ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad,
                       ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads, 1,
@@ -554,7 +574,10 @@ class UNetPlan:
             return
         q = self._view(self._q, m, 2 * e)
         o = self._view(self._o, m, 2 * e)
-        self._conv([Seg(norm2, cout, cout, TAPS_K3, m)], p.wq2, p.bq2, 2 * e, m, tp, tv, q, 2 * e)
+        # the composed conv2 . [Q_motion | Q_lyrics] GEMM executes 2 * 2E * 3C MACs per slot where
+        # the reference's conv2 followed by two Q projections needs 3C * C + 2E * C: credit that
+        self._conv(main, p.wq2, p.bq2, 2 * e, m, tp, tv, q, 2 * e, in_gn=in_gn2,
+                   flops_alg=2 * rows_valid * (3 * cout * cout + 2 * e * cout))
         self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
                   ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad, ops._ptr(self.kv_slot, r0),
                   self.nslots, nr, tp, tv, self.lk, e, p.heads,
@@ -595,7 +618,7 @@ class UNetPlan:
         self._side_op = False
         self._hold_join = True
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
-                  self.t, g.Tp[0], pm.in_pad)
+                  self.t, g.Tp[0], pm.in_pad, self.arena)
         cur = self._view(self._pp[0], g.M[0], pm.base)
         cur_st = self._stats(rows, 0, pm.base, 8)
         # CFG copies are identical up to the first (attention) block: input_proj runs on the cond
@@ -612,13 +635,8 @@ class UNetPlan:
         self._hold_join, self._force_join = False, True
         # concat slab of level l: [transposed-conv output (dims[l]) | skip (c_l)], normalised as
         # a whole by the decoder block. The transposed conv writes it as two launches (even / odd
-        # slots) in the geometry of level l+1, so its statistics need two slice ranges.
-        self.cat_st = []
-        for lvl in range(n_down):
-            ns_lo = g.Tp[lvl + 1] // 32 + 2
-            wcat = pm.cat_width(lvl)
-            self.cat_st.append(ops.Stats(rows, g.Tp[lvl], wcat, _stats_gran(wcat, 8), self.dev,
-                                         ns=max(g.Tp[lvl] // 32 + 2, 2 * ns_lo)))
+        # slots) in the geometry of level l+1; both add into the same exact sums.
+        self.cat_st = [self._stats(rows, lvl, pm.cat_width(lvl), 8) for lvl in range(n_down)]
         for lvl, (p, wd, bd) in enumerate(pm.downs):
             dim, wcat = pm.dims[lvl], pm.cat_width(lvl)
             self._resblock(p, lvl, cur, cur_c, 0, cur_st, self.cat[lvl], wcat, dim,
@@ -646,8 +664,7 @@ class UNetPlan:
             for half, w in enumerate((we, wo)):
                 self._conv([Seg(cur, cur_c, cur_c, TAPS_K3, g.M[lo])], w, bu, dim, g.M[lo],
                            g.Tp[lo], g.T[lo], self.cat[lvl], 2 * wcat, out_chan_off=half * wcat,
-                           k_real=2 * cur_c,
-                           stats=self.cat_st[lvl].view(0, 0, half * (g.Tp[lo] // 32 + 2)))
+                           k_real=2 * cur_c, stats=self.cat_st[lvl].view(0, 0))
             out = self._view(self._pp[pp], g.M[lvl], wcat)
             pp ^= 1
             self._resblock(p, lvl, self.cat[lvl], wcat, 0, self.cat_st[lvl], out, wcat, 0,
@@ -675,7 +692,7 @@ class UNetPlan:
         self._hold_join = True
         # x -> bf16 slab (CFG row duplication happens here), in_proj
         self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
-                  self.t, g.Tp[0], pm.in_pad)
+                  self.t, g.Tp[0], pm.in_pad, self.arena)
         groups_of = lambda blk_gn: blk_gn[2]  # noqa: E731
         cur = self._view(self._pp[0], g.M[0], pm.base)
         first = pm.downs[0][0][0]
@@ -767,12 +784,11 @@ class UNetPlan:
                 cur, cur_ld, cur_c, cur_st = out, p.cout, p.cout, out_st
 
         # out_proj: GN + SiLU + 1x1 conv, written as fp32 [rows, in_dim, T]
-        gm, bt, groups, eps = pm.gn_out
-        norm = self._view(self._norm, g.M[0], cur_c)
-        self._add(ops.gn_apply, cur, cur_c, norm, cur_c, cur_st, gm, bt, rows, g.Tp[0], g.T[0],
-                  cur_c, groups, eps, True, 0, 0, meta={"kind": "gn_apply", "flops": 0})
-        self._conv([Seg(norm, cur_c, cur_c, TAPS_K1, g.M[0])], pm.w_out, pm.b_out, pm.in_dim,
-                   g.M[0], g.Tp[0], g.T[0], self.eps, 0, out_mode=OUT_F32_NCT, block_n=128)
+        a, a_ld, a_off, in_gn = self._gn_operand(cur, cur_c, 0, cur_st, pm.gn_out, rows, g.Tp[0],
+                                                 g.T[0], cur_c)
+        self._conv([Seg(a, a_ld, cur_c, TAPS_K1, g.M[0], a_off)], pm.w_out, pm.b_out, pm.in_dim,
+                   g.M[0], g.Tp[0], g.T[0], self.eps, 0, out_mode=OUT_F32_NCT, block_n=128,
+                   in_gn=in_gn)
 
     # -- execution --------------------------------------------------------------------
     def set_conditions(self, motion_f, text_f, kv_slot):
@@ -902,8 +918,13 @@ class UNetPlan:
         return picked
 
     def flops(self):
-        """Algorithmic FLOPs of one forward over all rows (K/V hoisted, out_proj.fuse folded)."""
+        """Algorithmic FLOPs of one forward over all rows (K/V hoisted, out_proj.fuse folded):
+        what the roofline credits."""
         return sum(meta["flops"] for _, _, meta in self.ops)
+
+    def flops_executed(self):
+        """FLOPs the launches execute on valid slots (>= flops(): the composed conv2 . Q GEMM)."""
+        return sum(meta.get("flops_executed", meta["flops"]) for _, _, meta in self.ops)
 
     def profile(self, iters=10):
         """Per-launch device time for bench.py's roofline line and profiles/. Each launch is
@@ -915,21 +936,33 @@ class UNetPlan:
         return [(meta["kind"], meta, self._time_op(fn, args, iters)) for fn, args, meta in self.ops]
 
 
+def params_fingerprint(model):
+    """(data_ptr, version) of every parameter: changes whenever a parameter is re-allocated or
+    written in place through the tensor itself (load_state_dict, optimizer steps, EMA copy_,
+    the fused Adan step, .to()). Writes through `.data` / raw pointers do not bump the version
+    counter: call `model.refresh()` after those."""
+    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
 class UNetEngine:
     def __init__(self, model):
         p = next(model.parameters())
         ops.require_device(p)
         self.dev = p.device
+        self.fingerprint = params_fingerprint(model)
         legacy = hasattr(model, "input_proj")  # models/unet1d.py names vs unet1d_ultimate.py
-        self.pm = PackedLegacy(model, self.dev) if legacy else PackedModel(model, self.dev)
+        with torch.cuda.device(self.dev):
+            self.pm = PackedLegacy(model, self.dev) if legacy else PackedModel(model, self.dev)
         self.plans = {}
         self._cond_key = None
+        self._cond_ref = None
 
     def plan(self, rows, t, lk, nslots, copies=1, use_cond=True, uniform_t=False, uncond_rows=0):
         key = (rows, t, lk, nslots, copies, use_cond, uniform_t, uncond_rows)
         if key not in self.plans:
-            self.plans[key] = UNetPlan(self.pm, rows, t, lk, nslots, copies, use_cond, self.dev,
-                                       uniform_t, uncond_rows)
+            with torch.cuda.device(self.dev):
+                self.plans[key] = UNetPlan(self.pm, rows, t, lk, nslots, copies, use_cond,
+                                           self.dev, uniform_t, uncond_rows)
         return self.plans[key]
 
     def forward(self, x, t, motion_f=None, text_f=None):
@@ -943,15 +976,21 @@ class UNetEngine:
                          or text_f.shape[1] != lk):
             raise RuntimeError("motion_f / text_f must be (B, Lk, cond_dim) with matching B, Lk")
         plan = self.plan(b, tlen, lk, b if use_cond else 0, 1, use_cond)
-        if use_cond:
-            key = (id(plan), motion_f.data_ptr(), motion_f._version, text_f.data_ptr(),
-                   text_f._version)
-            if key != self._cond_key:
-                plan.set_conditions(motion_f, text_f,
-                                    torch.arange(b, device=self.dev, dtype=torch.int32))
-                self._cond_key = key
-        if not torch.is_tensor(t):
-            t = torch.full((b,), int(t), device=self.dev, dtype=torch.int64)
-        plan.x_in.copy_(x)
-        plan.t_in.copy_(t.reshape(-1).expand(b) if t.numel() == 1 else t)
-        return plan.run().clone()
+        with torch.cuda.device(self.dev):   # launches go to THIS device's current stream
+            if use_cond:
+                # The K/V caches are step-invariant: rebuilt only when the conditions change.
+                # The key holds the tensors themselves (strong references), so their storage
+                # cannot be recycled for another clip's conditions while the key is alive.
+                key = (id(plan), motion_f.data_ptr(), motion_f._version, text_f.data_ptr(),
+                       text_f._version)
+                same = (key == self._cond_key and self._cond_ref is not None
+                        and self._cond_ref[0] is motion_f and self._cond_ref[1] is text_f)
+                if not same:
+                    plan.set_conditions(motion_f, text_f,
+                                        torch.arange(b, device=self.dev, dtype=torch.int32))
+                    self._cond_key, self._cond_ref = key, (motion_f, text_f)
+            if not torch.is_tensor(t):
+                t = torch.full((b,), int(t), device=self.dev, dtype=torch.int64)
+            plan.x_in.copy_(x)
+            plan.t_in.copy_(t.reshape(-1).expand(b) if t.numel() == 1 else t)
+            return plan.run().clone()

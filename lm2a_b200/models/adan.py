@@ -100,6 +100,12 @@ class Adan(Optimizer):
                     ctypes.c_void_p(raw.data_ptr()), ctypes.c_void_p(ct.data_ptr()),
                     ctypes.c_void_p(ci.data_ptr()), ct.numel(), CHUNK, 1 if step0 == 0 else 0,
                     scal), "lm2a_adan_step")
-                for _, st, _ in items:
+                for p, st, shadow in items:
                     st["step"] = step
+                    # the kernel wrote the parameter (and its EMA shadow) through raw pointers:
+                    # bump the version counters so that caches keyed on them (packed GEMM
+                    # operands of UNet1D_ultimate / CondProjection) see the update
+                    torch._C._increment_version(p)
+                    if shadow is not None:
+                        torch._C._increment_version(shadow)
         return loss

@@ -244,6 +244,10 @@ class CfgSampler:
             self.graph = self._graphs[key]
             return
         keep_x = p.x_in.clone()
+        # the warm-up step and the capture below draw from the CUDA generator: put its state
+        # back afterwards, so the trajectory consumes the same noise stream whether or not this
+        # shape has been sampled before (x_T first, then one draw per step)
+        rng_state = torch.cuda.get_rng_state(self.dev)
         if os.environ.get("LM2A_AUTOTUNE", "0") == "1":
             # measured tile shape per GEMM launch instead of the wave model: opt-in — it raises
             # the isolated conv throughput (59.7 -> 61.4 % of peak) but not the in-graph step
@@ -262,13 +266,23 @@ class CfgSampler:
             self._step(draw)
         p.x_in.copy_(keep_x)
         self.ticket.zero_()
+        torch.cuda.synchronize(self.dev)
+        torch.cuda.set_rng_state(rng_state, self.dev)
         self._graphs[key] = self.graph = g
 
     @torch.no_grad()
     def run(self, motion_f, text_f, guidance_weight=1.0, x_init=None, noises=None,
             use_graph=True, report=None):
         """motion_f / text_f None: the condition slabs were already filled in place
-        (cond_slabs + CondProjection.project_raw); only the K/V caches are (re)built."""
+        (cond_slabs + CondProjection.project_raw); only the K/V caches are (re)built.
+        The captured step draws its noise at every replay, also at t == 0 where the update
+        masks it (GaussianDiffusion.p_sample of the reference does the same, diffusion.py:95;
+        the inline loop of sample.py:203-204 does not): one extra generator advance per
+        trajectory relative to sample.py."""
+        with torch.cuda.device(self.dev):
+            return self._run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report)
+
+    def _run(self, motion_f, text_f, guidance_weight, x_init, noises, use_graph, report):
         d, p = self.d, self.plan
         steps = d.T if self.ddim is None else len(self.taus)
         self.gw = float(guidance_weight)

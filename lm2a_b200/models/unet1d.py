@@ -76,10 +76,16 @@ class UNet1D(nn.Module):
         self._engine = None
 
     def engine(self):
-        from ..engine import UNetEngine
+        """See UNet1D_ultimate.engine: re-packed when a parameter's (data_ptr, version) changes."""
+        from ..engine import UNetEngine, params_fingerprint
+        if self._engine is not None and self._engine.fingerprint != params_fingerprint(self):
+            self._engine = None
         if self._engine is None:
             self._engine = UNetEngine(self)
         return self._engine
+
+    def refresh(self):
+        self._engine = None
 
     def _apply(self, fn, *a, **k):
         self._engine = None

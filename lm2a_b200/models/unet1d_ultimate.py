@@ -155,10 +155,20 @@ class UNet1D_ultimate(nn.Module):
 
     # -- engine plumbing ---------------------------------------------------------------
     def engine(self):
-        from ..engine import UNetEngine
+        """Packed weights + launch plans. Rebuilt whenever a parameter was re-allocated or
+        written in place (engine.params_fingerprint: data_ptr + version counter of every
+        parameter — load_state_dict, .to(), optimizer steps incl. the fused Adan, EMA copy_).
+        Writes through `.data` or raw pointers are invisible to it: call refresh() after."""
+        from ..engine import UNetEngine, params_fingerprint
+        if self._engine is not None and self._engine.fingerprint != params_fingerprint(self):
+            self._engine = None
         if self._engine is None:
             self._engine = UNetEngine(self)
         return self._engine
+
+    def refresh(self):
+        """Drop the packed weights (they are re-packed from the parameters on the next use)."""
+        self._engine = None
 
     def _apply(self, fn, *a, **k):
         self._engine = None  # device / dtype moved: packed weights are stale

@@ -17,6 +17,12 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def on_device_of(t):
+    """Context manager: launches go to the current stream of the tensor's device (a process may
+    drive several GPUs)."""
+    return torch.cuda.device(t.device)
+
+
 def _ptr(t, elem_offset=0):
     if t is None:
         return None
@@ -37,28 +43,75 @@ def reset_launch_count():
     _lib.load().lm2a_reset_launch_count()
 
 
+class StatsArena:
+    """One zero-initialised int64 region holding every GroupNorm statistics buffer of a launch
+    plan; lm2a_ingest_x (the first kernel of a step) clears the used part, the epilogues
+    accumulate into it. Fixed capacity: addresses are handed out while the plan is built."""
+
+    def __init__(self, dev, capacity_words):
+        self.dev, self.words = dev, 0
+        self.buf = torch.zeros(max(2, (capacity_words + 1) // 2 * 2), dtype=torch.int64,
+                               device=dev)
+
+    def reserve(self, words):
+        off = self.words
+        self.words += (words + 1) // 2 * 2      # keep every buffer 16-byte aligned
+        if self.words > self.buf.numel():
+            raise RuntimeError("GroupNorm statistics arena exhausted")
+        return off
+
+    def tensor(self):
+        return self.buf
+
+    def used(self):
+        return self.buf[: self.words]
+
+
 class Stats:
-    """Partial GroupNorm statistics of a slab [rows, tp, c]: float2 [rows, c/gran, ns] written by
-    the producing kernel's epilogue, read by gn_apply. `view(row0, chan0)` addresses a
-    row / channel sub-range (a launch over part of the rows, or one half of a concat slab)."""
+    """Exact GroupNorm sums of a slab [rows, tp, c] normalised in `groups` groups: int64
+    [rows, groups, 2] = {sum * 2^24, sum of squares * 2^20}, accumulated by the producing
+    kernel's epilogue (integer adds: independent of tile shape and batch position), read by the
+    consuming conv's operand transform or by gn_apply. `view(row0, chan0)` addresses a row /
+    channel sub-range (a launch over part of the rows, or one half of a concat slab). The
+    buffer must be zero before the producers of a step run: standalone objects are zeroed at
+    construction (one use), plan-owned ones live in a StatsArena that ingest_x clears."""
 
-    def __init__(self, rows, tp, c, gran, dev, buf=None, row0=0, chan0=0, slice0=0, ns=None):
-        self.rows, self.tp, self.c, self.gran = rows, tp, c, gran
-        self.sub = c // gran
-        # `ns` > tp/32 + 2: room for a second producer of the same (row, channels) whose slices
-        # start at `slice0` (the odd-slot launch of a transposed conv)
-        self.ns = ns if ns is not None else tp // 32 + 2
-        self.buf = buf if buf is not None else torch.zeros(rows * self.sub * self.ns, 2,
-                                                           dtype=torch.float32, device=dev)
-        self.row0, self.chan0, self.slice0 = row0, chan0, slice0
+    def __init__(self, rows, c, groups, dev, arena=None, _base=None, row0=0, chan0=0):
+        self.rows, self.c, self.groups = rows, c, groups
+        self.cg = c // groups
+        assert c % groups == 0 and self.cg % 8 == 0
+        self.row0, self.chan0 = row0, chan0
+        if _base is not None:
+            self._base = _base
+        elif arena is not None:
+            off = arena.reserve(rows * groups * 2)
+            self._base = (arena, off)
+        else:
+            self._base = (torch.zeros(rows * groups * 2, dtype=torch.int64, device=dev), 0)
 
-    def view(self, row0=0, chan0=0, slice0=0):
-        return Stats(self.rows, self.tp, self.c, self.gran, None, self.buf, self.row0 + row0,
-                     self.chan0 + chan0, self.slice0 + slice0, self.ns)
+    @property
+    def buf(self):
+        owner, off = self._base
+        t = owner.tensor() if isinstance(owner, StatsArena) else owner
+        return t[off: off + self.rows * self.groups * 2]
+
+    def zero_(self):
+        self.buf.zero_()
+
+    def view(self, row0=0, chan0=0):
+        assert chan0 % 8 == 0
+        return Stats(self.rows, self.c, self.groups, None, None, self._base, self.row0 + row0,
+                     self.chan0 + chan0)
 
     def ptr(self):
-        off = (self.row0 * self.sub + self.chan0 // self.gran) * self.ns + self.slice0
-        return self.buf.data_ptr() + off * 8
+        """Address of clip-row row0's sums; the channel offset travels separately (stats_c0):
+        a producer whose channels start inside a group still adds into the right one."""
+        return self.buf.data_ptr() + self.row0 * self.groups * 2 * 8
+
+    def sums(self):
+        """fp64 [rows, groups, 2] = (sum, sum of squares) decoded from the fixed-point words."""
+        v = self.buf.view(self.rows, self.groups, 2).double()
+        return torch.stack([v[..., 0] / 2.0 ** 24, v[..., 1] / 2.0 ** 20], dim=-1)
 
 
 class Seg:
@@ -73,9 +126,11 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
                    res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0,
-                   gn=None):
+                   in_gn=None):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
-    alive by attaching them to the descriptor object."""
+    alive by attaching them to the descriptor object.
+    in_gn = (Stats view of segs[0]'s slab, gamma, beta, eps, silu): GroupNorm (+ SiLU) applied to
+    the first segment's operand tiles on the fly."""
     d = ConvDesc()
     for i, s in enumerate(segs):
         d.seg[i].x = s.slab.data_ptr() + s.chan_off * 2
@@ -98,26 +153,28 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
         d.residual = residual.data_ptr() + res_chan_off * 2
         d.res_ld = res_ld
     d.out_mode = out_mode
-    if out is not None:
-        d.out = out.data_ptr() + out_chan_off * out.element_size()
+    d.out = out.data_ptr() + out_chan_off * out.element_size()
     d.out_ld = out_ld
     d.block_n = block_n
     d.cta_group = cta_group
-    if stats is not None:  # Stats view: partial GroupNorm sums of the output
+    if stats is not None:  # Stats view: exact GroupNorm sums of the output
         d.stats = stats.ptr()
-        d.stats_sub, d.stats_ns, d.stats_gran = stats.sub, stats.ns, stats.gran
-    if gn is not None:  # (gamma, beta, groups, eps, gn_out slab, gn_out_ld, barrier words)
-        gamma, beta, groups, eps, gn_out, gn_out_ld, barrier = gn
-        d.gn_gamma, d.gn_beta = gamma.data_ptr(), beta.data_ptr()
-        d.gn_groups, d.gn_eps = groups, eps
-        d.gn_out, d.gn_out_ld = gn_out.data_ptr(), gn_out_ld
-        d.gn_barrier = barrier.data_ptr()
-    d._keep = (segs, w, bias, film, residual, out, stats, gn)
+        d.stats_pitch, d.stats_cg, d.stats_c0 = stats.groups, stats.cg, stats.chan0
+    if in_gn is not None:
+        st, gamma, beta, eps, silu = in_gn
+        assert st.c == segs[0].cin and st.chan0 == 0
+        d.in_gn_stats = st.ptr()
+        d.in_gn_gamma, d.in_gn_beta = gamma.data_ptr(), beta.data_ptr()
+        d.in_gn_pitch, d.in_gn_groups = st.groups, st.groups
+        d.in_gn_eps, d.in_gn_silu = eps, 1 if silu else 0
+    d._keep = (segs, w, bias, film, residual, out, stats, in_gn)
     return d
 
 
-def conv_gn_fusable(m, n_pad):
-    return bool(_lib.load().lm2a_conv_gn_fusable(m, n_pad))
+def in_gn_supported(tp, groups):
+    """Whether the conv's operand transform can normalise clips of `tp` slots in `groups`
+    groups (a 130-slot tile must touch at most 512 (clip-row, group) pairs)."""
+    return ((128 + 1) // tp + 2) * groups <= 512
 
 
 def conv1d(desc):
@@ -160,9 +217,12 @@ def film(s, w, b, out, rows, dim, cols):
                                      cols), "lm2a_film")
 
 
-def ingest_x(x, slab, batch, copies, c, t, tp, ld):
+def ingest_x(x, slab, batch, copies, c, t, tp, ld, zero=None):
+    """zero: optional StatsArena (or int64 tensor) cleared by the same launch."""
+    zt = zero.used() if isinstance(zero, StatsArena) else zero
+    zbytes = 0 if zt is None else zt.numel() * zt.element_size()
     _lib.check(_lib.load().lm2a_ingest_x(_stream(), _ptr(x), _ptr(slab), batch, copies, c, t, tp,
-                                         ld), "lm2a_ingest_x")
+                                         ld, _ptr(zt), zbytes), "lm2a_ingest_x")
 
 
 def ingest_seq(x, slab, rows, t, c, tp, ld):
@@ -208,13 +268,14 @@ def bias_add(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c, stats=
     _lib.check(_lib.load().lm2a_bias_add_bf16(
         _stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld, _ptr(bias), slots, tp, t_valid, c,
         ctypes.c_void_p(stats.ptr()) if stats is not None else None,
-        stats.sub if stats is not None else 0, stats.ns if stats is not None else 0,
-        stats.gran if stats is not None else 0), "lm2a_bias_add_bf16")
+        stats.groups if stats is not None else 0, stats.cg if stats is not None else 0,
+        stats.chan0 if stats is not None else 0), "lm2a_bias_add_bf16")
 
 
 def gn_apply(x, x_ld, y, y_ld, stats, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-5,
              silu=True, x_chan_off=0, y_chan_off=0):
+    assert stats.cg * groups == c and stats.chan0 == 0
     _lib.check(_lib.load().lm2a_gn_apply_bf16(
         _stream(), _ptr(x, x_chan_off), x_ld, _ptr(y, y_chan_off), y_ld,
-        ctypes.c_void_p(stats.ptr()), stats.sub, stats.ns, stats.gran, _ptr(gamma), _ptr(beta),
+        ctypes.c_void_p(stats.ptr()), stats.groups, _ptr(gamma), _ptr(beta),
         rows, tp, t_valid, c, groups, eps, 1 if silu else 0), "lm2a_gn_apply_bf16")

@@ -18,3 +18,17 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture
+def record():
+    """record(name, **values): appends a JSON line to gpurun_out/test_metrics.jsonl (measured
+    distances of the parity tests, read back after a GPU run; a no-op without that directory)."""
+    import json
+
+    def _rec(name, **values):
+        d = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(d):
+            with open(os.path.join(d, "test_metrics.jsonl"), "a") as f:
+                f.write(json.dumps({"test": name, **values}) + "\n")
+    return _rec

@@ -31,8 +31,9 @@ def test_library_exports_every_declared_symbol():
 def test_conv_desc_struct_matches_header_layout():
     from lm2a_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSeg) == 32
-    assert ctypes.sizeof(_lib.ConvDesc) == 224
+    assert ctypes.sizeof(_lib.ConvDesc) == 216
     assert _lib.ConvDesc.out.offset == 136 and _lib.ConvDesc.m.offset == 80
+    assert _lib.ConvDesc.stats.offset == 152 and _lib.ConvDesc.in_gn_stats.offset == 176
 
 
 def test_state_dict_layout_matches_reference_inventory():
@@ -82,13 +83,26 @@ def test_geometry_and_plan():
     pm = PackedModel(net, torch.device("cpu"))
     plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
     kinds = [m["kind"] for _, _, m in plan.ops]
-    assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 31
+    # every GroupNorm + SiLU runs inside the conv that consumes it (operand transform): 31 of
+    # the 47 GEMM launches carry one, no stand-alone normalisation launch is left
+    assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 0
+    assert sum(1 for _, _, m in plan.ops if m.get("in_gn")) == 31
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
-    # K/V hoisted, out_proj.fuse folded, conv2 o q-proj composed (costs 1.35 GF of executed
-    # work, saves a launch per attention block): production net = 29.58 GFLOP per row-step
+    assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 62
+    # (clips too short for the operand transform would fall back to the stand-alone gn_apply
+    # pass; with <= 8 groups every clip length the geometry admits is long enough)
+    from lm2a_b200 import ops as _ops
+    assert _ops.in_gn_supported(3, 8) and not _ops.in_gn_supported(3, 32)
+    # K/V hoisted, out_proj.fuse folded; the composed conv2 o q-proj GEMM executes 29.58 GFLOP
+    # per row-step in total, of which 28.23 are the reference's algorithmic work (credited)
     big = PackedModel(UNet1D_ultimate(80, 256, (1, 2, 4), 128, 256, 2, 3, 8), torch.device("cpu"))
-    gf = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu")).flops() / 2 / 1e9
-    assert abs(gf - 29.58) < 0.02
+    bp = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu"))
+    assert abs(bp.flops() / 2 / 1e9 - 28.23) < 0.02
+    assert abs(sum(m.get("flops_executed", m["flops"]) for _, _, m in bp.ops) / 2 / 1e9 - 29.58) < 0.02
+    # production CFG step (B = 32, uncond shortcut, shared leading rows): 71 launches
+    cfgp = UNetPlan(big, 64, 516, 516, 33, 2, True, torch.device("cpu"), uniform_t=True,
+                    uncond_rows=32)
+    assert len(cfgp.ops) == 71 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
     with pytest.raises(RuntimeError, match="multiples of 64"):
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 

@@ -204,8 +204,8 @@ def test_gn_silu(ops, r, t, tp, c, groups):
 ])
 @pytest.mark.parametrize("cta_group", [1, 2])
 def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0, cta_group):
-    """conv epilogue emits partial GroupNorm sums; gn_apply consumes them: together they must
-    equal F.group_norm + SiLU of the conv output (unet1d_ultimate.py:136-147)."""
+    """conv epilogue accumulates the exact GroupNorm sums; gn_apply consumes them: together they
+    must equal F.group_norm + SiLU of the conv output (unet1d_ultimate.py:136-147)."""
     nr = r - r0
     x = rnd(r, cin, t, seed=50)
     w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=51)
@@ -214,9 +214,7 @@ def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0, cta_grou
     beta = 0.1 * rnd(cout, seed=54)
     xs = to_slab(x, tp)
     h = torch.zeros(r * tp, cout, dtype=BF16, device="cuda")
-    cg = cout // groups
-    gran = 32 if cg % 32 == 0 else (16 if cg % 16 == 0 else 8)
-    st = ops.Stats(r, tp, cout, gran, "cuda")
+    st = ops.Stats(r, cout, groups, "cuda")
     # launch over rows [r0, r): slabs and stats addressed through row-offset views
     d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, nr * tp, chan_off=r0 * tp * cin)],
                            pack_w(w), pad_bias(b, (cout + 127) // 128 * 128), cout, nr * tp, tp, t,
@@ -231,72 +229,128 @@ def test_conv_stats_feed_gn_apply(ops, r, t, tp, cin, cout, groups, r0, cta_grou
     ref = F.silu(F.group_norm(hf, groups, gamma, beta, 1e-5))
     assert_close(from_slab(y, r, tp, t, cout)[r0:], ref, 6e-3, "conv stats -> gn_apply")
     assert pads_are_zero(y[r0 * tp:], nr, tp, t)
-    # the statistics themselves: sum over slices == per-(row, group) sums of the conv output
-    sums = st.buf.view(r, cout // gran, st.ns, 2).sum(2)[r0:].view(nr, groups, -1, 2).sum(2)
-    ref1 = hf.reshape(nr, groups, -1).sum(-1)
-    ref2 = (hf.reshape(nr, groups, -1) ** 2).sum(-1)
+    # the statistics themselves: per-(row, group) sums of the conv output (fp32 values before
+    # the bf16 store; compared with the stored bf16 values)
+    sums = st.sums()[r0:]
+    assert bool((st.sums()[:r0] == 0).all()), "rows outside the launch must stay untouched"
+    ref1 = hf.double().reshape(nr, groups, -1).sum(-1)
+    ref2 = (hf.double().reshape(nr, groups, -1) ** 2).sum(-1)
     assert torch.allclose(sums[..., 0], ref1, rtol=2e-2, atol=0.5)
     assert torch.allclose(sums[..., 1], ref2, rtol=2e-2)
-    # determinism: a second run writes bit-identical statistics
+    # exactness: integer accumulation -> a second run (different atomic order) and any other
+    # tile shape give bit-identical sums
     before = st.buf.clone()
+    for bn, cg in ((128, 1), (128, 2)) + (((256, 1), (256, 2)) if cout % 256 == 0 else ()):
+        st.zero_()
+        d.block_n, d.cta_group = bn, cg
+        ops.conv1d(d)
+        torch.cuda.synchronize()
+        assert torch.equal(before, st.buf), f"stats differ for tile {bn} x cta_group {cg}"
+
+
+def _gn_input_case(ops, r, t, tp, cin, cout, groups, taps, r0, cta_group, block_n, skip_c=0,
+                   silu=True):
+    """y = conv(SiLU(GroupNorm(x))) [+ 1x1 skip conv of a raw second segment] with the
+    normalisation applied inside the conv (operand transform) vs torch, and vs the same conv
+    run on gn_apply's output (must be bit-identical: same arithmetic on the same operands)."""
+    nr = r - r0
+    k = 3 if taps == ops.TAPS_K3 else 1
+    x = rnd(r, cin, t, seed=80) * 1.3 + 0.2
+    w = rnd(cout, cin, k, scale=1 / math.sqrt(k * cin), seed=81)
+    b = rnd(cout, scale=0.3, seed=82)
+    gamma = 1 + 0.1 * rnd(cin, seed=83)
+    beta = 0.1 * rnd(cin, seed=84)
+    n_pad = (cout + 127) // 128 * 128
+    # x and its exact sums come from a producer kernel (bias_add with a zero bias)
+    xs = torch.zeros(r * tp, cin, dtype=BF16, device="cuda")
+    st = ops.Stats(r, cin, groups, "cuda")
+    ops.bias_add(to_slab(x, tp), cin, 0, xs, cin, 0, torch.zeros(cin, device="cuda"), r * tp, tp, t,
+                 cin, st)
+    segs = [ops.Seg(xs, cin, cin, taps, nr * tp, chan_off=r0 * tp * cin)]
+    wk = pack_w(w)
+    ref_extra = 0
+    if skip_c:
+        xsk = rnd(r, skip_c, t, seed=85)
+        wsk = rnd(cout, skip_c, 1, scale=1 / math.sqrt(skip_c), seed=86)
+        sks = to_slab(xsk, tp)
+        segs.append(ops.Seg(sks, skip_c, skip_c, ops.TAPS_K1, nr * tp, chan_off=r0 * tp * skip_c))
+        wk = torch.cat([wk, pack_w(wsk)], dim=1).contiguous()
+        ref_extra = F.conv1d(bf(xsk), bf(wsk))[r0:]
+    out = torch.full((r * tp, cout), 7.0, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc(segs, wk, pad_bias(b, n_pad), cout, nr * tp, tp, t, out, cout,
+                           out_chan_off=r0 * tp * cout, block_n=block_n, cta_group=cta_group,
+                           in_gn=(st.view(r0, 0), gamma, beta, 1e-5, silu))
     ops.conv1d(d)
     torch.cuda.synchronize()
-    assert torch.equal(before, st.buf)
+    xf = from_slab(xs, r, tp, t, cin)
+    n = F.group_norm(xf, groups, gamma, beta, 1e-5)
+    n = F.silu(n) if silu else n
+    ref = F.conv1d(bf(n), bf(w), b, padding=k // 2)[r0:] + ref_extra
+    got = from_slab(out, r, tp, t, cout)[r0:]
+    assert_close(got, ref, 8e-3, "conv with GroupNorm'd operand")
+    assert pads_are_zero(out[r0 * tp:], nr, tp, t)
+    assert bool((out[: r0 * tp] == 7.0).all()), "rows before the launch range were touched"
+    # reference path: stand-alone gn_apply -> plain conv
+    norm = torch.zeros(r * tp, cin, dtype=BF16, device="cuda")
+    ops.gn_apply(xs, cin, norm, cin, st, gamma, beta, r, tp, t, cin, groups, silu=silu)
+    segs2 = [ops.Seg(norm, cin, cin, taps, nr * tp, chan_off=r0 * tp * cin)] + segs[1:]
+    out2 = torch.full((r * tp, cout), 7.0, dtype=BF16, device="cuda")
+    d2 = ops.make_conv_desc(segs2, wk, pad_bias(b, n_pad), cout, nr * tp, tp, t, out2, cout,
+                            out_chan_off=r0 * tp * cout, block_n=block_n, cta_group=cta_group)
+    ops.conv1d(d2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "operand transform differs from gn_apply + conv"
 
 
 @pytest.mark.parametrize("block_n,cta_group", [(0, 0), (256, 1), (256, 2), (128, 1), (128, 2)])
-@pytest.mark.parametrize("r,t,tp,cin,cout,groups,film", [
-    (4, 516, 520, 256, 256, 8, True),      # level 0 shape, few tiles
-    (64, 516, 520, 256, 256, 8, True),     # production level 0 conv1: 260 tiles, two per CTA
-    (32, 64, 65, 1024, 1024, 8, True),     # production mid level: 128-channel groups
-    (5, 129, 130, 128, 512, 8, False),     # 64-channel groups, no FiLM, clip straddles warps
+@pytest.mark.parametrize("r,t,tp,cin,cout,groups,r0", [
+    (4, 516, 520, 256, 256, 8, 0),       # production level 0: tiles inside one clip
+    (64, 516, 520, 256, 256, 8, 32),     # production conv1, cond rows of a CFG batch
+    (32, 64, 65, 1024, 1024, 8, 0),      # mid level: every tile touches 3 clips, K = 3072
+    (5, 129, 130, 128, 512, 8, 2),       # 16-channel groups: four groups per 64-channel block
 ])
-def test_conv_fused_groupnorm(ops, r, t, tp, cin, cout, groups, film, block_n, cta_group):
-    """conv1 + FiLM + GroupNorm + SiLU in one launch (tiles resident in TMEM across a grid
-    barrier) == F.conv1d -> FiLM -> F.group_norm -> SiLU (unet1d_ultimate.py:138-147)."""
-    m, n_pad = r * tp, (cout + 127) // 128 * 128
-    if block_n:
-        tiles = -(-m // (128 * cta_group)) * (n_pad // block_n)
-        if -(-tiles // (148 // cta_group)) > 512 // block_n:
-            pytest.skip("shape does not fit the TMEM accumulators with this tile")
-    else:
-        assert ops.conv_gn_fusable(m, n_pad)
-    x = rnd(r, cin, t, seed=70)
-    w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=71)
-    b = rnd(cout, scale=0.3, seed=72)
-    gamma = 1 + 0.1 * rnd(cout, seed=73)
-    beta = 0.1 * rnd(cout, seed=74)
-    ftab = rnd(1, 2 * cout, scale=0.3, seed=75) if film else None
-    xs = to_slab(x, tp)
-    st = ops.Stats(r, tp, cout, 32, "cuda")
-    y = torch.full((m, cout), 3.0, dtype=BF16, device="cuda")
-    barrier = torch.zeros(2, dtype=torch.int32, device="cuda")
-    d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, m)], pack_w(w), pad_bias(b, n_pad), cout,
-                           m, tp, t, None, cout, film=ftab, film_col=0, film_shift_off=cout,
-                           film_bcast=True, stats=st, block_n=block_n, cta_group=cta_group,
-                           gn=(gamma, beta, groups, 1e-5, y, cout, barrier))
-    for _ in range(2):  # twice: the grid barrier must be reusable
-        ops.conv1d(d)
-    torch.cuda.synchronize()
-    h = F.conv1d(bf(x), bf(w), b, padding=1)
-    if film:
-        h = h * (1 + ftab[:, :cout, None]) + ftab[:, cout:, None]
-    ref = F.silu(F.group_norm(h, groups, gamma, beta, 1e-5))
-    assert_close(from_slab(y, r, tp, t, cout), ref, 6e-3, "conv + fused GroupNorm")
-    assert pads_are_zero(y, r, tp, t)
-    assert int(barrier[0]) == 0 and int(barrier[1]) == 2
+def test_conv_k3_groupnorm_operand(ops, r, t, tp, cin, cout, groups, r0, block_n, cta_group):
+    _gn_input_case(ops, r, t, tp, cin, cout, groups, ops.TAPS_K3, r0, cta_group, block_n)
 
 
-@pytest.mark.parametrize("r,t,tp,c,groups,gran", [(3, 129, 130, 512, 8, 32), (33, 64, 65, 1024, 8, 32),
-                                                  (5, 9, 10, 64, 8, 8), (4, 516, 520, 256, 8, 32)])
-def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_conv_groupnorm_operand_variants(ops, cta_group):
+    # k1 (out_proj: GroupNorm + SiLU + 1x1 conv), 80 real output channels would need the fp32
+    # epilogue: here a 128-channel slab
+    _gn_input_case(ops, 3, 100, 104, 256, 128, 8, ops.TAPS_K1, 0, cta_group, 128)
+    # conv2 + raw 1x1 skip segment (only the first segment is normalised)
+    _gn_input_case(ops, 3, 129, 130, 256, 128, 8, ops.TAPS_K3, 1, cta_group, 128, skip_c=128)
+    # very short clips: a tile touches 11 of them (12-slot pitch)
+    _gn_input_case(ops, 40, 11, 12, 64, 128, 8, ops.TAPS_K3, 0, cta_group, 128)
+    # GroupNorm without SiLU, legacy concat width 1536 (192-channel groups straddle 64-blocks)
+    _gn_input_case(ops, 2, 64, 65, 1536, 128, 8, ops.TAPS_K3, 0, cta_group, 128, silu=False)
+    # the largest supported channel count
+    _gn_input_case(ops, 2, 130, 132, 2048, 256, 8, ops.TAPS_K3, 0, cta_group, 256)
+
+
+def test_conv_groupnorm_operand_rejects_unsupported(ops):
+    x = torch.zeros(64 * 2, 64, dtype=BF16, device="cuda")
+    w = torch.zeros(128, 192, dtype=BF16, device="cuda")
+    b = torch.zeros(128, device="cuda")
+    g = torch.ones(64, device="cuda")
+    out = torch.zeros(128, 128, dtype=BF16, device="cuda")
+    st = ops.Stats(64, 64, 8, "cuda")
+    assert not ops.in_gn_supported(2, 8) and ops.in_gn_supported(65, 8)
+    with pytest.raises(RuntimeError, match="clip-rows"):   # 2-slot clips: 66 clips per tile
+        ops.conv1d(ops.make_conv_desc([ops.Seg(x, 64, 64, ops.TAPS_K3, 128)], w, b, 128, 128, 2, 1,
+                                      out, 128, in_gn=(st, g, g, 1e-5, True)))
+
+
+@pytest.mark.parametrize("r,t,tp,c,groups", [(3, 129, 130, 512, 8), (33, 64, 65, 1024, 8),
+                                             (5, 9, 10, 64, 8), (4, 516, 520, 256, 8)])
+def test_bias_add_stats(ops, r, t, tp, c, groups):
     x = rnd(r, c, t, seed=60)
     bias = rnd(c, scale=0.5, seed=61)
     gamma = 1 + 0.1 * rnd(c, seed=62)
     beta = 0.1 * rnd(c, seed=63)
     xs = to_slab(x, tp)
     y = torch.full((r * tp, c), 2.0, dtype=BF16, device="cuda")
-    st = ops.Stats(r, tp, c, gran, "cuda")
+    st = ops.Stats(r, c, groups, "cuda")
     ops.bias_add(xs, c, 0, y, c, 0, bias, r * tp, tp, t, c, st)
     z = torch.zeros_like(y)
     ops.gn_apply(y, c, z, c, st, gamma, beta, r, tp, t, c, groups)
@@ -306,6 +360,13 @@ def test_bias_add_stats(ops, r, t, tp, c, groups, gran):
     assert pads_are_zero(y, r, tp, t)
     ref = F.silu(F.group_norm(yf, groups, gamma, beta, 1e-5))
     assert_close(from_slab(z, r, tp, t, c), ref, 6e-3, "bias_add stats -> gn_apply")
+    # exact sums do not depend on where the rows sit: the same clips in another order
+    perm = torch.randperm(r, device="cuda")
+    st2 = ops.Stats(r, c, groups, "cuda")
+    xs2 = to_slab(x[perm], tp)
+    ops.bias_add(xs2, c, 0, torch.empty_like(y), c, 0, bias, r * tp, tp, t, c, st2)
+    torch.cuda.synchronize()
+    assert torch.equal(st2.buf.view(r, groups, 2), st.buf.view(r, groups, 2)[perm])
 
 
 @pytest.mark.parametrize("e,heads,t,lk,qgain", [
@@ -365,8 +426,7 @@ def test_gn_apply_channel_counts_off_the_cta_grid(ops, r, t, tp, c, groups):
     xs = to_slab(x, tp)
     bias = rnd(c, seed=61, scale=0.1)
     gamma, beta = 1.0 + 0.1 * rnd(c, seed=62), 0.1 * rnd(c, seed=63)
-    gran = 32 if (c // groups) % 32 == 0 else (16 if (c // groups) % 16 == 0 else 8)
-    st = ops.Stats(r, tp, c, gran, "cuda")
+    st = ops.Stats(r, c, groups, "cuda")
     y = torch.zeros_like(xs)
     z = torch.zeros_like(xs)
     ops.bias_add(xs, c, 0, y, c, 0, bias, r * tp, tp, t, c, st)
@@ -382,8 +442,8 @@ def test_gn_apply_channel_counts_off_the_cta_grid(ops, r, t, tp, c, groups):
                                                     (2, 16, 192, 64, 64)])
 def test_conv_transpose_k4s2_as_two_k3_gemms(ops, r, t_lo, cin, cout, skip):
     """ConvTranspose1d k4 s2 p1 (legacy models/unet1d.py:105) = an even-slot and an odd-slot k3
-    GEMM writing one row pair of the [M_lo, 2 * ld] view of the level-above concat slab; the
-    statistics of both launches land in disjoint slice ranges and feed gn_apply."""
+    GEMM writing one row pair of the [M_lo, 2 * ld] view of the level-above concat slab; both
+    launches add into the same exact sums, which feed gn_apply."""
     from lm2a_b200.engine import _convT_w, _finish
     tp_lo, tp_hi = t_lo + 1, 2 * (t_lo + 1)
     t_hi = 2 * t_lo + 1          # the skip is one frame longer (129 vs 2 * 64): F.pad path
@@ -397,12 +457,11 @@ def test_conv_transpose_k4s2_as_two_k3_gemms(ops, r, t_lo, cin, cout, skip):
     wo, _ = _finish(odd, b.double(), "cuda")
     cat = torch.zeros(r * tp_hi, ld, dtype=BF16, device="cuda")
     cat[:, cout:] = 1.0   # the skip half must survive untouched
-    ns_lo = tp_lo // 32 + 2
-    st = ops.Stats(r, tp_hi, ld, 8, "cuda", ns=max(tp_hi // 32 + 2, 2 * ns_lo))
+    st = ops.Stats(r, cout, 8, "cuda")
     for half, wt in enumerate((we, wo)):
         d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, r * tp_lo)], wt, bias, cout,
                                r * tp_lo, tp_lo, t_lo, cat, 2 * ld, out_chan_off=half * ld,
-                               stats=st.view(0, 0, half * ns_lo))
+                               stats=st)
         ops.conv1d(d)
     torch.cuda.synchronize()
     ref = F.conv_transpose1d(bf(x), bf(w), b, stride=2, padding=1)       # [r, cout, 2 * t_lo]
@@ -507,10 +566,12 @@ def test_ingest(ops):
     b, c, t, tp, ld = 3, 80, 77, 80, 128
     x = rnd(b, c, t, seed=41)
     slab = torch.full((2 * b * tp, ld), 9.0, dtype=BF16, device="cuda")
-    ops.ingest_x(x, slab, b, 2, c, t, tp, ld)
+    arena = torch.full((1000,), 5, dtype=torch.int64, device="cuda")
+    ops.ingest_x(x, slab, b, 2, c, t, tp, ld, zero=arena[:998])
     torch.cuda.synchronize()
     ref = to_slab(torch.cat([x, x], 0), tp, ld)
     assert torch.equal(slab, ref)
+    assert bool((arena[:998] == 0).all()) and bool((arena[998:] == 5).all())
     seq = rnd(2, 50, 234, seed=42)
     s2 = torch.full((2 * 50, 256), 9.0, dtype=BF16, device="cuda")
     ops.ingest_seq(seq, s2, 2, 50, 234, 50, 256)
