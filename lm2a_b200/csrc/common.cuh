@@ -385,6 +385,14 @@ __device__ __forceinline__ float silu_tanh(float v) {
   return v * fmaf(0.5f, t, 0.5f);
 }
 
+// SiLU of v given vh = v / 2: v * sigmoid(v) = vh * tanh(vh) + vh. Callers fold the 1/2 into the
+// affine map in front of it (GroupNorm scale / shift), which is exact in fp32.
+__device__ __forceinline__ float silu_from_half(float vh) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(vh));
+  return fmaf(vh, t, vh);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -45,8 +45,11 @@ constexpr int kASlotRows = 136;                      // 128 + 2 halo rows, round
 constexpr int kASlotBytes = kASlotRows * kBlockK * 2;  // 17408 = 17 * 1024
 constexpr int kXformWarps = 4;
 constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes half of the columns
-constexpr int kFirstEpiWarp = 2 + kXformWarps;
-constexpr int kThreads = 32 * (2 + kXformWarps + kEpiWarps);
+// warps: 0 TMA producer, 1 MMA issuer, [2, 6) operand transform (XF launches only), then epilogue
+__host__ __device__ constexpr int first_epi_warp(bool xf) { return xf ? 2 + kXformWarps : 2; }
+__host__ __device__ constexpr int num_threads(bool xf) {
+  return 32 * (first_epi_warp(xf) + kEpiWarps);
+}
 constexpr int kMaxGnChannels = 2048;   // gamma / beta of the input GroupNorm staged in smem
 constexpr int kMaxGnEntries = 512;     // (clip-rows touched by a tile) x groups
 constexpr float kStatScale1 = 16777216.0f;   // 2^24: sum
@@ -77,14 +80,18 @@ struct ConvArgs {
   const float* gn_beta;
   int gn_pitch, gn_groups, gn_cg, gn_silu;
   float gn_eps;
-  int desc_base_offset;       // 1: row-shifted tap views carry the matrix base offset
+  int share_taps;             // 1: one A block serves all taps (row-shifted views); 0: one
+                              //    128-slot box per tap
+  int dbg_noshift;            // timing experiments only: every tap reads the unshifted view
 };
 
-template <int BLOCK_N, int CG>
+// XF: the launch normalises segment 0 on the fly (operand transform warps active). Without it the
+// gamma / beta / statistics tables are not needed and the rings get the space.
+template <int BLOCK_N, int CG, bool XF>
 struct SmemLayout {
   static constexpr int kBSlotBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits W along N
-  static constexpr int kAStages = (BLOCK_N == 256 && CG == 1) ? 3 : 4;
-  static constexpr int kBStages = (BLOCK_N == 256 && CG == 1) ? 4 : (kBSlotBytes == 16384 ? 6 : 8);
+  static constexpr int kAStages = kBSlotBytes == 32768 ? (XF ? 3 : 4) : (XF ? 4 : 6);
+  static constexpr int kBStages = kBSlotBytes == 32768 ? 4 : (kBSlotBytes == 16384 ? 6 : 8);
   static constexpr int kAOffset = 0;
   static constexpr int kBOffset = kAStages * kASlotBytes;
   // epilogue: per warp a [32 rows][32 cols] bf16 staging tile (TMA store source, 64B swizzle)
@@ -96,22 +103,22 @@ struct SmemLayout {
   // operand transform: gamma | beta of the input GroupNorm, (mean, rstd) per (clip-row, group)
   // of the current tile, clip-row index of every slot of the A block
   static constexpr int kGammaOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
-  static constexpr int kMrOffset = kGammaOffset + 2 * kMaxGnChannels * 4;
-  static constexpr int kRowInfoOffset = kMrOffset + kMaxGnEntries * 8;
-  static constexpr int kBarOffset = kRowInfoOffset + kASlotRows * 4;
+  static constexpr int kMrOffset = kGammaOffset + (XF ? 2 * kMaxGnChannels * 4 : 0);
+  static constexpr int kRowInfoOffset = kMrOffset + (XF ? kMaxGnEntries * 8 : 0);
+  static constexpr int kBarOffset = kRowInfoOffset + (XF ? kASlotRows * 4 : 0);
   static constexpr int kNumBars = 3 * kAStages + 2 * kBStages + 4;
   static constexpr int kBytes = kBarOffset + 8 * kNumBars + 16 + 1024;  // + tmem slot + align
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
 
 // 128B-swizzled K-major operand descriptor of a tile that starts `row_shift` (< 8) rows into a
-// 1024-byte aligned slot: start address advanced by whole 128-byte rows, the swizzle phase of
-// the first row in the matrix-base-offset field (bits 49-51).
-__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t slot_addr, uint32_t row_shift,
-                                                        uint32_t use_base_offset) {
-  uint64_t d = umma_desc_sw128_kmajor(slot_addr + row_shift * 128u);
-  if (use_base_offset) d |= static_cast<uint64_t>(row_shift & 7u) << 49;
-  return d;
+// 1024-byte aligned slot: the start address advances by whole 128-byte rows and nothing else
+// changes. The tensor core applies the swizzle XOR to the absolute shared-memory address bits
+// (measured on B200: with the matrix-base-offset field, bits 49-51, set to the row phase the
+// result is wrong; with the field left 0 every tap view is exact), exactly like the +32 B
+// K-step advance inside a swizzle row.
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t slot_addr, uint32_t row_shift) {
+  return umma_desc_sw128_kmajor(slot_addr + row_shift * 128u);
 }
 
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -149,6 +156,7 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // The K loop of one output tile as a sequence of A blocks, each followed by the W blocks of
 // the taps it serves. on_a(seg, cb, row0, chan): box at slot m0 + row0, channel `chan` of the
 // segment's tensor map. on_b(shift, kb): tap view `shift` rows into the A block, W K-block kb.
+// share_taps == 0: every tap gets a 128-slot box of its own (row0 = the tap's shift, view 0).
 template <typename FA, typename FB>
 __device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_b) {
   int kb_base = 0;
@@ -157,6 +165,26 @@ __device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_
     const int cblk = p.seg_cblk[seg];
     if (cblk == 0) continue;
     const int mode = p.seg_taps[seg];
+    const int ntaps_all = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4);
+    if (!p.share_taps) {
+#pragma unroll 1
+      for (int tap = 0; tap < ntaps_all; ++tap) {
+        int row0 = 0, choff = 0;
+        if (mode == LM2A_TAPS_K3) {
+          row0 = tap - 1;
+        } else if (mode == LM2A_TAPS_K4S2) {
+          row0 = tap == 0 ? -1 : (tap == 3 ? 1 : 0);
+          choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < cblk; ++cb) {
+          on_a(seg, cb, row0, choff + cb * kBlockK);
+          on_b(0, kb_base + tap * cblk + cb);
+        }
+      }
+      kb_base += cblk * ntaps_all;
+      continue;
+    }
     const int nhalf = mode == LM2A_TAPS_K4S2 ? 2 : 1;
     const int ntap = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 2);
 #pragma unroll 1
@@ -172,27 +200,29 @@ __device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_
 #pragma unroll 1
         for (int j = 0; j < ntap; ++j) {
           const int tap = mode == LM2A_TAPS_K4S2 ? 2 * j + hf : j;
-          on_b(j, kb_base + tap * cblk + cb);
+          on_b(p.dbg_noshift ? 0 : j, kb_base + tap * cblk + cb);
         }
       }
     }
-    kb_base += cblk * (mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4));
+    kb_base += cblk * ntaps_all;
   }
 }
 
-__device__ __forceinline__ uint32_t a_box_bytes(int mode) {
-  const int rows = mode == LM2A_TAPS_K1 ? 128 : (mode == LM2A_TAPS_K3 ? 130 : 129);
+__device__ __forceinline__ uint32_t a_box_bytes(int mode, int share_taps) {
+  const int rows =
+      (mode == LM2A_TAPS_K1 || !share_taps) ? 128 : (mode == LM2A_TAPS_K3 ? 130 : 129);
   return (uint32_t)rows * kBlockK * 2;
 }
 
-template <int BLOCK_N, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BLOCK_N, int CG, bool XF>
+__global__ void __launch_bounds__(num_threads(XF), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
-  using L = SmemLayout<BLOCK_N, CG>;
+  using L = SmemLayout<BLOCK_N, CG, XF>;
   constexpr int NA = L::kAStages, NB = L::kBStages;
+  constexpr int kFirstEpiWarp = first_epi_warp(XF);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
@@ -215,7 +245,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;       // tile-walking unit
   const int num_units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
-  const bool xform = p.gn_stats != nullptr;
+  // XF launches hand every A block to the transform warps (a_full -> transform / pass-through
+  // -> a_ready); plain launches let the TMA complete straight on the barrier the MMA waits on
+  constexpr bool xform = XF;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -296,8 +328,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             p,
             [&](int seg, int, int row0, int chan) {
               mbar_wait(a_empty(sa), pa ^ 1u);
-              mbar_expect_tx(a_full(sa), a_box_bytes(p.seg_taps[seg]));
-              tma_load_2d(a_slot(sa), seg ? &tmA1 : &tmA0, chan, m0 + row0, a_full(sa));
+              const uint32_t bytes = a_box_bytes(p.seg_taps[seg], p.share_taps);
+              const CUtensorMap* tm = seg ? &tmA1 : &tmA0;
+              if (XF || CG == 1) {
+                mbar_expect_tx(a_full(sa), bytes);
+                tma_load_2d(a_slot(sa), tm, chan, m0 + row0, a_full(sa));
+              } else {
+                // pair, no transform: both CTAs' boxes complete on the LEADER's barrier
+                if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * bytes);
+                tma_load_2d_cg2(a_slot(sa), tm, chan, m0 + row0, mapa_shared(a_full(sa), 0));
+              }
               if (++sa == NA) {
                 sa = 0;
                 pa ^= 1u;
@@ -342,7 +382,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               if (a_open) {  // every tap of the previous A block has been issued: free its slot
                 if (CG == 2) umma_commit_cg2(a_empty(cur_a)); else umma_commit(a_empty(cur_a));
               }
-              if (CG == 2) mbar_wait_cluster(a_ready(sa), pa); else mbar_wait(a_ready(sa), pa);
+              if (!XF) mbar_wait(a_full(sa), pa);
+              else if (CG == 2) mbar_wait_cluster(a_ready(sa), pa);
+              else mbar_wait(a_ready(sa), pa);
               tc_fence_after_sync();
               cur_a = sa;
               a_open = true;
@@ -354,8 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             [&](int shift, int) {
               mbar_wait(b_full(sb), pb);
               tc_fence_after_sync();
-              const uint64_t adesc =
-                  umma_desc_sw128_rows(a_slot(cur_a), (uint32_t)shift, (uint32_t)p.desc_base_offset);
+              const uint64_t adesc = umma_desc_sw128_rows(a_slot(cur_a), (uint32_t)shift);
               const uint64_t bdesc = umma_desc_sw128_kmajor(b_slot(sb));
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
@@ -382,6 +423,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   } else if (warp < kFirstEpiWarp) {
     // ------------------------------------------------- operand transform (128 threads)
+    // (plain launches: the TMA signals the MMA warp directly and these warps idle)
+    if constexpr (XF) {
     const int xt = threadIdx.x - 64;
     const int chunk = xt & 7;    // 16-byte chunk (8 channels) of a 128-byte operand row
     const int rl = xt >> 3;      // row lane: rows rl, rl + 16, ...
@@ -389,7 +432,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     float2* mr = reinterpret_cast<float2*>(smem_gen + L::kMrOffset);
     int* row_info = reinterpret_cast<int*>(smem_gen + L::kRowInfoOffset);
     const int mode0 = p.seg_taps[0];
-    const int rows0 = mode0 == LM2A_TAPS_K3 ? 130 : 128;   // slots per A block of segment 0
+    // XF launches always share taps: segment 0 is one 130-slot (k3) / 128-slot (k1) block
+    const int rows0 = mode0 == LM2A_TAPS_K3 ? 130 : 128;
     const int roff0 = mode0 == LM2A_TAPS_K3 ? -1 : 0;
     uint32_t sa = 0, pa = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
@@ -436,13 +480,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               const uint32_t slot = a_slot(sa);
               const int c0 = cb * kBlockK + chunk * 8;
               const int g = c0 / p.gn_cg;
+              // y = SiLU(x * a + b) as vh = x * (a/2) + b/2, y = vh * tanh(vh) + vh: the halves
+              // are folded into gamma / beta (exact), two FMAs and one MUFU per element
+              const float hs = p.gn_silu ? 0.5f : 1.0f;
               float ga[8], be[8];
 #pragma unroll
               for (int e = 0; e < 8; e += 4) {
                 const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + e);
                 const float4 b4 = *reinterpret_cast<const float4*>(sg + kMaxGnChannels + c0 + e);
-                ga[e] = g4.x; ga[e + 1] = g4.y; ga[e + 2] = g4.z; ga[e + 3] = g4.w;
-                be[e] = b4.x; be[e + 1] = b4.y; be[e + 2] = b4.z; be[e + 3] = b4.w;
+                ga[e] = g4.x * hs; ga[e + 1] = g4.y * hs; ga[e + 2] = g4.z * hs; ga[e + 3] = g4.w * hs;
+                be[e] = b4.x * hs; be[e + 1] = b4.y * hs; be[e + 2] = b4.z * hs; be[e + 3] = b4.w * hs;
               }
               if (single_clip) {
                 const float2 s = mr[g];
@@ -452,7 +499,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                   be[e] = fmaf(-s.x, ga[e], be[e]);
                 }
               }
-#pragma unroll 1
+#pragma unroll 2
               for (int i = rl; i < rows0; i += 16) {
                 const int info = row_info[i];
                 if (info < 0) continue;   // pad slot / outside the slab: stays zero
@@ -482,8 +529,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                   float v0 = fmaf(x.x, a[2 * e], b[2 * e]);
                   float v1 = fmaf(x.y, a[2 * e + 1], b[2 * e + 1]);
                   if (p.gn_silu) {
-                    v0 = silu_tanh(v0);
-                    v1 = silu_tanh(v1);
+                    v0 = silu_from_half(v0);
+                    v1 = silu_from_half(v1);
                   }
                   w[e] = pack_bf16x2(v0, v1);
                 }
@@ -505,6 +552,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           },
           [](int, int) {});
     }
+    }  // XF
   } else {
     // ----------------------------------------------------------------- epilogue
     const int ew = warp - kFirstEpiWarp;
@@ -756,11 +804,11 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-template <int BLOCK_N, int CG>
+template <int BLOCK_N, int CG, bool XF>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
            const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
-  using L = SmemLayout<BLOCK_N, CG>;
-  auto kern = conv_gemm_kernel<BLOCK_N, CG>;
+  using L = SmemLayout<BLOCK_N, CG, XF>;
+  auto kern = conv_gemm_kernel<BLOCK_N, CG, XF>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured))
     LM2A_CUDA_OK(
@@ -768,7 +816,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   const int tiles = args.m_tiles * args.n_tiles;
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
-  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(kThreads), L::kBytes, stream,
+  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF)), L::kBytes, stream,
                                      (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
@@ -825,6 +873,20 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   ConvArgs a{};
   CUtensorMap tmA[2];
   int k_total = 0;
+  // One A block per (segment, 64 channels) serving every tap through row-shifted views, or one
+  // 128-slot box per tap. Launches that normalise their operand on the fly always share (the
+  // transform then runs once per element, not once per tap); for plain launches
+  // LM2A_CONV_SHARE_TAPS=0|1 overrides the default.
+  static const int share_env = [] {
+    const char* e = getenv("LM2A_CONV_SHARE_TAPS");
+    return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  static const int noshift_env = [] {
+    const char* e = getenv("LM2A_CONV_DBG_NOSHIFT");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  a.share_taps = d->in_gn_stats != nullptr ? 1 : (share_env >= 0 ? share_env : 1);
+  a.dbg_noshift = noshift_env;
   for (int s = 0; s < 2; ++s) {
     const lm2a_conv_seg& g = d->seg[s];
     if (g.x == nullptr) {
@@ -854,7 +916,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
       // slot pairs: one row of the [rows / 2, 2 * ld] view = (even slot | odd slot); a box
       // covers the pairs t (+1 halo) of one half
       if (encode_2d(&tmA[s], g.x, (uint64_t)g.ld + g.cin, (uint64_t)g.rows / 2,
-                    (uint64_t)g.ld * 2, kBlockM + 1))
+                    (uint64_t)g.ld * 2, a.share_taps ? kBlockM + 1 : kBlockM))
         return 1;
     } else {
       LM2A_REQUIRE(g.rows == d->m, "conv1d: seg %d slots (%lld) != output slots (%lld)", s,
@@ -862,7 +924,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
       a.seg_half[s] = 0;
       ntaps = g.taps == LM2A_TAPS_K3 ? 3 : 1;
       if (encode_2d(&tmA[s], g.x, (uint64_t)g.cin, (uint64_t)g.rows, (uint64_t)g.ld,
-                    g.taps == LM2A_TAPS_K3 ? kBlockM + 2 : kBlockM))
+                    (g.taps == LM2A_TAPS_K3 && a.share_taps) ? kBlockM + 2 : kBlockM))
         return 1;
     }
     k_total += ntaps * g.cin;
@@ -974,22 +1036,22 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   } else {
     LM2A_REQUIRE(d->out_mode == LM2A_OUT_F32_NCT, "conv1d: bad out_mode %d", d->out_mode);
   }
-  // LM2A_DESC_BASE_OFFSET=0: row-shifted tap views without the matrix-base-offset field
-  static const int base_off = [] {
-    const char* e = getenv("LM2A_DESC_BASE_OFFSET");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
-  }();
-  a.desc_base_offset = base_off;
-
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmOut = tmB;  // unused in the fp32 output mode
   if (d->out_mode == LM2A_OUT_BF16_SLAB &&
       encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
     return 1;
+  const bool xf = a.gn_stats != nullptr;
   if (cg == 2) {
-    if (block_n == 256) return launch<256, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
-    return launch<128, 2>(st, tmA[0], tmA[1], tmB, tmOut, a);
+    if (block_n == 256)
+      return xf ? launch<256, 2, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
+                : launch<256, 2, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
+    return xf ? launch<128, 2, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
+              : launch<128, 2, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
   }
-  if (block_n == 256) return launch<256, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
-  return launch<128, 1>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  if (block_n == 256)
+    return xf ? launch<256, 1, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
+              : launch<256, 1, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  return xf ? launch<128, 1, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
+            : launch<128, 1, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
 }

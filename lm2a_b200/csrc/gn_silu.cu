@@ -188,12 +188,15 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
     }
     const int g = (cv * 8) / cg;
     const float mean = s_mean[g], rstd = s_rstd[g];
+    // y = SiLU(x * a + b) evaluated as vh = x * (a/2) + b/2, y = vh * tanh(vh) + vh (the same
+    // arithmetic as the conv's operand transform: the two paths are bit-identical)
+    const float hs = apply_silu ? 0.5f : 1.0f;
     float ga[8], be[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float gm = __ldg(gamma + cv * 8 + e) * rstd;
+      const float gm = (__ldg(gamma + cv * 8 + e) * hs) * rstd;
       ga[e] = gm;
-      be[e] = fmaf(-mean, gm, __ldg(beta + cv * 8 + e));
+      be[e] = fmaf(-mean, gm, __ldg(beta + cv * 8 + e) * hs);
     }
 #pragma unroll
     for (int k = 0; k < kApplyVec; ++k) {
@@ -209,8 +212,8 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
           float v0 = fmaf(a.x, ga[2 * e], be[2 * e]);
           float v1 = fmaf(a.y, ga[2 * e + 1], be[2 * e + 1]);
           if (apply_silu) {
-            v0 = silu_tanh(v0);
-            v1 = silu_tanh(v1);
+            v0 = silu_from_half(v0);
+            v1 = silu_from_half(v1);
           }
           ow[e] = pack_bf16x2(v0, v1);
         }
