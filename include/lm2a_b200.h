@@ -119,7 +119,7 @@ typedef struct lm2a_conv_desc {
   int32_t in_gn_pitch;
   int32_t in_gn_groups;
   float in_gn_eps;
-  int32_t in_gn_silu;       /* 0: GroupNorm only                                */
+  int32_t in_gn_silu;       /* must be 1 (GroupNorm without SiLU: lm2a_gn_apply_bf16) */
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);

@@ -164,6 +164,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait that may last for a whole mainloop (epilogue warps waiting for an accumulator): the
+// try_wait carries a suspend-time hint, so the eight waiting warps do not keep the MIO queue
+// busy with polls (the default time limit re-polls every ~50 ns) while other warps of the CTA
+// work through shared memory. The thread still wakes as soon as the phase completes.
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(2000u)
+        : "memory");
+    if (done) return;
+    if ((++spins & 0xff) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+      printf("lm2a: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n",
+             (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA -----------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m))
@@ -383,6 +410,19 @@ __device__ __forceinline__ float silu_tanh(float v) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
   return v * fmaf(0.5f, t, 0.5f);
+}
+
+// GroupNorm statistics of one (clip-row, group) from the producer's exact fixed-point sums
+// (sum * 2^24, sum of squares * 2^20; see lm2a_conv_desc.stats): rstd and -mean * rstd, so that
+// the normalisation is one FMA per element. Explicit round-to-nearest operations: every kernel
+// that consumes the sums derives bit-identical scalars (no compiler-chosen FMA contraction).
+__device__ __forceinline__ float2 gn_rstd_cm(long long s1, long long s2, double inv_n, float eps) {
+  const double mean = __dmul_rn(__dmul_rn((double)s1, 1.0 / 16777216.0), inv_n);
+  double var = __dsub_rn(__dmul_rn(__dmul_rn((double)s2, 1.0 / 1048576.0), inv_n),
+                         __dmul_rn(mean, mean));
+  var = var > 0.0 ? var : 0.0;
+  const float rstd = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(var, (double)eps)));
+  return make_float2(rstd, __fmul_rn(-(float)mean, rstd));
 }
 
 // SiLU of v given vh = v / 2: v * sigmoid(v) = vh * tanh(vh) + vh. Callers fold the 1/2 into the

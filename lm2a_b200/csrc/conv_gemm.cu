@@ -46,9 +46,11 @@ constexpr int kASlotBytes = kASlotRows * kBlockK * 2;  // 17408 = 17 * 1024
 constexpr int kXformWarps = 4;
 constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes half of the columns
 // warps: 0 TMA producer, 1 MMA issuer, [2, 6) operand transform (XF launches only), then epilogue
-__host__ __device__ constexpr int first_epi_warp(bool xf) { return xf ? 2 + kXformWarps : 2; }
-__host__ __device__ constexpr int num_threads(bool xf) {
-  return 32 * (first_epi_warp(xf) + kEpiWarps);
+__host__ __device__ constexpr int first_epi_warp(bool xf, int cg) {
+  return xf ? 2 + kXformWarps + (cg == 2 ? 1 : 0) : 2;   // pair: + the hand-off warp
+}
+__host__ __device__ constexpr int num_threads(bool xf, int cg) {
+  return 32 * (first_epi_warp(xf, cg) + kEpiWarps);
 }
 constexpr int kMaxGnChannels = 2048;   // gamma / beta of the input GroupNorm staged in smem
 constexpr int kMaxGnEntries = 512;     // (clip-rows touched by a tile) x groups
@@ -78,11 +80,13 @@ struct ConvArgs {
   const long long* gn_stats;  // null = raw operand
   const float* gn_gamma;
   const float* gn_beta;
-  int gn_pitch, gn_groups, gn_cg, gn_silu;
+  int gn_pitch, gn_groups, gn_cg;
+  unsigned int gn_cg_magic;   // ceil(2^22 / gn_cg): c / gn_cg == (c * magic) >> 22 for c < 2048
   float gn_eps;
   int share_taps;             // 1: one A block serves all taps (row-shifted views); 0: one
                               //    128-slot box per tap
   int dbg_noshift;            // timing experiments only: every tap reads the unshifted view
+  int dbg_noxform;            // timing experiments only: transform warps pass blocks through
 };
 
 // XF: the launch normalises segment 0 on the fly (operand transform warps active). Without it the
@@ -106,7 +110,7 @@ struct SmemLayout {
   static constexpr int kMrOffset = kGammaOffset + (XF ? 2 * kMaxGnChannels * 4 : 0);
   static constexpr int kRowInfoOffset = kMrOffset + (XF ? kMaxGnEntries * 8 : 0);
   static constexpr int kBarOffset = kRowInfoOffset + (XF ? kASlotRows * 4 : 0);
-  static constexpr int kNumBars = 3 * kAStages + 2 * kBStages + 4;
+  static constexpr int kNumBars = 4 * kAStages + 2 * kBStages + 4;
   static constexpr int kBytes = kBarOffset + 8 * kNumBars + 16 + 1024;  // + tmem slot + align
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
@@ -167,17 +171,21 @@ __device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_
     const int mode = p.seg_taps[seg];
     const int ntaps_all = mode == LM2A_TAPS_K1 ? 1 : (mode == LM2A_TAPS_K3 ? 3 : 4);
     if (!p.share_taps) {
+      // same K order as the shared-block walk (channel block outer, tap inner; for k4s2 the odd
+      // half's taps 0, 2 before the even half's 1, 3): the accumulation order, and with it every
+      // output bit, does not depend on how the operand is staged
 #pragma unroll 1
-      for (int tap = 0; tap < ntaps_all; ++tap) {
-        int row0 = 0, choff = 0;
-        if (mode == LM2A_TAPS_K3) {
-          row0 = tap - 1;
-        } else if (mode == LM2A_TAPS_K4S2) {
-          row0 = tap == 0 ? -1 : (tap == 3 ? 1 : 0);
-          choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
-        }
+      for (int cb = 0; cb < cblk; ++cb) {
 #pragma unroll 1
-        for (int cb = 0; cb < cblk; ++cb) {
+        for (int j = 0; j < ntaps_all; ++j) {
+          int tap = j, row0 = 0, choff = 0;
+          if (mode == LM2A_TAPS_K3) {
+            row0 = tap - 1;
+          } else if (mode == LM2A_TAPS_K4S2) {
+            tap = (j & 1) * 2 + (j >> 1);          // 0, 2, 1, 3
+            row0 = tap == 0 ? -1 : (tap == 3 ? 1 : 0);
+            choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
+          }
           on_a(seg, cb, row0, choff + cb * kBlockK);
           on_b(0, kb_base + tap * cblk + cb);
         }
@@ -215,14 +223,14 @@ __device__ __forceinline__ uint32_t a_box_bytes(int mode, int share_taps) {
 }
 
 template <int BLOCK_N, int CG, bool XF>
-__global__ void __launch_bounds__(num_threads(XF), 1)
+__global__ void __launch_bounds__(num_threads(XF, CG), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
   using L = SmemLayout<BLOCK_N, CG, XF>;
   constexpr int NA = L::kAStages, NB = L::kBStages;
-  constexpr int kFirstEpiWarp = first_epi_warp(XF);
+  constexpr int kFirstEpiWarp = first_epi_warp(XF, CG);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
@@ -235,6 +243,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   auto b_empty = [&](int s) { return bar_base + 8u * (3 * NA + NB + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + s); };
+  auto x_done = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 4 + s); };
   const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
   auto a_slot = [&](int s) { return smem_base + L::kAOffset + s * kASlotBytes; };
   auto b_slot = [&](int s) { return smem_base + L::kBOffset + s * L::kBSlotBytes; };
@@ -256,7 +265,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     tma_prefetch_desc(&tmOut);
     for (int s = 0; s < NA; ++s) {
       mbar_init(a_full(s), 1);
-      mbar_init(a_ready(s), kXformWarps * CG);  // pair: the leader collects both CTAs' blocks
+      // single CTA: the four transform warps arrive; pair: one hand-off thread per CTA
+      mbar_init(a_ready(s), CG == 2 ? 2 : kXformWarps);
+      mbar_init(x_done(s), kXformWarps);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < NB; ++s) {
@@ -279,7 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       tmem_relinquish();
     }
   }
-  if (warp >= 2 && warp < kFirstEpiWarp && xform) {
+  if (warp >= 2 && warp < 2 + kXformWarps && xform) {
     // gamma / beta of the input GroupNorm (parameters: never written by a kernel of the stream)
     float* sg = reinterpret_cast<float*>(smem_gen + L::kGammaOffset);
     const int gn_c = p.gn_groups * p.gn_cg;
@@ -421,10 +432,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp < kFirstEpiWarp) {
+  } else if (warp < 2 + kXformWarps && XF) {
     // ------------------------------------------------- operand transform (128 threads)
-    // (plain launches: the TMA signals the MMA warp directly and these warps idle)
-    if constexpr (XF) {
+    // One warp per scheduler and no other warp to hide its latencies behind: the loop is laid
+    // out for instruction-level parallelism. A thread owns one 16-byte chunk (8 channels) of
+    // the rows rl, rl + 16, ... of every A block of the tile; which of those rows are real
+    // slots, and of which clip, is the same for all blocks of a tile and lives in registers;
+    // rows are processed three at a time with their loads issued up front.
     const int xt = threadIdx.x - 64;
     const int chunk = xt & 7;    // 16-byte chunk (8 channels) of a 128-byte operand row
     const int rl = xt >> 3;      // row lane: rows rl, rl + 16, ...
@@ -435,116 +449,108 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // XF launches always share taps: segment 0 is one 130-slot (k3) / 128-slot (k1) block
     const int rows0 = mode0 == LM2A_TAPS_K3 ? 130 : 128;
     const int roff0 = mode0 == LM2A_TAPS_K3 ? -1 : 0;
+    constexpr int kRowsPerThread = 9;   // ceil(130 / 16)
+    // byte offset of this thread's chunk inside row rl (rows rl + 16 k share its swizzle phase)
+    const uint32_t thr_off = (uint32_t)rl * 128u + (((uint32_t)(chunk ^ (rl & 7))) << 4);
     uint32_t sa = 0, pa = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_base = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM + roff0;
-      bool single_clip = false;
-      if (xform) {
-        // clip-row of every slot of the block and (mean, rstd) of every (clip-row, group) it
-        // touches, from the producer's exact integer sums
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
-        const int m_lo = m_base > 0 ? m_base : 0;
-        const long long m_hi_ll = (long long)m_base + rows0 - 1;
-        const int m_hi = m_hi_ll < p.m - 1 ? (int)m_hi_ll : (int)(p.m - 1);
-        const int r_first = m_lo / p.tp;
-        const int r_last = m_hi >= m_lo ? m_hi / p.tp : r_first - 1;
-        single_clip = r_last == r_first;
-        for (int i = xt; i < rows0; i += 32 * kXformWarps) {
-          const long long m = (long long)m_base + i;
-          int info = -1;
-          if (m >= 0 && m < p.m) {
-            const int r = (int)m / p.tp;
-            const int t = (int)m - r * p.tp;
-            if (t < p.t_valid) info = r - r_first;
-          }
-          row_info[i] = info;
+      // clip-row of every slot of the block and (mean, rstd) of every (clip-row, group) it
+      // touches, from the producer's exact integer sums
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
+      const int m_lo = m_base > 0 ? m_base : 0;
+      const long long m_hi_ll = (long long)m_base + rows0 - 1;
+      const int m_hi = m_hi_ll < p.m - 1 ? (int)m_hi_ll : (int)(p.m - 1);
+      const int r_first = m_lo / p.tp;
+      const int r_last = m_hi >= m_lo ? m_hi / p.tp : r_first - 1;
+      for (int i = xt; i < kASlotRows; i += 32 * kXformWarps) {
+        const long long m = (long long)m_base + i;
+        int info = -1;
+        if (i < rows0 && m >= 0 && m < p.m) {
+          const int r = (int)m / p.tp;
+          const int t = (int)m - r * p.tp;
+          if (t < p.t_valid) info = r - r_first;
         }
-        const int nent = (r_last - r_first + 1) * p.gn_groups;
-        const double inv_n = 1.0 / ((double)p.gn_cg * (double)p.t_valid);
-        for (int e = xt; e < nent; e += 32 * kXformWarps) {
-          const int rr = r_first + e / p.gn_groups, g = e % p.gn_groups;
-          const long long* sp = p.gn_stats + ((size_t)rr * p.gn_pitch + g) * 2;
-          const long long s1 = __ldcg(sp), s2 = __ldcg(sp + 1);
-          const double mean = (double)s1 * (1.0 / 16777216.0) * inv_n;
-          double var = (double)s2 * (1.0 / 1048576.0) * inv_n - mean * mean;
-          var = var > 0.0 ? var : 0.0;
-          mr[e] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)p.gn_eps)));
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
+        row_info[i] = info;
       }
+      const int nent = (r_last - r_first + 1) * p.gn_groups;
+      const double inv_n = 1.0 / ((double)p.gn_cg * (double)p.t_valid);
+      for (int e = xt; e < nent; e += 32 * kXformWarps) {
+        const int rr = r_first + e / p.gn_groups, g = e % p.gn_groups;
+        const long long* sp = p.gn_stats + ((size_t)rr * p.gn_pitch + g) * 2;
+        // (rstd, -mean * rstd): u = x * rstd - mean * rstd is one FMA per element
+        mr[e] = gn_rstd_cm(__ldcg(sp), __ldcg(sp + 1), inv_n, p.gn_eps);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kXformWarps) : "memory");
+      // per row of this thread: byte offset of its clip's (rstd, -mean rstd) table row and an
+      // all-ones / all-zeros store mask (pad slots and rows outside the slab must stay zero:
+      // they are the conv padding). Branch-free below: every row runs the same instructions.
+      uint32_t mr_off[kRowsPerThread], keep[kRowsPerThread];
+#pragma unroll
+      for (int k = 0; k < kRowsPerThread; ++k) {
+        const int i = rl + 16 * k;
+        const int inf = i < kASlotRows ? row_info[i] : -1;
+        keep[k] = inf >= 0 ? 0xffffffffu : 0u;
+        mr_off[k] = (uint32_t)((inf > 0 ? inf : 0) * p.gn_groups) * 8u;
+      }
+      const uint32_t mr_base = smem_base + L::kMrOffset;
       walk_tile(
           p,
           [&](int seg, int cb, int, int) {
             mbar_wait(a_full(sa), pa);
-            if (seg == 0 && xform) {
-              const uint32_t slot = a_slot(sa);
+            if (seg == 0 && !p.dbg_noxform) {
+              const uint32_t base = a_slot(sa) + thr_off;
               const int c0 = cb * kBlockK + chunk * 8;
-              const int g = c0 / p.gn_cg;
-              // y = SiLU(x * a + b) as vh = x * (a/2) + b/2, y = vh * tanh(vh) + vh: the halves
-              // are folded into gamma / beta (exact), two FMAs and one MUFU per element
-              const float hs = p.gn_silu ? 0.5f : 1.0f;
+              const uint32_t g = ((uint32_t)c0 * (uint32_t)p.gn_cg_magic) >> 22;   // c0 / gn_cg
+              // y = SiLU(v), v = u * gamma + beta, u = x * rstd - mean * rstd, evaluated as
+              // vh = u * (gamma/2) + beta/2, y = vh * tanh(vh) + vh (the halves fold exactly)
               float ga[8], be[8];
 #pragma unroll
               for (int e = 0; e < 8; e += 4) {
                 const float4 g4 = *reinterpret_cast<const float4*>(sg + c0 + e);
                 const float4 b4 = *reinterpret_cast<const float4*>(sg + kMaxGnChannels + c0 + e);
-                ga[e] = g4.x * hs; ga[e + 1] = g4.y * hs; ga[e + 2] = g4.z * hs; ga[e + 3] = g4.w * hs;
-                be[e] = b4.x * hs; be[e + 1] = b4.y * hs; be[e + 2] = b4.z * hs; be[e + 3] = b4.w * hs;
+                ga[e] = g4.x * 0.5f; ga[e + 1] = g4.y * 0.5f; ga[e + 2] = g4.z * 0.5f; ga[e + 3] = g4.w * 0.5f;
+                be[e] = b4.x * 0.5f; be[e + 1] = b4.y * 0.5f; be[e + 2] = b4.z * 0.5f; be[e + 3] = b4.w * 0.5f;
               }
-              if (single_clip) {
-                const float2 s = mr[g];
+              const uint32_t mr_g = mr_base + g * 8u;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  ga[e] *= s.y;
-                  be[e] = fmaf(-s.x, ga[e], be[e]);
+              for (int k0 = 0; k0 < kRowsPerThread; k0 += 3) {
+                uint32_t w[3][4];
+                float2 sc[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  // the last row of a thread (rl + 128) exists only for rl < 8: the slot has 136
+                  // rows (warp-uniform: a warp holds four consecutive row lanes)
+                  if (k0 + j == kRowsPerThread - 1 && rl >= kASlotRows - 128) continue;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(w[j][0]), "=r"(w[j][1]), "=r"(w[j][2]), "=r"(w[j][3])
+                               : "r"(base + (uint32_t)(k0 + j) * 2048u));
+                  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
+                               : "=f"(sc[j].x), "=f"(sc[j].y)
+                               : "r"(mr_g + mr_off[k0 + j]));
                 }
-              }
-#pragma unroll 2
-              for (int i = rl; i < rows0; i += 16) {
-                const int info = row_info[i];
-                if (info < 0) continue;   // pad slot / outside the slab: stays zero
-                float a[8], b[8];
-                if (single_clip) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    a[e] = ga[e];
-                    b[e] = be[e];
-                  }
-                } else {
-                  const float2 s = mr[info * p.gn_groups + g];
+                for (int j = 0; j < 3; ++j) {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    a[e] = ga[e] * s.y;
-                    b[e] = fmaf(-s.x, a[e], be[e]);
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 x = unpack_bf16x2(w[j][e]);
+                    const float v0 = fmaf(fmaf(x.x, sc[j].x, sc[j].y), ga[2 * e], be[2 * e]);
+                    const float v1 = fmaf(fmaf(x.y, sc[j].x, sc[j].y), ga[2 * e + 1], be[2 * e + 1]);
+                    w[j][e] = pack_bf16x2(silu_from_half(v0), silu_from_half(v1)) & keep[k0 + j];
                   }
                 }
-                const uint32_t addr = slot + (uint32_t)i * 128u + (((uint32_t)(chunk ^ (i & 7))) << 4);
-                uint32_t w[4];
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
-                             : "r"(addr));
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 x = unpack_bf16x2(w[e]);
-                  float v0 = fmaf(x.x, a[2 * e], b[2 * e]);
-                  float v1 = fmaf(x.y, a[2 * e + 1], b[2 * e + 1]);
-                  if (p.gn_silu) {
-                    v0 = silu_from_half(v0);
-                    v1 = silu_from_half(v1);
-                  }
-                  w[e] = pack_bf16x2(v0, v1);
-                }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]),
-                             "r"(w[1]), "r"(w[2]), "r"(w[3])
-                             : "memory");
+                for (int j = 0; j < 3; ++j)
+                  if (!(k0 + j == kRowsPerThread - 1 && rl >= kASlotRows - 128))
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                   base + (uint32_t)(k0 + j) * 2048u),
+                               "r"(w[j][0]), "r"(w[j][1]), "r"(w[j][2]), "r"(w[j][3])
+                               : "memory");
               }
               fence_proxy_async_smem();
             }
             __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(mapa_shared(a_ready(sa), 0));
-              else mbar_arrive(a_ready(sa));
-            }
+            if (lane == 0) mbar_arrive(CG == 2 ? x_done(sa) : a_ready(sa));
             if (++sa == NA) {
               sa = 0;
               pa ^= 1u;
@@ -552,7 +558,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           },
           [](int, int) {});
     }
-    }  // XF
+  } else if (warp == 2 + kXformWarps && XF && CG == 2) {
+    // --------------------------------------------------------- pair: hand-off warp
+    // The leader's MMA reads both CTAs' transformed blocks, so each CTA has to release its
+    // block at cluster scope - a fence that costs several hundred cycles. One otherwise idle
+    // thread pays it, off the transform warps' critical path: they arrive on a CTA-local
+    // barrier (cheap), this thread forwards the arrival to the leader's a_ready.
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        walk_tile(
+            p,
+            [&](int, int, int, int) {
+              mbar_wait(x_done(sa), pa);
+              mbar_arrive_cluster(mapa_shared(a_ready(sa), 0));
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1u;
+              }
+            },
+            [](int, int) {});
+      }
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // (plain launches have no such warps)
   } else {
     // ----------------------------------------------------------------- epilogue
     const int ew = warp - kFirstEpiWarp;
@@ -610,7 +639,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         __syncwarp();
       }
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait_long(tfull_bar(acc), acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
 
@@ -816,7 +845,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   const int tiles = args.m_tiles * args.n_tiles;
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
-  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF)), L::kBytes, stream,
+  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF, CG)), L::kBytes, stream,
                                      (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
@@ -875,8 +904,10 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   int k_total = 0;
   // One A block per (segment, 64 channels) serving every tap through row-shifted views, or one
   // 128-slot box per tap. Launches that normalise their operand on the fly always share (the
-  // transform then runs once per element, not once per tap); for plain launches
-  // LM2A_CONV_SHARE_TAPS=0|1 overrides the default.
+  // transform then runs once per element, not once per tap). Plain launches are MMA-bound, not
+  // load-bound, and measured equal or slightly faster with one box per tap (B200, production
+  // shapes: 50.6 vs 53.7 us at M 8320 x N 1024 x K 3584): their default;
+  // LM2A_CONV_SHARE_TAPS=0|1 overrides it.
   static const int share_env = [] {
     const char* e = getenv("LM2A_CONV_SHARE_TAPS");
     return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
@@ -885,8 +916,13 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     const char* e = getenv("LM2A_CONV_DBG_NOSHIFT");
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
-  a.share_taps = d->in_gn_stats != nullptr ? 1 : (share_env >= 0 ? share_env : 1);
+  a.share_taps = d->in_gn_stats != nullptr ? 1 : (share_env >= 0 ? share_env : 0);
   a.dbg_noshift = noshift_env;
+  static const int noxform_env = [] {
+    const char* e = getenv("LM2A_CONV_DBG_NOXFORM");
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
+  }();
+  a.dbg_noxform = noxform_env;
   for (int s = 0; s < 2; ++s) {
     const lm2a_conv_seg& g = d->seg[s];
     if (g.x == nullptr) {
@@ -1007,7 +1043,6 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   a.gn_pitch = d->in_gn_pitch;
   a.gn_groups = d->in_gn_groups;
   a.gn_eps = d->in_gn_eps;
-  a.gn_silu = d->in_gn_silu;
   if (d->in_gn_stats != nullptr) {
     const lm2a_conv_seg& g = d->seg[0];
     LM2A_REQUIRE(d->in_gn_gamma != nullptr && d->in_gn_beta != nullptr && d->in_gn_groups > 0 &&
@@ -1022,7 +1057,11 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
                    reinterpret_cast<uintptr_t>(d->in_gn_gamma) |
                    reinterpret_cast<uintptr_t>(d->in_gn_beta)) & 15) == 0,
                  "conv1d: input GroupNorm stats / gamma / beta must be 16-byte aligned");
+    LM2A_REQUIRE(d->in_gn_silu != 0,
+                 "conv1d: the operand transform is GroupNorm + SiLU (in_gn_silu = 0: use "
+                 "lm2a_gn_apply_bf16 in front of the conv)");
     a.gn_cg = g.cin / d->in_gn_groups;
+    a.gn_cg_magic = (unsigned int)(((1u << 22) + a.gn_cg - 1) / a.gn_cg);
     const int clip_rows = (kBlockM + 2 - 1) / d->tp + 2;   // clip-rows a 130-slot block can touch
     LM2A_REQUIRE(clip_rows * d->in_gn_groups <= kMaxGnEntries,
                  "conv1d: input GroupNorm: %d clip-rows x %d groups per tile exceed %d entries "

@@ -140,7 +140,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
                 int tp, int t_valid, int c, int groups, float eps, int apply_silu) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_sc[64];   // (rstd, -mean * rstd) per group
   const int r = blockIdx.y;
   const int cg = c / groups;
   // thread -> (vector column, slot) mapping; the first pass's loads are issued before the
@@ -167,11 +167,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
     const int g = threadIdx.x;
     const long long* sp = stats + ((size_t)r * stats_pitch + g) * 2;
     const double inv_n = 1.0 / ((double)cg * (double)t_valid);
-    const double mean = (double)__ldcg(sp) * (1.0 / 16777216.0) * inv_n;
-    double var = (double)__ldcg(sp + 1) * (1.0 / 1048576.0) * inv_n - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    s_mean[g] = (float)mean;
-    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    s_sc[g] = gn_rstd_cm(__ldcg(sp), __ldcg(sp + 1), inv_n, eps);
   }
   __syncthreads();
 
@@ -187,16 +183,16 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
       }
     }
     const int g = (cv * 8) / cg;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    // y = SiLU(x * a + b) evaluated as vh = x * (a/2) + b/2, y = vh * tanh(vh) + vh (the same
-    // arithmetic as the conv's operand transform: the two paths are bit-identical)
+    // y = SiLU(v), v = u * gamma + beta, u = x * rstd - mean * rstd, evaluated as
+    // vh = u * (gamma/2) + beta/2, y = vh * tanh(vh) + vh (the same arithmetic as the conv's
+    // operand transform: the two paths are bit-identical)
+    const float rstd = s_sc[g].x, cm = s_sc[g].y;
     const float hs = apply_silu ? 0.5f : 1.0f;
     float ga[8], be[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float gm = (__ldg(gamma + cv * 8 + e) * hs) * rstd;
-      ga[e] = gm;
-      be[e] = fmaf(-mean, gm, __ldg(beta + cv * 8 + e) * hs);
+      ga[e] = __ldg(gamma + cv * 8 + e) * hs;
+      be[e] = __ldg(beta + cv * 8 + e) * hs;
     }
 #pragma unroll
     for (int k = 0; k < kApplyVec; ++k) {
@@ -209,8 +205,8 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* __
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 a = unpack_bf16x2(w[e]);
-          float v0 = fmaf(a.x, ga[2 * e], be[2 * e]);
-          float v1 = fmaf(a.y, ga[2 * e + 1], be[2 * e + 1]);
+          float v0 = fmaf(fmaf(a.x, rstd, cm), ga[2 * e], be[2 * e]);
+          float v1 = fmaf(fmaf(a.y, rstd, cm), ga[2 * e + 1], be[2 * e + 1]);
           if (apply_silu) {
             v0 = silu_from_half(v0);
             v1 = silu_from_half(v1);

@@ -322,8 +322,8 @@ def test_conv_groupnorm_operand_variants(ops, cta_group):
     _gn_input_case(ops, 3, 129, 130, 256, 128, 8, ops.TAPS_K3, 1, cta_group, 128, skip_c=128)
     # very short clips: a tile touches 11 of them (12-slot pitch)
     _gn_input_case(ops, 40, 11, 12, 64, 128, 8, ops.TAPS_K3, 0, cta_group, 128)
-    # GroupNorm without SiLU, legacy concat width 1536 (192-channel groups straddle 64-blocks)
-    _gn_input_case(ops, 2, 64, 65, 1536, 128, 8, ops.TAPS_K3, 0, cta_group, 128, silu=False)
+    # legacy concat width 1536 (192-channel groups straddle 64-channel blocks)
+    _gn_input_case(ops, 2, 64, 65, 1536, 128, 8, ops.TAPS_K3, 0, cta_group, 128)
     # the largest supported channel count
     _gn_input_case(ops, 2, 130, 132, 2048, 256, 8, ops.TAPS_K3, 0, cta_group, 256)
 
@@ -339,6 +339,10 @@ def test_conv_groupnorm_operand_rejects_unsupported(ops):
     with pytest.raises(RuntimeError, match="clip-rows"):   # 2-slot clips: 66 clips per tile
         ops.conv1d(ops.make_conv_desc([ops.Seg(x, 64, 64, ops.TAPS_K3, 128)], w, b, 128, 128, 2, 1,
                                       out, 128, in_gn=(st, g, g, 1e-5, True)))
+    st2 = ops.Stats(2, 64, 8, "cuda")
+    with pytest.raises(RuntimeError, match="SiLU"):        # GroupNorm alone: gn_apply's job
+        ops.conv1d(ops.make_conv_desc([ops.Seg(x, 64, 64, ops.TAPS_K3, 128)], w, b, 128, 128, 64, 60,
+                                      out, 128, in_gn=(st2, g, g, 1e-5, False)))
 
 
 @pytest.mark.parametrize("r,t,tp,c,groups", [(3, 129, 130, 512, 8), (33, 64, 65, 1024, 8),

@@ -17,6 +17,8 @@ from lm2a_b200 import ops  # noqa: E402
 dev = torch.device("cuda", 0)
 BF16 = torch.bfloat16
 tag = sys.argv[1] if len(sys.argv) > 1 else "default"
+ONLY = sys.argv[2] if len(sys.argv) > 2 else None      # substring filter on the shape name
+SILU = os.environ.get("BENCH_GN_SILU", "1") != "0"
 
 # (name, rows, T, Tp, cin, cout, taps, skip_cin, in_gn)
 SHAPES = [
@@ -56,6 +58,8 @@ def time_op(fn, iters=10):
 print(f"# variant {tag}: SHARE_TAPS={os.environ.get('LM2A_CONV_SHARE_TAPS')} "
       f"NOSHIFT={os.environ.get('LM2A_CONV_DBG_NOSHIFT')} CG={os.environ.get('LM2A_CONV_CG')}")
 for name, r, t, tp, cin, cout, taps, skip_c, in_gn in SHAPES:
+    if ONLY and ONLY not in name:
+        continue
     m = r * tp
     k = 3 if taps == "k3" else 1
     tk = ops.TAPS_K3 if taps == "k3" else ops.TAPS_K1
@@ -76,7 +80,7 @@ for name, r, t, tp, cin, cout, taps, skip_c, in_gn in SHAPES:
         st = ops.Stats(r, cin, 8, dev)
         ops.bias_add(x, cin, 0, torch.empty_like(x), cin, 0, torch.zeros(cin, device=dev), m, tp, t,
                      cin, st)
-        gn = (st, torch.ones(cin, device=dev), torch.zeros(cin, device=dev), 1e-5, True)
+        gn = (st, torch.ones(cin, device=dev), torch.zeros(cin, device=dev), 1e-5, SILU)
     d = ops.make_conv_desc(segs, w, bias, cout, m, tp, t, out, cout, stats=st_out, in_gn=gn)
     sec = time_op(lambda: ops.conv1d(d))
     fl = 2.0 * r * t * cout * ktot
