@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]): production UNet1D_ultimate (base 256, mults
 8 heads, 134 M params, random init), B = 32 clips per GPU under classifier-free guidance
 (64 rows), mel (80, 516), conditions (516, 128) per stream, guidance 2.1, bf16 tensor-core
 path. A "step" is ONE denoising step of the whole batch = one CUDA Graph replay
-(x ingest -> UNet -> CFG blend + clamps + DDPM posterior, timestep advanced on device).
+(UNet -> one update kernel: CFG blend + clamps + DDPM posterior + noise drawn in the kernel +
+the next step's input slab, timestep advanced on device; every launch is a kernel of this repo).
 `value` = clips/s for the reference's 1000-step trajectory = N*B / (1000 * s_per_step),
 inputs resident in HBM. `e2e` = the same metric through lm2a_b200.sample.sample_clips_raw
 with HOST inputs shaped like the npz files (motion (180, 234), lyrics (516, 768) per clip):
@@ -308,6 +309,7 @@ def run_b200(args):
         plan = sampler.plan
         plan.x_in.normal_()
         plan.t_in.fill_(TRAJ_STEPS - 1)
+        sampler._start_fused()      # input slab of the first replayed step
 
         def barrier():
             if world > 1:
@@ -354,6 +356,7 @@ def run_b200(args):
         tiled = {"const_text_stream": bool(plan.const_text)}
         sampler._ensure_graph()
         plan.t_in.fill_(TRAJ_STEPS - 1)
+        sampler._start_fused()
         for _ in range(warmup):
             sampler.graph.replay()
         barrier()
@@ -384,6 +387,7 @@ def run_b200(args):
             s64._ensure_graph()
             s64.plan.x_in.normal_()
             s64.plan.t_in.fill_(TRAJ_STEPS - 1)
+            s64._start_fused()
             for _ in range(warmup):
                 s64.graph.replay()
             barrier()

@@ -31,6 +31,9 @@
  *   lm2a_ingest_x      torch.cat([x, x]) + layout change, sample.py:162
  *   lm2a_cfg_posterior sample.py:167-174 (CFG blend + clamps) and
  *                      sample.py:186-210 == models/diffusion.py:71-102
+ *   lm2a_cfg_step      sample.py:162-210 in one launch (blend + posterior + noise drawn
+ *                      in the kernel + next step's input slab); lm2a_philox_normal
+ *                      torch.randn of sample.py:136,204
  *   lm2a_cfg_ddim      models/diffusion.py:124-165 (ddim_sample)
  *   lm2a_resample_seq  datasetcode/dataset.py:49-87 (match_len 'interp')
  *   lm2a_mel_metrics   val.py:25-113 (compute_metrics)
@@ -45,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 7
+#define LM2A_ABI_VERSION 8
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -245,6 +248,32 @@ int lm2a_cfg_posterior(void* stream, float* x, const float* eps,
                        int64_t* t_dev, int32_t n_t, uint32_t* ticket,
                        int32_t batch, int64_t elems_per_clip, float guidance,
                        int32_t guided, int32_t advance, float* eps_out);
+
+/* ---- the whole per-step update as one kernel -------------------------------- */
+/* sample.py:162-210 between two UNet evaluations: CFG blend + clamps, DDPM
+ * posterior update, noise injection, the next step's input slab (the
+ * torch.cat([x, x]) + layout change lm2a_ingest_x performs) and the clearing of
+ * the step's GroupNorm statistics arena. x fp32 [B, c, t] in place; eps / sched /
+ * t_dev / ticket / guidance / guided / advance / eps_out as in lm2a_cfg_posterior.
+ * Noise: `noise` fp32 [B, c, t] if given (injected draws, parity runs); else, if
+ * clip_seed (uint64 [B]) is given, drawn in the kernel: z[b, ch, i] at timestep s =
+ * Box-Muller of Philox4x32-10(counter = (ch * ceil(t/4) + i/4, s, 0, 0), key =
+ * clip_seed[b]), component i % 4, u = (word >> 8) * 2^-24 + 2^-25 - a function of
+ * the clip's seed, the element and the timestep only, so a clip's trajectory does
+ * not depend on the batch (or GPU) it is sampled in; else no noise. slab (optional):
+ * bf16 [copies*B, tp, ld] rows written from the NEW x (pad slots / channels zero).
+ * zero / zero_bytes: region cleared by the same launch (may be NULL / 0).       */
+int lm2a_cfg_step(void* stream, float* x, const float* eps, const float* noise,
+                  const uint64_t* clip_seed, const float* sched, int64_t* t_dev,
+                  int32_t n_t, uint32_t* ticket, int32_t batch, int32_t c,
+                  int32_t t, float guidance, int32_t guided, int32_t advance,
+                  void* slab, int32_t copies, int32_t tp, int32_t ld, void* zero,
+                  int64_t zero_bytes, float* eps_out);
+/* out fp32 [B, c, t] = the normals lm2a_cfg_step draws at counter word `step`
+ * (a trajectory's x_T uses step = number of timesteps: one past the largest t;
+ * reference sample.py:136 draws it with torch.randn).                          */
+int lm2a_philox_normal(void* stream, float* out, const uint64_t* clip_seed,
+                       int32_t batch, int32_t c, int32_t t, uint32_t step);
 
 /* ---- CFG blend + DDIM update over a strided timestep sequence ------------- */
 /* Reference models/diffusion.py:124-165 (ddim_sample; never called by the

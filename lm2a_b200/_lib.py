@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblm2a_b200.so")
+# LM2A_LIB_PATH: load another build of the same ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("LM2A_LIB_PATH") or os.path.join(_HERE, "liblm2a_b200.so")
 
 c_void_p, c_int32, c_int64, c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
@@ -30,7 +31,7 @@ class ConvDesc(ctypes.Structure):
                 ("in_gn_silu", c_int32)]
 
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -78,6 +79,12 @@ SIGNATURES = {
     "lm2a_cfg_posterior": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_int32, c_void_p, c_int32, c_int64, c_float, c_int32,
                                      c_int32, c_void_p]),
+    "lm2a_cfg_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_float,
+                                c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                c_int64, c_void_p]),
+    "lm2a_philox_normal": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     ctypes.c_uint32]),
     "lm2a_cfg_ddim": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_float,
                                 c_int32, c_int32, c_void_p]),

@@ -14,17 +14,24 @@
 //     and the GroupNorm sums of the OUTPUT for the next consumer.
 //
 // One CTA per SM, persistent over 128 x BLOCK_N output tiles (CG = 2: a CTA pair per
-// 256 x BLOCK_N tile, cta_group::2 UMMA):
-//   warp 0      TMA producer. An "A block" is ONE box of 128 (+ halo) slots x 64 channels that
-//               serves every tap of the conv: a tap is a row shift, and a row-shifted view of a
-//               128B-swizzled tile is expressed in the UMMA descriptor (start address + 128 B
-//               per row, matrix base offset = row phase). Operand bytes per output tile drop by
-//               the tap count versus one box per tap. W boxes ride in a ring of their own.
-//   warp 1      tcgen05.mma issuer (one thread), fp32 accumulators double-buffered in TMEM
-//   warps 2-5   operand transform: wait for the A block, normalise + SiLU in place (or pass it
-//               through untouched), fence to the async proxy, hand it to the MMA warp
-//   warps 6-13  epilogue: tcgen05.ld -> bias / FiLM / residual -> GroupNorm sums -> bf16 slab via
-//               TMA store (or the final fp32 [R, C, T] eps tensor)
+// 256 x BLOCK_N tile, cta_group::2 UMMA). Two pipelines behind one epilogue (template XF):
+//   plain (XF = 0)   warp 0 TMA producer: per K block one 128-slot A box (a tap is a row shift
+//               of the flattened slab; the zero slot between clips and TMA's out-of-bounds zero
+//               fill are the conv padding) and one W box in the same stage; warp 1 MMA issuer
+//               (one thread; one barrier wait + one commit per K block), fp32 accumulators
+//               double-buffered in TMEM; warps 2-9 epilogue
+//   operand transform (XF = 1)   an "A block" is ONE box of 128 (+ 2 halo) slots x 64 channels
+//               that serves every tap: a row-shifted view of a 128B-swizzled tile is the same
+//               UMMA descriptor with its start address advanced by 128 B per row (the tensor
+//               core applies the swizzle to absolute shared-memory address bits, see
+//               umma_desc_sw128_rows). W boxes ride in a ring of their own. Warps 2-5 wait for
+//               an A block, apply y = SiLU(GroupNorm(x)) to it in place (one pass per element,
+//               not per tap), fence to the async proxy and hand it to the MMA warp; in a CTA
+//               pair warp 6 forwards the hand-off to the leader at cluster scope; the next 8
+//               warps are the epilogue
+//   epilogue    tcgen05.ld -> bias / FiLM / residual -> GroupNorm sums -> bf16 slab via TMA
+//               store (or the final fp32 [R, C, T] eps tensor); warp w reads TMEM lane quadrant
+//               w % 4 and one half of the columns
 //
 // GroupNorm sums are exact: every lane's per-slot channel sums (a fixed-order fp32 sum that does
 // not depend on where the slot sits in the batch) are converted to 40.24 / 44.20 fixed point and
@@ -43,14 +50,21 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kASlotRows = 136;                      // 128 + 2 halo rows, rounded to 8-row atoms
 constexpr int kASlotBytes = kASlotRows * kBlockK * 2;  // 17408 = 17 * 1024
-constexpr int kXformWarps = 4;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;     // 16384: a plain 128-row box
+constexpr int kXformWarps = 8;       // two per scheduler: one warp's latencies hide under the other's
+constexpr int kFirstXformWarp = 4;   // warpgroup-aligned (setmaxnreg works per warpgroup)
 constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each takes half of the columns
 // warps: 0 TMA producer, 1 MMA issuer, [2, 6) operand transform (XF launches only), then epilogue
-__host__ __device__ constexpr int first_epi_warp(bool xf, int cg) {
-  return xf ? 2 + kXformWarps + (cg == 2 ? 1 : 0) : 2;   // pair: + the hand-off warp
+// XF launches: warpgroup 0 = {TMA producer, MMA issuer, pair hand-off, idle}, warpgroups 1-2 =
+// operand transform, warpgroups 3-4 = epilogue; registers are moved from the first three to the
+// epilogue with setmaxnreg (40 / 80 / 136 per thread). The pool is what the CTA was launched
+// with (640 threads x 96 registers = 61440), not the SM's register file: 128 x 40 + 256 x 80 +
+// 256 x 136 = 60416 fits; asking for more than the pool holds spins forever.
+__host__ __device__ constexpr int first_epi_warp(bool xf) {
+  return xf ? kFirstXformWarp + kXformWarps : 2;
 }
-__host__ __device__ constexpr int num_threads(bool xf, int cg) {
-  return 32 * (first_epi_warp(xf, cg) + kEpiWarps);
+__host__ __device__ constexpr int num_threads(bool xf) {
+  return 32 * (first_epi_warp(xf) + kEpiWarps);
 }
 constexpr int kMaxGnChannels = 2048;   // gamma / beta of the input GroupNorm staged in smem
 constexpr int kMaxGnEntries = 512;     // (clip-rows touched by a tile) x groups
@@ -94,10 +108,15 @@ struct ConvArgs {
 template <int BLOCK_N, int CG, bool XF>
 struct SmemLayout {
   static constexpr int kBSlotBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits W along N
-  static constexpr int kAStages = kBSlotBytes == 32768 ? (XF ? 3 : 4) : (XF ? 4 : 6);
-  static constexpr int kBStages = kBSlotBytes == 32768 ? 4 : (kBSlotBytes == 16384 ? 6 : 8);
+  // XF: a ring of A blocks (136 rows: one box serves every tap) and a ring of W blocks.
+  // Plain: ONE ring of stages, each a 128-row A box plus its W box behind one barrier pair
+  // (one wait and one commit per K block for the MMA-issuing thread).
+  static constexpr int kASlot = XF ? kASlotBytes : kATileBytes;
+  static constexpr int kBStages = XF ? (kBSlotBytes == 32768 ? 4 : (kBSlotBytes == 16384 ? 6 : 8))
+                                     : (kBSlotBytes == 32768 ? 4 : (kBSlotBytes == 16384 ? 6 : 8));
+  static constexpr int kAStages = XF ? (kBSlotBytes == 32768 ? 3 : 4) : kBStages;
   static constexpr int kAOffset = 0;
-  static constexpr int kBOffset = kAStages * kASlotBytes;
+  static constexpr int kBOffset = kAStages * kASlot;
   // epilogue: per warp a [32 rows][32 cols] bf16 staging tile (TMA store source, 64B swizzle)
   // and a table of per-column (scale, offset) pairs for its BLOCK_N / 2 columns
   static constexpr int kOutOffset = kBOffset + kBStages * kBSlotBytes;
@@ -223,14 +242,14 @@ __device__ __forceinline__ uint32_t a_box_bytes(int mode, int share_taps) {
 }
 
 template <int BLOCK_N, int CG, bool XF>
-__global__ void __launch_bounds__(num_threads(XF, CG), 1)
+__global__ void __launch_bounds__(num_threads(XF), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const ConvArgs p) {
   using L = SmemLayout<BLOCK_N, CG, XF>;
   constexpr int NA = L::kAStages, NB = L::kBStages;
-  constexpr int kFirstEpiWarp = first_epi_warp(XF, CG);
+  constexpr int kFirstEpiWarp = first_epi_warp(XF);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic view of smem_base
@@ -245,7 +264,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + s); };
   auto x_done = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 4 + s); };
   const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
-  auto a_slot = [&](int s) { return smem_base + L::kAOffset + s * kASlotBytes; };
+  auto a_slot = [&](int s) { return smem_base + L::kAOffset + s * L::kASlot; };
   auto b_slot = [&](int s) { return smem_base + L::kBOffset + s * L::kBSlotBytes; };
 
   const int warp = threadIdx.x >> 5;
@@ -290,11 +309,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       tmem_relinquish();
     }
   }
-  if (warp >= 2 && warp < 2 + kXformWarps && xform) {
+  if (warp >= kFirstXformWarp && warp < kFirstXformWarp + kXformWarps && xform) {
     // gamma / beta of the input GroupNorm (parameters: never written by a kernel of the stream)
     float* sg = reinterpret_cast<float*>(smem_gen + L::kGammaOffset);
     const int gn_c = p.gn_groups * p.gn_cg;
-    for (int i = threadIdx.x - 64; i < gn_c; i += 32 * kXformWarps) {
+    for (int i = threadIdx.x - 32 * kFirstXformWarp; i < gn_c; i += 32 * kXformWarps) {
       sg[i] = __ldg(p.gn_gamma + i);
       sg[kMaxGnChannels + i] = __ldg(p.gn_beta + i);
     }
@@ -315,11 +334,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               [&](int, int kb) {
                 if (w_prefetched >= NB) return;
                 const int s = w_prefetched++;
+                // plain launches: the stage's barrier also covers its A box (128 rows), which
+                // follows after griddepcontrol.wait
+                const uint32_t bytes = L::kBSlotBytes + (XF ? 0 : kATileBytes);
                 if (CG == 2) {
-                  if (cta_rank == 0) mbar_expect_tx(b_full(s), 2 * L::kBSlotBytes);
+                  if (cta_rank == 0) mbar_expect_tx(b_full(s), 2 * bytes);
                   tma_load_2d_cg2(b_slot(s), &tmB, kb * kBlockK, n0, mapa_shared(b_full(s), 0));
                 } else {
-                  mbar_expect_tx(b_full(s), L::kBSlotBytes);
+                  mbar_expect_tx(b_full(s), bytes);
                   tma_load_2d(b_slot(s), &tmB, kb * kBlockK, n0, b_full(s));
                 }
               });
@@ -327,6 +349,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   pdl_wait();
   pdl_launch_dependents();
 
+  // XF launches re-balance the register file per warpgroup (setmaxnreg is warpgroup-wide, so
+  // each class of warps executes its own at the top of the region it dominates)
+  if (XF && warp < kFirstXformWarp) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -335,20 +360,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int m0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
         const int n0 = (tile % p.n_tiles) * BLOCK_N + cta_rank * (BLOCK_N / CG);
+        const CUtensorMap* cur_tm = &tmA0;
+        int cur_chan = 0, cur_row = 0;
         walk_tile(
             p,
             [&](int seg, int, int row0, int chan) {
-              mbar_wait(a_empty(sa), pa ^ 1u);
-              const uint32_t bytes = a_box_bytes(p.seg_taps[seg], p.share_taps);
               const CUtensorMap* tm = seg ? &tmA1 : &tmA0;
-              if (XF || CG == 1) {
-                mbar_expect_tx(a_full(sa), bytes);
-                tma_load_2d(a_slot(sa), tm, chan, m0 + row0, a_full(sa));
-              } else {
-                // pair, no transform: both CTAs' boxes complete on the LEADER's barrier
-                if (cta_rank == 0) mbar_expect_tx(a_full(sa), 2 * bytes);
-                tma_load_2d_cg2(a_slot(sa), tm, chan, m0 + row0, mapa_shared(a_full(sa), 0));
+              if (!XF) {   // plain: the A box travels with its W box (below)
+                cur_tm = tm;
+                cur_chan = chan;
+                cur_row = m0 + row0;
+                return;
               }
+              mbar_wait(a_empty(sa), pa ^ 1u);
+              mbar_expect_tx(a_full(sa), a_box_bytes(p.seg_taps[seg], 1));
+              tma_load_2d(a_slot(sa), tm, chan, m0 + row0, a_full(sa));
               if (++sa == NA) {
                 sa = 0;
                 pa ^= 1u;
@@ -356,16 +382,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             },
             [&](int, int kb) {
               // first tile: the W boxes of the first stages are already in flight (see above)
-              if (b_issued >= w_prefetched) {
-                mbar_wait(b_empty(sb), pb ^ 1u);
-                if (CG == 2) {
-                  // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
-                  if (cta_rank == 0) mbar_expect_tx(b_full(sb), 2 * L::kBSlotBytes);
-                  tma_load_2d_cg2(b_slot(sb), &tmB, kb * kBlockK, n0, mapa_shared(b_full(sb), 0));
-                } else {
-                  mbar_expect_tx(b_full(sb), L::kBSlotBytes);
-                  tma_load_2d(b_slot(sb), &tmB, kb * kBlockK, n0, b_full(sb));
-                }
+              const bool w_done = b_issued < w_prefetched;
+              if (!w_done) mbar_wait(b_empty(sb), pb ^ 1u);
+              const uint32_t bytes = L::kBSlotBytes + (XF ? 0 : kATileBytes);
+              if (CG == 2) {
+                // both CTAs' boxes complete on the LEADER's barrier; only it arms the count
+                const uint32_t fb = mapa_shared(b_full(sb), 0);
+                if (cta_rank == 0 && !w_done) mbar_expect_tx(b_full(sb), 2 * bytes);
+                if (!XF) tma_load_2d_cg2(a_slot(sb), cur_tm, cur_chan, cur_row, fb);
+                if (!w_done) tma_load_2d_cg2(b_slot(sb), &tmB, kb * kBlockK, n0, fb);
+              } else {
+                if (!w_done) mbar_expect_tx(b_full(sb), bytes);
+                if (!XF) tma_load_2d(a_slot(sb), cur_tm, cur_chan, cur_row, b_full(sb));
+                if (!w_done) tma_load_2d(b_slot(sb), &tmB, kb * kBlockK, n0, b_full(sb));
               }
               ++b_issued;
               if (++sb == NB) {
@@ -390,11 +419,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         walk_tile(
             p,
             [&](int, int, int, int) {
+              if (!XF) return;   // plain: the A box arrives with its W box
               if (a_open) {  // every tap of the previous A block has been issued: free its slot
                 if (CG == 2) umma_commit_cg2(a_empty(cur_a)); else umma_commit(a_empty(cur_a));
               }
-              if (!XF) mbar_wait(a_full(sa), pa);
-              else if (CG == 2) mbar_wait_cluster(a_ready(sa), pa);
+              if (CG == 2) mbar_wait_cluster(a_ready(sa), pa);
               else mbar_wait(a_ready(sa), pa);
               tc_fence_after_sync();
               cur_a = sa;
@@ -407,7 +436,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             [&](int shift, int) {
               mbar_wait(b_full(sb), pb);
               tc_fence_after_sync();
-              const uint64_t adesc = umma_desc_sw128_rows(a_slot(cur_a), (uint32_t)shift);
+              const uint64_t adesc = XF ? umma_desc_sw128_rows(a_slot(cur_a), (uint32_t)shift)
+                                        : umma_desc_sw128_kmajor(a_slot(sb));
               const uint64_t bdesc = umma_desc_sw128_kmajor(b_slot(sb));
 #pragma unroll
               for (int k = 0; k < kBlockK / 16; ++k) {
@@ -432,16 +462,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp < 2 + kXformWarps && XF) {
-    // ------------------------------------------------- operand transform (128 threads)
+  } else if (warp >= kFirstXformWarp && warp < kFirstEpiWarp && XF) {
+    // ------------------------------------------------- operand transform (256 threads)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // One warp per scheduler and no other warp to hide its latencies behind: the loop is laid
     // out for instruction-level parallelism. A thread owns one 16-byte chunk (8 channels) of
-    // the rows rl, rl + 16, ... of every A block of the tile; which of those rows are real
+    // the rows rl, rl + 32, ... of every A block of the tile; which of those rows are real
     // slots, and of which clip, is the same for all blocks of a tile and lives in registers;
-    // rows are processed three at a time with their loads issued up front.
-    const int xt = threadIdx.x - 64;
+    // rows are processed two at a time with their loads issued up front.
+    const int xt = threadIdx.x - 32 * kFirstXformWarp;
     const int chunk = xt & 7;    // 16-byte chunk (8 channels) of a 128-byte operand row
-    const int rl = xt >> 3;      // row lane: rows rl, rl + 16, ...
+    const int rl = xt >> 3;      // row lane: rows rl, rl + 32, ...
     const float* sg = reinterpret_cast<const float*>(smem_gen + L::kGammaOffset);
     float2* mr = reinterpret_cast<float2*>(smem_gen + L::kMrOffset);
     int* row_info = reinterpret_cast<int*>(smem_gen + L::kRowInfoOffset);
@@ -449,8 +480,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // XF launches always share taps: segment 0 is one 130-slot (k3) / 128-slot (k1) block
     const int rows0 = mode0 == LM2A_TAPS_K3 ? 130 : 128;
     const int roff0 = mode0 == LM2A_TAPS_K3 ? -1 : 0;
-    constexpr int kRowsPerThread = 9;   // ceil(130 / 16)
-    // byte offset of this thread's chunk inside row rl (rows rl + 16 k share its swizzle phase)
+    constexpr int kRowsPerThread = 5;   // ceil(130 / 32)
+    // byte offset of this thread's chunk inside row rl (rows rl + 32 k share its swizzle phase)
     const uint32_t thr_off = (uint32_t)rl * 128u + (((uint32_t)(chunk ^ (rl & 7))) << 4);
     uint32_t sa = 0, pa = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
@@ -488,7 +519,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       uint32_t mr_off[kRowsPerThread], keep[kRowsPerThread];
 #pragma unroll
       for (int k = 0; k < kRowsPerThread; ++k) {
-        const int i = rl + 16 * k;
+        const int i = rl + 32 * k;
         const int inf = i < kASlotRows ? row_info[i] : -1;
         keep[k] = inf >= 0 ? 0xffffffffu : 0u;
         mr_off[k] = (uint32_t)((inf > 0 ? inf : 0) * p.gn_groups) * 8u;
@@ -514,23 +545,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
               }
               const uint32_t mr_g = mr_base + g * 8u;
 #pragma unroll
-              for (int k0 = 0; k0 < kRowsPerThread; k0 += 3) {
-                uint32_t w[3][4];
-                float2 sc[3];
+              for (int k0 = 0; k0 < kRowsPerThread; k0 += 2) {
+                uint32_t w[2][4];
+                float2 sc[2];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < 2; ++j) {
+                  if (k0 + j >= kRowsPerThread) continue;
                   // the last row of a thread (rl + 128) exists only for rl < 8: the slot has 136
                   // rows (warp-uniform: a warp holds four consecutive row lanes)
                   if (k0 + j == kRowsPerThread - 1 && rl >= kASlotRows - 128) continue;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                : "=r"(w[j][0]), "=r"(w[j][1]), "=r"(w[j][2]), "=r"(w[j][3])
-                               : "r"(base + (uint32_t)(k0 + j) * 2048u));
+                               : "r"(base + (uint32_t)(k0 + j) * 4096u));
                   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];"
                                : "=f"(sc[j].x), "=f"(sc[j].y)
                                : "r"(mr_g + mr_off[k0 + j]));
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                for (int j = 0; j < 2; ++j) {
+                  if (k0 + j >= kRowsPerThread) continue;
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const float2 x = unpack_bf16x2(w[j][e]);
@@ -540,12 +573,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                   }
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j)
+                for (int j = 0; j < 2; ++j) {
+                  if (k0 + j >= kRowsPerThread) continue;
                   if (!(k0 + j == kRowsPerThread - 1 && rl >= kASlotRows - 128))
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
-                                   base + (uint32_t)(k0 + j) * 2048u),
-                               "r"(w[j][0]), "r"(w[j][1]), "r"(w[j][2]), "r"(w[j][3])
-                               : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                     base + (uint32_t)(k0 + j) * 4096u),
+                                 "r"(w[j][0]), "r"(w[j][1]), "r"(w[j][2]), "r"(w[j][3])
+                                 : "memory");
+                }
               }
               fence_proxy_async_smem();
             }
@@ -558,7 +593,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           },
           [](int, int) {});
     }
-  } else if (warp == 2 + kXformWarps && XF && CG == 2) {
+  } else if (warp == 2 && XF && CG == 2) {
     // --------------------------------------------------------- pair: hand-off warp
     // The leader's MMA reads both CTAs' transformed blocks, so each CTA has to release its
     // block at cluster scope - a fence that costs several hundred cycles. One otherwise idle
@@ -584,6 +619,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     // (plain launches have no such warps)
   } else {
     // ----------------------------------------------------------------- epilogue
+    if (XF) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
     const int ew = warp - kFirstEpiWarp;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int half = ew >> 2;
@@ -639,7 +675,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         __syncwarp();
       }
 
-      mbar_wait_long(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
 
@@ -845,7 +881,7 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
   const int tiles = args.m_tiles * args.n_tiles;
   const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
   const int grid = (tiles < units ? tiles : units) * CG;
-  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF, CG)), L::kBytes, stream,
+  LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF)), L::kBytes, stream,
                                      (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
@@ -902,21 +938,17 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   ConvArgs a{};
   CUtensorMap tmA[2];
   int k_total = 0;
-  // One A block per (segment, 64 channels) serving every tap through row-shifted views, or one
-  // 128-slot box per tap. Launches that normalise their operand on the fly always share (the
-  // transform then runs once per element, not once per tap). Plain launches are MMA-bound, not
-  // load-bound, and measured equal or slightly faster with one box per tap (B200, production
-  // shapes: 50.6 vs 53.7 us at M 8320 x N 1024 x K 3584): their default;
-  // LM2A_CONV_SHARE_TAPS=0|1 overrides it.
-  static const int share_env = [] {
-    const char* e = getenv("LM2A_CONV_SHARE_TAPS");
-    return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
-  }();
+  // Launches that normalise their operand on the fly stage ONE A block per (segment, 64
+  // channels) and serve every tap through row-shifted views of it (the transform then runs once
+  // per element, not once per tap). Plain launches are MMA-bound, not load-bound: measured on
+  // B200 at the production shapes, one 128-slot box per tap riding in the same stage as its W
+  // box (one barrier wait + one commit per K block for the MMA-issuing thread) is equal or
+  // faster than shared blocks with split rings (50.6 vs 53.7 us at M 8320 x N 1024 x K 3584).
   static const int noshift_env = [] {
     const char* e = getenv("LM2A_CONV_DBG_NOSHIFT");
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
-  a.share_taps = d->in_gn_stats != nullptr ? 1 : (share_env >= 0 ? share_env : 0);
+  a.share_taps = d->in_gn_stats != nullptr ? 1 : 0;
   a.dbg_noshift = noshift_env;
   static const int noxform_env = [] {
     const char* e = getenv("LM2A_CONV_DBG_NOXFORM");

@@ -839,21 +839,23 @@ class UNetPlan:
         self.kv_slot.copy_(kv_slot.to(torch.int32))
         self._fill_const_text()
 
-    def run(self):
-        """Launches the plan on torch's current stream. Ops tagged `side` (the uncond rows'
+    def run(self, skip_ingest=False):
+        """Launches the plan on torch's current stream (skip_ingest: the input slab and the
+        cleared statistics arena were already produced by the previous step's lm2a_cfg_step). Ops tagged `side` (the uncond rows'
         `skip(x) + const` kernels and the timestep / FiLM tables: small launches that nothing
         on the main chain needs until the tagged `join` op) go to a second stream, forked from
         and joined back into the current one — under CUDA Graph capture they become a parallel
         branch, off the critical path of the cond rows' pipeline."""
+        todo = [op for op in self.ops if not (skip_ingest and op[2]["kind"] == "ingest_x")]
         if not self.use_side_stream:
-            for fn, args, _ in self.ops:
+            for fn, args, _ in todo:
                 fn(*args)
             return self.eps
         main = torch.cuda.current_stream(self.dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.dev)
         side, pending = self._side, False
-        for fn, args, meta in self.ops:
+        for fn, args, meta in todo:
             if meta.get("side"):
                 side.wait_stream(main)  # fork after everything enqueued so far
                 with torch.cuda.stream(side):

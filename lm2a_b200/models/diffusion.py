@@ -6,9 +6,12 @@ alpha_bars) and methods. `p_sample` / `sample` are the reference's plain DDPM
 reference only has inline for B = 1 (sample.py:144-210): CFG batch doubling, guidance
 blend with both clamps and the posterior update, one CUDA Graph replay per step.
 
-Every tensor op on the path is a C-ABI kernel (lm2a_cfg_posterior + the UNet plan);
-torch is used for memory, RNG draws (torch.randn — the same generator stream the
-reference consumes) and stream / graph plumbing.
+Every tensor op on the path is a C-ABI kernel: the UNet plan plus ONE update kernel per step
+(lm2a_cfg_step: CFG blend, clamps, posterior, noise drawn in the kernel from a per-clip
+counter-based generator, the next step's input slab). torch is used for memory, the per-clip
+seeds (torch.randint on the CPU generator: torch.manual_seed makes a run reproducible) and
+stream / graph plumbing. Injected-noise runs (parity tests) take lm2a_cfg_posterior with the
+caller's tensors instead.
 """
 import os
 
@@ -152,17 +155,21 @@ class GaussianDiffusion:
 
     @torch.no_grad()
     def sample_cfg(self, shape, motion_f, text_f, guidance_weight=1.0, x_init=None, noises=None,
-                   use_graph=True, report=None):
+                   use_graph=True, report=None, clip_seeds=None):
         """Returns the final normalised mel x_0 of shape (B, 80, T).
 
         guidance_weight <= 1 -> plain conditional sampling (sample.py:148-150); otherwise the
         [uncond, cond] doubled batch with the uncond rows attending to zeroed conditions.
         x_init / noises ([steps-1, B, 80, T] or a callable i -> tensor) inject the randomness
-        for parity runs; by default x_T and the per-step noise come from torch.randn on
-        `device` in the reference's order (one draw per step; none consumed at t = 0)."""
+        for parity runs. By default x_T and the per-step noise come from a counter-based
+        generator keyed per clip (lm2a_cfg_step): `clip_seeds` (B int64 values, e.g. derived from
+        the clips' dataset indices) or, if None, seeds drawn with torch.randint - a clip's result
+        then depends on its seed only, not on the batch or GPU it was sampled on. (The reference
+        never seeds torch, sample.py:136,204: there is no generator stream to reproduce.)"""
         bsz, _, t_len = shape
         s = self.sampler(bsz, t_len, motion_f.shape[1], guidance_weight > 1.0)
-        return s.run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report)
+        return s.run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report,
+                     clip_seeds)
 
 
 class CfgSampler:
@@ -183,6 +190,7 @@ class CfgSampler:
         self.plan = eng.plan(rows, t_len, lk, nslots, 2 if guided else 1, True, uniform_t=True,
                              uncond_rows=batch if (guided and uncond_shortcut) else 0)
         self.noise = torch.zeros(batch, eng.pm.in_dim, t_len, dtype=torch.float32, device=self.dev)
+        self.clip_seed = torch.zeros(batch, dtype=torch.int64, device=self.dev)
         self.ticket = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.gw = 1.0
         self.graph = None          # the captured step in effect
@@ -215,6 +223,8 @@ class CfgSampler:
         return self.plan.cond_slabs(1 if self.guided else 0)
 
     def _step(self, draw_noise):
+        """One step with the noise taken from self.noise (injected draws; draw_noise refills it
+        with torch's generator): UNet plan incl. x ingest, then lm2a_cfg_posterior / cfg_ddim."""
         p = self.plan
         if draw_noise:
             self.noise.normal_()
@@ -227,6 +237,24 @@ class CfgSampler:
                          self.t_seq, self.step_idx, p.t_in, self.ticket, self.batch,
                          p.x_in[0].numel(), self.gw, self.guided, True)
 
+    def _fused_step(self):
+        """One DDPM step of the default sampling path: UNet launches (input slab and cleared
+        statistics already in place), then ONE update kernel that blends, updates, injects the
+        per-clip Philox noise, writes the next step's input slab and clears the statistics."""
+        p = self.plan
+        pm = p.pm
+        p.run(skip_ingest=True)
+        ops.cfg_step(p.x_in, p.eps, None, self.clip_seed, self.d.sched, p.t_in, self.ticket,
+                     self.batch, pm.in_dim, self.t_len, self.gw, self.guided, True,
+                     slab=p.x_slab, copies=p.copies, tp=p.geo.Tp[0], ld=pm.in_pad, zero=p.arena)
+
+    def _start_fused(self):
+        """Input slab of the first step + cleared statistics (every later step gets both from
+        the previous step's update kernel)."""
+        p = self.plan
+        ops.ingest_x(p.x_in, p.x_slab, self.batch, p.copies, p.pm.in_dim, self.t_len,
+                     p.geo.Tp[0], p.pm.in_pad, p.arena)
+
     def _reset_clock(self):
         """Device-side step state at the start of a trajectory."""
         if self.ddim is None:
@@ -235,36 +263,46 @@ class CfgSampler:
             self.plan.t_in.fill_(self.taus[0])
             self.step_idx.zero_()
 
-    def _ensure_graph(self):
+    def _ensure_graph(self, fused=None):
         """One captured step per (guidance weight, launch-list variant of the plan: full, or
-        constant lyrics stream — chosen per batch when the conditions are set)."""
+        constant lyrics stream - chosen per batch when the conditions are set, update kernel).
+        fused (default for DDPM): the lm2a_cfg_step path, no library kernel in the graph."""
         p = self.plan
-        key = (self.gw, p.const_text)
+        if fused is None:
+            fused = self.ddim is None
+        key = (self.gw, p.const_text, fused)
+        self.fused = fused
         if key in self._graphs:
             self.graph = self._graphs[key]
             return
-        keep_x = p.x_in.clone()
-        # the warm-up step and the capture below draw from the CUDA generator: put its state
-        # back afterwards, so the trajectory consumes the same noise stream whether or not this
-        # shape has been sampled before (x_T first, then one draw per step)
+        keep_x, keep_t = p.x_in.clone(), p.t_in.clone()
+        # the unfused capture draws from the CUDA generator: put its state back afterwards
         rng_state = torch.cuda.get_rng_state(self.dev)
         if os.environ.get("LM2A_AUTOTUNE", "0") == "1":
-            # measured tile shape per GEMM launch instead of the wave model: opt-in — it raises
-            # the isolated conv throughput (59.7 -> 61.4 % of peak) but not the in-graph step
-            # (2.116 vs 2.103 ms), see DESIGN.md
+            # measured tile shape per GEMM launch instead of the wave model: opt-in, see DESIGN.md
             p.autotune()
         draw = self.ddim is None or self.eta > 0
+
+        def one_step():
+            if fused:
+                self._fused_step()
+            else:
+                self._step(draw)
+
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             self._reset_clock()
-            self._step(draw)  # warm-up outside capture: first-launch attribute setup
+            if fused:
+                self._start_fused()
+            one_step()  # warm-up outside capture: first-launch attribute setup
         torch.cuda.current_stream(self.dev).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         self._reset_clock()
         with torch.cuda.graph(g):
-            self._step(draw)
+            one_step()
         p.x_in.copy_(keep_x)
+        p.t_in.copy_(keep_t)
         self.ticket.zero_()
         torch.cuda.synchronize(self.dev)
         torch.cuda.set_rng_state(rng_state, self.dev)
@@ -272,17 +310,27 @@ class CfgSampler:
 
     @torch.no_grad()
     def run(self, motion_f, text_f, guidance_weight=1.0, x_init=None, noises=None,
-            use_graph=True, report=None):
+            use_graph=True, report=None, clip_seeds=None):
         """motion_f / text_f None: the condition slabs were already filled in place
         (cond_slabs + CondProjection.project_raw); only the K/V caches are (re)built.
-        The captured step draws its noise at every replay, also at t == 0 where the update
-        masks it (GaussianDiffusion.p_sample of the reference does the same, diffusion.py:95;
-        the inline loop of sample.py:203-204 does not): one extra generator advance per
-        trajectory relative to sample.py."""
+        noises given -> injected draws through lm2a_cfg_posterior (parity runs, eager launches).
+        Otherwise DDPM steps run the fused update kernel with per-clip Philox noise
+        (`clip_seeds`, default: torch.randint), x_T from the same generator unless x_init is
+        given; DDIM keeps torch's generator for its (eta > 0) draws."""
         with torch.cuda.device(self.dev):
-            return self._run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report)
+            return self._run(motion_f, text_f, guidance_weight, x_init, noises, use_graph, report,
+                             clip_seeds)
 
-    def _run(self, motion_f, text_f, guidance_weight, x_init, noises, use_graph, report):
+    def set_clip_seeds(self, clip_seeds=None):
+        if clip_seeds is None:
+            clip_seeds = torch.randint(0, 2 ** 62, (self.batch,), dtype=torch.int64)
+        seeds = torch.as_tensor(clip_seeds, dtype=torch.int64).reshape(-1)
+        if seeds.numel() != self.batch:
+            raise RuntimeError(f"clip_seeds must hold {self.batch} values; got {seeds.numel()}")
+        self.clip_seed.copy_(seeds.to(self.dev))
+
+    def _run(self, motion_f, text_f, guidance_weight, x_init, noises, use_graph, report,
+             clip_seeds):
         d, p = self.d, self.plan
         steps = d.T if self.ddim is None else len(self.taus)
         self.gw = float(guidance_weight)
@@ -293,13 +341,19 @@ class CfgSampler:
             p.build_kv(self.kv_slot)
         else:
             self.set_conditions(motion_f, text_f)
-        if x_init is None:
-            x_init = torch.randn((self.batch, p.x_in.shape[1], self.t_len), device=self.dev)
         injected = noises is not None
+        fused = self.ddim is None and not injected
+        if fused or x_init is None:
+            self.set_clip_seeds(clip_seeds)
+        if x_init is None:
+            x_init = torch.empty((self.batch, p.x_in.shape[1], self.t_len), device=self.dev)
+            ops.philox_normal(x_init, self.clip_seed, steps)   # counter word one past t = T-1
         if use_graph and not injected:
-            self._ensure_graph()
+            self._ensure_graph(fused)
         p.x_in.copy_(x_init)
         self._reset_clock()
+        if fused:
+            self._start_fused()
         interval = max(1, steps // 10)
         for i in range(steps):
             if self.ddim is None:
@@ -315,6 +369,8 @@ class CfgSampler:
                 self._step(False)
             elif use_graph:
                 self.graph.replay()
+            elif fused:
+                self._fused_step()
             else:
                 self._step(needs_noise)
             if report is not None and (i % interval == 0 or i == steps - 1):

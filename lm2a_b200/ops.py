@@ -249,6 +249,25 @@ def cfg_posterior(x, eps, noise, sched, t_dev, ticket, batch, elems_per_clip, gu
         1 if advance else 0, _ptr(eps_out)), "lm2a_cfg_posterior")
 
 
+def cfg_step(x, eps, noise, clip_seed, sched, t_dev, ticket, batch, c, t, guidance, guided,
+             advance, slab=None, copies=1, tp=0, ld=0, zero=None, eps_out=None):
+    """The whole per-step update in one launch (see lm2a_cfg_step). zero: StatsArena / tensor."""
+    zt = zero.used() if isinstance(zero, StatsArena) else zero
+    zbytes = 0 if zt is None else zt.numel() * zt.element_size()
+    _lib.check(_lib.load().lm2a_cfg_step(
+        _stream(), _ptr(x), _ptr(eps), _ptr(noise), _ptr(clip_seed), _ptr(sched), _ptr(t_dev),
+        t_dev.numel(), _ptr(ticket), batch, c, t, float(guidance), 1 if guided else 0,
+        1 if advance else 0, _ptr(slab), copies, tp, ld, _ptr(zt), zbytes, _ptr(eps_out)),
+        "lm2a_cfg_step")
+
+
+def philox_normal(out, clip_seed, step):
+    """out fp32 [B, c, t] <- the per-clip Philox normals of counter word `step`."""
+    b, c, t = out.shape
+    _lib.check(_lib.load().lm2a_philox_normal(_stream(), _ptr(out), _ptr(clip_seed), b, c, t,
+                                              int(step)), "lm2a_philox_normal")
+
+
 def cfg_ddim(x, eps, noise, table, t_seq, step_idx, t_dev, ticket, batch, elems_per_clip,
              guidance, guided, advance, x0_out=None):
     _lib.check(_lib.load().lm2a_cfg_ddim(

@@ -56,35 +56,102 @@ def test_short_trajectory_vs_oracle(gw):
         assert cos > 0.999, f"clip {b}: frame cosine {cos:.6f}"
 
 
-def test_graph_replay_equals_eager():
-    """The CUDA-Graph path (noise drawn inside the graph, timestep advanced on device) and the
-    eager path fed the SAME noise give bit-identical trajectories."""
+def test_graph_replay_equals_eager_and_is_shard_invariant():
+    """Default sampling: the CUDA-Graph path (update kernel with in-kernel Philox noise, timestep
+    advanced on device) and the same launches issued eagerly give bit-identical trajectories;
+    a clip's result depends on its seed only, not on the batch it is sampled in."""
     _need_gpu()
     from lm2a_b200.models import GaussianDiffusion
     cfg, sd, net = _b64()
-    steps, bsz, t_len = 6, 2, 72
+    steps, bsz, t_len = 6, 4, 72
     g = torch.Generator().manual_seed(5)
-    x0 = torch.randn(bsz, 80, t_len, generator=g).cuda()
     mf = torch.randn(bsz, t_len, 128, generator=g).cuda()
     tf = torch.randn(bsz, t_len, 128, generator=g).cuda()
+    seeds = [11, 2 ** 40 + 7, 3, 2 ** 61 + 1]
     diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    x_graph = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, clip_seeds=seeds)
     s = diff.sampler(bsz, t_len, t_len, guided=True)
-    s.gw = 2.1
-    s.set_conditions(mf, tf)
-    s._ensure_graph()
-    s.plan.x_in.copy_(x0)
-    s.plan.t_in.fill_(steps - 1)
-    used = []
-    for i in range(steps):
-        s.graph.replay()
-        used.append(s.noise.clone())
-        assert int(s.plan.t_in[0]) == steps - 2 - i
-    x_graph = s.plan.x_in.clone()
-    x_eager = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, x_init=x0, noises=used)
-    assert torch.equal(x_graph, x_eager)
-    # and the public entry point in graph mode runs end to end
-    x_pub = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, x_init=x0)
-    assert torch.isfinite(x_pub).all() and x_pub.shape == x0.shape
+    assert int(s.plan.t_in[0]) == -1 and s.fused          # device clock ran T steps
+    x_eager = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, clip_seeds=seeds, use_graph=False)
+    assert torch.equal(x_graph, x_eager) and torch.isfinite(x_graph).all()
+    # the captured graph holds no library kernel: every launch of a step is one of ours
+    from lm2a_b200 import ops
+    ops.reset_launch_count()
+    diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1, clip_seeds=seeds, use_graph=False)
+    per_step = len(s.plan.ops)          # plan launches minus ingest_x plus the update kernel
+    assert ops.launch_count() == steps * per_step + 2 + len(s.plan.kv_ops) + 2   # + x_T, ingest, K/V
+    # two "shards" (what two GPUs would sample) == the single batch, bit for bit
+    lo = diff.sample_cfg((1, 80, t_len), mf[:1].contiguous(), tf[:1].contiguous(), 2.1,
+                         clip_seeds=seeds[:1])
+    hi = diff.sample_cfg((3, 80, t_len), mf[1:].contiguous(), tf[1:].contiguous(), 2.1,
+                         clip_seeds=seeds[1:])
+    assert torch.equal(torch.cat([lo, hi]), x_graph)
+    # seeds drawn by default: reproducible through torch.manual_seed
+    torch.manual_seed(99)
+    a = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1)
+    torch.manual_seed(99)
+    b = diff.sample_cfg((bsz, 80, t_len), mf, tf, 2.1)
+    assert torch.equal(a, b) and not torch.equal(a, x_graph)
+    # unguided plan through the same path
+    u = diff.sample_cfg((bsz, 80, t_len), mf, tf, 1.0, clip_seeds=seeds)
+    assert torch.isfinite(u).all() and not torch.equal(u, x_graph)
+
+
+def test_step_kernel_equals_posterior_plus_ingest_and_philox_oracle():
+    """lm2a_cfg_step == lm2a_cfg_posterior + lm2a_ingest_x (bit for bit) with injected noise;
+    with a clip seed its noise is exactly lm2a_philox_normal's, which matches the numpy
+    restatement of Philox4x32-10 + Box-Muller (oracle.philox_normal)."""
+    _need_gpu()
+    from lm2a_b200 import ops
+    b, c, t, tp, ld, steps = 3, 80, 77, 80, 128, 50
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn(b, c, t, generator=g, device="cuda")
+    eps = torch.randn(2 * b, c, t, generator=g, device="cuda") * 3
+    noise = torch.randn(b, c, t, generator=g, device="cuda")
+    betas, alphas, abars = orc.diffusion_tables(steps, "cuda")
+    sched = torch.stack([1.0 / alphas.sqrt(), betas / (1.0 - abars).sqrt(), betas.sqrt(),
+                         torch.zeros_like(betas)], dim=1).contiguous()
+    seeds = torch.tensor([5, 2 ** 35 + 9, 2 ** 62 - 1], dtype=torch.int64, device="cuda")
+    for tt in (37, 0):
+        # reference: unfused kernels
+        xa = x.clone()
+        ta = torch.full((2 * b,), tt, dtype=torch.int64, device="cuda")
+        tk = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ops.cfg_posterior(xa, eps, noise, sched, ta, tk, b, c * t, 2.1, True, True)
+        slab_a = torch.full((2 * b * tp, ld), 9.0, dtype=torch.bfloat16, device="cuda")
+        ops.ingest_x(xa, slab_a, b, 2, c, t, tp, ld)
+        # fused, injected noise
+        xb = x.clone()
+        tb = torch.full((2 * b,), tt, dtype=torch.int64, device="cuda")
+        slab_b = torch.full((2 * b * tp, ld), 9.0, dtype=torch.bfloat16, device="cuda")
+        arena = torch.full((64,), 3, dtype=torch.int64, device="cuda")
+        eps_out = torch.zeros(b, c, t, device="cuda")
+        ops.cfg_step(xb, eps, noise, None, sched, tb, tk, b, c, t, 2.1, True, True, slab=slab_b,
+                     copies=2, tp=tp, ld=ld, zero=arena, eps_out=eps_out)
+        torch.cuda.synchronize()
+        assert torch.equal(xa, xb) and torch.equal(slab_a, slab_b)
+        assert bool((arena == 0).all()) and bool((tb == tt - 1).all()) and int(tk) == 0
+        assert torch.equal(eps_out, orc.cfg_eps(eps[:b], eps[b:], 2.1))
+        # fused, in-kernel noise == posterior fed with lm2a_philox_normal's draws
+        z = torch.empty(b, c, t, device="cuda")
+        ops.philox_normal(z, seeds, tt)
+        xc, xd = x.clone(), x.clone()
+        tc = torch.full((2 * b,), tt, dtype=torch.int64, device="cuda")
+        td = tc.clone()
+        ops.cfg_posterior(xc, eps, z, sched, tc, tk, b, c * t, 2.1, True, False)
+        ops.cfg_step(xd, eps, None, seeds, sched, td, tk, b, c, t, 2.1, True, False)
+        torch.cuda.synchronize()
+        assert torch.equal(xc, xd)
+    z = torch.empty(b, c, t, device="cuda")
+    ops.philox_normal(z, seeds, 999)
+    torch.cuda.synchronize()
+    for i in range(b):
+        want = orc.philox_normal(int(seeds[i]), c, t, 999)
+        np.testing.assert_allclose(z[i].cpu().numpy(), want, rtol=0, atol=4e-6)
+    big = torch.empty(8, 80, 516, device="cuda")
+    ops.philox_normal(big, torch.arange(8, dtype=torch.int64, device="cuda"), 1000)
+    assert abs(float(big.mean())) < 5e-3 and abs(float(big.std()) - 1.0) < 5e-3
+    assert abs(float((big[0] * big[1]).mean())) < 1e-2        # clips are independent streams
 
 
 def test_p_sample_matches_oracle():
