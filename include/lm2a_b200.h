@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 8
+#define LM2A_ABI_VERSION 9
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -123,6 +123,14 @@ typedef struct lm2a_conv_desc {
   int32_t in_gn_groups;
   float in_gn_eps;
   int32_t in_gn_silu;       /* must be 1 (GroupNorm without SiLU: lm2a_gn_apply_bf16) */
+  /* Optional x2 linear upsampling (align_corners = True) of seg[0] fused into the
+   * conv (UpSampleConv, unet1d_ultimate.py:210-239): seg[0] then describes the
+   * LOW-resolution slab (rows = m / 2 slots of pitch in_up_tp, in_up_t valid per
+   * clip, k3 taps) and the operand tiles are interpolated from it on the fly -
+   * same arithmetic as lm2a_upsample2x_bf16, so the result is bit-identical to
+   * upsampling first. tp = 2 * in_up_tp, t_valid = 2 * in_up_t. 0 = off.        */
+  int32_t in_up_tp;
+  int32_t in_up_t;
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);

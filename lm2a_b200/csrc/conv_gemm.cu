@@ -97,15 +97,19 @@ struct ConvArgs {
   int gn_pitch, gn_groups, gn_cg;
   unsigned int gn_cg_magic;   // ceil(2^22 / gn_cg): c / gn_cg == (c * magic) >> 22 for c < 2048
   float gn_eps;
+  // x2 linear upsampling (align_corners) of segment 0 on the fly (XF = 2): the low-res slab
+  const __nv_bfloat16* up_src;
+  int up_ld, up_tp_in, up_t_in;
   int share_taps;             // 1: one A block serves all taps (row-shifted views); 0: one
                               //    128-slot box per tap
   int dbg_noshift;            // timing experiments only: every tap reads the unshifted view
   int dbg_noxform;            // timing experiments only: transform warps pass blocks through
 };
 
-// XF: the launch normalises segment 0 on the fly (operand transform warps active). Without it the
-// gamma / beta / statistics tables are not needed and the rings get the space.
-template <int BLOCK_N, int CG, bool XF>
+// XF: the launch builds segment 0's operand tiles on the fly (transform warps active): 1 =
+// GroupNorm + SiLU of the landed tile, 2 = x2 linear upsampling of a lower-resolution slab.
+// Plain launches (0) have no such warps and a single ring of combined stages.
+template <int BLOCK_N, int CG, int XF>
 struct SmemLayout {
   static constexpr int kBSlotBytes = (BLOCK_N / CG) * kBlockK * 2;  // a CTA pair splits W along N
   // XF: a ring of A blocks (136 rows: one box serves every tap) and a ring of W blocks.
@@ -126,9 +130,9 @@ struct SmemLayout {
   // operand transform: gamma | beta of the input GroupNorm, (mean, rstd) per (clip-row, group)
   // of the current tile, clip-row index of every slot of the A block
   static constexpr int kGammaOffset = kTabOffset + kEpiWarps * kTabBytesPerWarp;
-  static constexpr int kMrOffset = kGammaOffset + (XF ? 2 * kMaxGnChannels * 4 : 0);
-  static constexpr int kRowInfoOffset = kMrOffset + (XF ? kMaxGnEntries * 8 : 0);
-  static constexpr int kBarOffset = kRowInfoOffset + (XF ? kASlotRows * 4 : 0);
+  static constexpr int kMrOffset = kGammaOffset + (XF == 1 ? 2 * kMaxGnChannels * 4 : 0);
+  static constexpr int kRowInfoOffset = kMrOffset + (XF == 1 ? kMaxGnEntries * 8 : 0);
+  static constexpr int kBarOffset = kRowInfoOffset + (XF == 1 ? kASlotRows * 4 : 0);
   static constexpr int kNumBars = 4 * kAStages + 2 * kBStages + 4;
   static constexpr int kBytes = kBarOffset + 8 * kNumBars + 16 + 1024;  // + tmem slot + align
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
@@ -241,7 +245,7 @@ __device__ __forceinline__ uint32_t a_box_bytes(int mode, int share_taps) {
   return (uint32_t)rows * kBlockK * 2;
 }
 
-template <int BLOCK_N, int CG, bool XF>
+template <int BLOCK_N, int CG, int XF>
 __global__ void __launch_bounds__(num_threads(XF), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                  const __grid_constant__ CUtensorMap tmA1,
@@ -275,7 +279,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int num_units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
   // XF launches hand every A block to the transform warps (a_full -> transform / pass-through
   // -> a_ready); plain launches let the TMA complete straight on the barrier the MMA waits on
-  constexpr bool xform = XF;
+  constexpr bool xform = XF == 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -373,8 +377,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                 return;
               }
               mbar_wait(a_empty(sa), pa ^ 1u);
-              mbar_expect_tx(a_full(sa), a_box_bytes(p.seg_taps[seg], 1));
-              tma_load_2d(a_slot(sa), tm, chan, m0 + row0, a_full(sa));
+              if (XF == 2 && seg == 0) {
+                // the transform warps build this block themselves: the slot is theirs now
+                mbar_arrive(a_full(sa));
+              } else {
+                mbar_expect_tx(a_full(sa), a_box_bytes(p.seg_taps[seg], 1));
+                tma_load_2d(a_slot(sa), tm, chan, m0 + row0, a_full(sa));
+              }
               if (++sa == NA) {
                 sa = 0;
                 pa ^= 1u;
@@ -483,6 +492,86 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     constexpr int kRowsPerThread = 5;   // ceil(130 / 32)
     // byte offset of this thread's chunk inside row rl (rows rl + 32 k share its swizzle phase)
     const uint32_t thr_off = (uint32_t)rl * 128u + (((uint32_t)(chunk ^ (rl & 7))) << 4);
+    if constexpr (XF == 2) {
+      // ---- x2 linear upsampling, align_corners = True (F.interpolate of reference
+      // unet1d_ultimate.py:231-236) of the low-resolution slab straight into the operand block:
+      // out slot t of a clip reads low slots i0 = floor(t * (T-1)/(2T-1)) and min(i0+1, T-1) with
+      // weights (1 - w, w); slots t >= 2T stay zero (F.pad, :409-413). The arithmetic is
+      // upsample2x_kernel's, so fusing does not change a bit.
+      const __nv_bfloat16* src = p.up_src + chunk * 8;
+      const int t_in = p.up_t_in;
+      const float scale = p.t_valid > 1 ? (float)(t_in - 1) / (float)(p.t_valid - 1) : 0.f;
+      uint32_t sa = 0, pa = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        const int m_base = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM + roff0;
+        // per row of this thread: element offsets of its two source slots, the lerp weight and
+        // the store mask (same for every channel block of the tile)
+        uint32_t off0[kRowsPerThread], off1[kRowsPerThread], keep[kRowsPerThread];
+        float w1[kRowsPerThread];
+#pragma unroll
+        for (int k = 0; k < kRowsPerThread; ++k) {
+          const long long m = (long long)m_base + rl + 32 * k;
+          keep[k] = 0u;
+          off0[k] = off1[k] = 0u;
+          w1[k] = 0.f;
+          if (rl + 32 * k < rows0 && m >= 0 && m < p.m) {
+            const int r = (int)m / p.tp;
+            const int t = (int)m - r * p.tp;
+            if (t < p.t_valid) {
+              const float sp = scale * (float)t;
+              const int i0 = (int)sp;
+              const int i1 = i0 + (i0 < t_in - 1 ? 1 : 0);
+              w1[k] = sp - (float)i0;
+              off0[k] = (uint32_t)((r * p.up_tp_in + i0) * p.up_ld);
+              off1[k] = (uint32_t)((r * p.up_tp_in + i1) * p.up_ld);
+              keep[k] = 0xffffffffu;
+            }
+          }
+        }
+        walk_tile(
+            p,
+            [&](int seg, int cb, int, int) {
+              mbar_wait(a_full(sa), pa);
+              if (seg == 0) {
+                const uint32_t base = a_slot(sa) + thr_off;
+                const __nv_bfloat16* sc = src + cb * kBlockK;
+                uint4 qa[kRowsPerThread], qb[kRowsPerThread];
+#pragma unroll
+                for (int k = 0; k < kRowsPerThread; ++k) {
+                  qa[k] = __ldg(reinterpret_cast<const uint4*>(sc + off0[k]));
+                  qb[k] = __ldg(reinterpret_cast<const uint4*>(sc + off1[k]));
+                }
+#pragma unroll
+                for (int k = 0; k < kRowsPerThread; ++k) {
+                  if (k == kRowsPerThread - 1 && rl >= kASlotRows - 128) continue;
+                  const float wb = w1[k], wa = 1.0f - wb;
+                  const uint32_t aw[4] = {qa[k].x, qa[k].y, qa[k].z, qa[k].w};
+                  const uint32_t bw[4] = {qb[k].x, qb[k].y, qb[k].z, qb[k].w};
+                  uint32_t ow[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 fa = unpack_bf16x2(aw[e]);
+                    const float2 fb = unpack_bf16x2(bw[e]);
+                    ow[e] = pack_bf16x2(__fmaf_rn(wb, fb.x, __fmul_rn(wa, fa.x)),
+                                        __fmaf_rn(wb, fb.y, __fmul_rn(wa, fa.y))) & keep[k];
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                                   base + (uint32_t)k * 4096u),
+                               "r"(ow[0]), "r"(ow[1]), "r"(ow[2]), "r"(ow[3])
+                               : "memory");
+                }
+                fence_proxy_async_smem();
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(CG == 2 ? x_done(sa) : a_ready(sa));
+              if (++sa == NA) {
+                sa = 0;
+                pa ^= 1u;
+              }
+            },
+            [](int, int) {});
+      }
+    } else {
     uint32_t sa = 0, pa = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_base = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM + roff0;
@@ -593,6 +682,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
           },
           [](int, int) {});
     }
+    }  // XF == 1
   } else if (warp == 2 && XF && CG == 2) {
     // --------------------------------------------------------- pair: hand-off warp
     // The leader's MMA reads both CTAs' transformed blocks, so each CTA has to release its
@@ -869,7 +959,7 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-template <int BLOCK_N, int CG, bool XF>
+template <int BLOCK_N, int CG, int XF>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
            const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
   using L = SmemLayout<BLOCK_N, CG, XF>;
@@ -948,7 +1038,8 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     const char* e = getenv("LM2A_CONV_DBG_NOSHIFT");
     return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
-  a.share_taps = d->in_gn_stats != nullptr ? 1 : 0;
+  const bool up2x = d->in_up_t > 0;
+  a.share_taps = (d->in_gn_stats != nullptr || up2x) ? 1 : 0;
   a.dbg_noshift = noshift_env;
   static const int noxform_env = [] {
     const char* e = getenv("LM2A_CONV_DBG_NOXFORM");
@@ -975,6 +1066,23 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     a.seg_cblk[s] = g.cin / 64;
     a.seg_taps[s] = g.taps;
     int ntaps = 1;
+    if (s == 0 && up2x) {
+      // seg[0] is the LOW-resolution slab: the operand tiles are interpolated from it by the
+      // transform warps (no tensor map; a placeholder keeps the kernel signature uniform)
+      LM2A_REQUIRE(g.taps == LM2A_TAPS_K3 && 2 * g.rows == d->m && d->tp == 2 * d->in_up_tp &&
+                       d->t_valid == 2 * d->in_up_t && d->in_up_t <= d->in_up_tp &&
+                       d->in_gn_stats == nullptr,
+                   "conv1d: fused x2 upsampling needs a k3 segment over the low-res slab with "
+                   "m = 2 * rows, tp = 2 * in_up_tp, t_valid = 2 * in_up_t and no input GroupNorm");
+      LM2A_REQUIRE(g.rows * (long long)g.ld < (1ll << 31), "conv1d: low-res slab too large");
+      a.seg_half[s] = 0;
+      a.up_src = reinterpret_cast<const __nv_bfloat16*>(g.x);
+      a.up_ld = g.ld;
+      a.up_tp_in = d->in_up_tp;
+      a.up_t_in = d->in_up_t;
+      k_total += 3 * g.cin;
+      continue;
+    }
     if (g.taps == LM2A_TAPS_K4S2) {
       LM2A_REQUIRE(g.rows == 2 * d->m,
                    "conv1d: k4s2 needs input slots (%lld) == 2 * output slots (%lld)",
@@ -1032,6 +1140,10 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
                 (uint32_t)(block_n / cg)))
     return 1;
 
+  if (up2x) {
+    tmA[0] = tmB;
+    if (d->seg[1].x == nullptr) tmA[1] = tmB;
+  }
   a.m_tiles = (int)((d->m + kBlockM * cg - 1) / (kBlockM * cg));
   a.n_tiles = d->n_pad / block_n;
   a.m = d->m;
@@ -1112,17 +1224,12 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   if (d->out_mode == LM2A_OUT_BF16_SLAB &&
       encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
     return 1;
-  const bool xf = a.gn_stats != nullptr;
-  if (cg == 2) {
-    if (block_n == 256)
-      return xf ? launch<256, 2, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
-                : launch<256, 2, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
-    return xf ? launch<128, 2, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
-              : launch<128, 2, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
-  }
-  if (block_n == 256)
-    return xf ? launch<256, 1, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
-              : launch<256, 1, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
-  return xf ? launch<128, 1, true>(st, tmA[0], tmA[1], tmB, tmOut, a)
-            : launch<128, 1, false>(st, tmA[0], tmA[1], tmB, tmOut, a);
+  const int xf = a.gn_stats != nullptr ? 1 : (a.up_src != nullptr ? 2 : 0);
+#define LM2A_CONV_LAUNCH(BN, CGV)                                                         \
+  (xf == 1 ? launch<BN, CGV, 1>(st, tmA[0], tmA[1], tmB, tmOut, a)                        \
+           : (xf == 2 ? launch<BN, CGV, 2>(st, tmA[0], tmA[1], tmB, tmOut, a)             \
+                      : launch<BN, CGV, 0>(st, tmA[0], tmA[1], tmB, tmOut, a)))
+  if (cg == 2) return block_n == 256 ? LM2A_CONV_LAUNCH(256, 2) : LM2A_CONV_LAUNCH(128, 2);
+  return block_n == 256 ? LM2A_CONV_LAUNCH(256, 1) : LM2A_CONV_LAUNCH(128, 1);
+#undef LM2A_CONV_LAUNCH
 }

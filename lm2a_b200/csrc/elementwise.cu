@@ -150,7 +150,9 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, __nv_bfloat16* 
     for (int e = 0; e < 4; ++e) {
       const float2 fa = unpack_bf16x2(aw[e]);
       const float2 fb = unpack_bf16x2(bw[e]);
-      ow[e] = pack_bf16x2(w0 * fa.x + w1 * fb.x, w0 * fa.y + w1 * fb.y);
+      // explicit rounding order (shared with the conv's fused upsampling: bit-identical)
+      ow[e] = pack_bf16x2(__fmaf_rn(w1, fb.x, __fmul_rn(w0, fa.x)),
+                          __fmaf_rn(w1, fb.y, __fmul_rn(w0, fa.y)));
     }
     o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }

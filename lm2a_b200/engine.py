@@ -342,7 +342,7 @@ class UNetPlan:
         # scratch slabs shared by all blocks (sized for the largest level)
         cmax = max(g.M[lvl] * pm.scratch_width(lvl) for lvl in range(n_down + 1))
         flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
-        self._h1, self._q, self._o, self._xup = flat(), flat(), flat(), flat()
+        self._h1, self._q, self._o = flat(), flat(), flat()
         self._flat = flat
         self._norm = None   # only for clips too short for the conv's operand transform
         # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
@@ -429,7 +429,8 @@ class UNetPlan:
         executed = 2 * (m // tp) * t_valid * n_valid * k_total
         flops = min(executed, k.pop("flops_alg", None) or executed)
         meta = {"kind": "conv_gemm", "flops": flops, "flops_executed": executed,
-                "m": m, "n": n_valid, "k": k_total, "in_gn": k.get("in_gn") is not None}
+                "m": m, "n": n_valid, "k": k_total, "in_gn": k.get("in_gn") is not None,
+                "up2x": k.get("up2x") is not None}
         self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
                   meta=meta)
 
@@ -764,11 +765,11 @@ class UNetPlan:
             dim = pm.dims[lvl]
             t_up = 2 * g.T[lvl + 1]
             assert t_up <= g.T[lvl]
-            xup = self._view(self._xup, g.M[lvl], cur_c)
-            self._add(ops.upsample2x, cur, cur_c, xup, cur_c, rows, g.Tp[lvl + 1], g.T[lvl + 1],
-                      g.Tp[lvl], cur_c)
-            self._conv([Seg(xup, cur_c, cur_c, TAPS_K3, g.M[lvl])], wu, bu, dim, g.M[lvl],
-                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim, stats=self.cat_st[lvl].view(0, 0))
+            # UpSampleConv: the x2 linear interpolation happens in the conv's operand path (the
+            # transform warps build each operand block from the low-resolution slab)
+            self._conv([Seg(cur, cur_c, cur_c, TAPS_K3, g.M[lvl + 1])], wu, bu, dim, g.M[lvl],
+                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim, stats=self.cat_st[lvl].view(0, 0),
+                       up2x=(g.Tp[lvl + 1], g.T[lvl + 1]))
             cur, cur_ld, cur_c, cur_st = self.cat[lvl], 2 * dim, 2 * dim, self.cat_st[lvl]
             for bi, p in enumerate(blocks):
                 out = self._view(self._pp[pp], g.M[lvl], p.cout)

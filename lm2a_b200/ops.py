@@ -126,11 +126,13 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
                    res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0,
-                   in_gn=None):
+                   in_gn=None, up2x=None):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object.
     in_gn = (Stats view of segs[0]'s slab, gamma, beta, eps, silu): GroupNorm (+ SiLU) applied to
-    the first segment's operand tiles on the fly."""
+    the first segment's operand tiles on the fly.
+    up2x = (tp_in, t_in): segs[0] is the LOW-resolution slab (rows = m / 2); its x2 linear
+    upsampling (align_corners) is computed inside the conv's operand path."""
     d = ConvDesc()
     for i, s in enumerate(segs):
         d.seg[i].x = s.slab.data_ptr() + s.chan_off * 2
@@ -167,6 +169,8 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
         d.in_gn_gamma, d.in_gn_beta = gamma.data_ptr(), beta.data_ptr()
         d.in_gn_pitch, d.in_gn_groups = st.groups, st.groups
         d.in_gn_eps, d.in_gn_silu = eps, 1 if silu else 0
+    if up2x is not None:
+        d.in_up_tp, d.in_up_t = up2x
     d._keep = (segs, w, bias, film, residual, out, stats, in_gn)
     return d
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_conv_desc_struct_matches_header_layout():
     from lm2a_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSeg) == 32
-    assert ctypes.sizeof(_lib.ConvDesc) == 216
+    assert ctypes.sizeof(_lib.ConvDesc) == 224
     assert _lib.ConvDesc.out.offset == 136 and _lib.ConvDesc.m.offset == 80
     assert _lib.ConvDesc.stats.offset == 152 and _lib.ConvDesc.in_gn_stats.offset == 176
 
@@ -88,7 +88,9 @@ def test_geometry_and_plan():
     assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 0
     assert sum(1 for _, _, m in plan.ops if m.get("in_gn")) == 31
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
-    assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 62
+    assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 59
+    # the x2 interpolation of the three UpSampleConvs runs inside their convs
+    assert kinds.count("upsample2x") == 0 and sum(1 for _, _, m in plan.ops if m.get("up2x")) == 3
     # (clips too short for the operand transform would fall back to the stand-alone gn_apply
     # pass; with <= 8 groups every clip length the geometry admits is long enough)
     from lm2a_b200 import ops as _ops
@@ -102,7 +104,7 @@ def test_geometry_and_plan():
     # production CFG step (B = 32, uncond shortcut, shared leading rows): 71 launches
     cfgp = UNetPlan(big, 64, 516, 516, 33, 2, True, torch.device("cpu"), uniform_t=True,
                     uncond_rows=32)
-    assert len(cfgp.ops) == 71 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
+    assert len(cfgp.ops) == 68 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
     with pytest.raises(RuntimeError, match="multiples of 64"):
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 

@@ -328,6 +328,48 @@ def test_conv_groupnorm_operand_variants(ops, cta_group):
     _gn_input_case(ops, 2, 130, 132, 2048, 256, 8, ops.TAPS_K3, 0, cta_group, 256)
 
 
+@pytest.mark.parametrize("block_n,cta_group", [(0, 0), (256, 1), (128, 2)])
+@pytest.mark.parametrize("r,t_in,cin,cout", [(3, 129, 256, 128), (64, 64, 1024, 1024),
+                                              (5, 258, 512, 256), (2, 20, 64, 128)])
+def test_conv_fused_upsampling(ops, r, t_in, cin, cout, block_n, cta_group):
+    """UpSampleConv (unet1d_ultimate.py:210-239): x2 linear interpolation (align_corners) fused
+    into the k3 conv's operand path == upsample2x kernel followed by the plain conv, bit for bit,
+    and == F.interpolate + F.conv1d within bf16 tolerance. The output slab is one slot longer
+    than 2 * t_in per clip (the skip's length): those slots must come out as conv-of-zero-pad."""
+    if block_n and ((cout + 127) // 128 * 128) % block_n:
+        pytest.skip("block_n does not divide n_pad")
+    tp_in = t_in + 1
+    tp_out = 2 * tp_in
+    t_up = 2 * t_in
+    x = rnd(r, cin, t_in, seed=90)
+    w = rnd(cout, cin, 3, scale=1 / math.sqrt(3 * cin), seed=91)
+    b = rnd(cout, scale=0.2, seed=92)
+    xs = to_slab(x, tp_in)
+    n_pad = (cout + 127) // 128 * 128
+    st = ops.Stats(r, cout, 8, "cuda")
+    out = torch.full((r * tp_out, cout), 7.0, dtype=BF16, device="cuda")
+    d = ops.make_conv_desc([ops.Seg(xs, cin, cin, ops.TAPS_K3, r * tp_in)], pack_w(w),
+                           pad_bias(b, n_pad), cout, r * tp_out, tp_out, t_up, out, cout, stats=st,
+                           block_n=block_n, cta_group=cta_group, up2x=(tp_in, t_in))
+    ops.conv1d(d)
+    # unfused: upsample kernel -> plain conv
+    up = torch.zeros(r * tp_out, cin, dtype=BF16, device="cuda")
+    ops.upsample2x(xs, cin, up, cin, r, tp_in, t_in, tp_out, cin)
+    st2 = ops.Stats(r, cout, 8, "cuda")
+    out2 = torch.full((r * tp_out, cout), 7.0, dtype=BF16, device="cuda")
+    d2 = ops.make_conv_desc([ops.Seg(up, cin, cin, ops.TAPS_K3, r * tp_out)], pack_w(w),
+                            pad_bias(b, n_pad), cout, r * tp_out, tp_out, t_up, out2, cout,
+                            stats=st2, block_n=block_n, cta_group=cta_group)
+    ops.conv1d(d2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2), "fused upsampling differs from upsample2x + conv"
+    assert torch.equal(st.buf, st2.buf)
+    ref = F.conv1d(bf(F.interpolate(bf(x), scale_factor=2, mode="linear", align_corners=True)),
+                   bf(w), b, padding=1)
+    assert_close(from_slab(out, r, tp_out, t_up, cout), ref, 8e-3, "fused upsample + conv")
+    assert pads_are_zero(out, r, tp_out, t_up)
+
+
 def test_conv_groupnorm_operand_rejects_unsupported(ops):
     x = torch.zeros(64 * 2, 64, dtype=BF16, device="cuda")
     w = torch.zeros(128, 192, dtype=BF16, device="cuda")
