@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 9
+#define LM2A_ABI_VERSION 10
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -97,8 +97,9 @@ typedef struct lm2a_conv_desc {
    * (clip-row r relative to this launch, group g = (stats_c0 + c) / stats_cg of
    * output channel c relative to `out`) at stats[(r * stats_pitch + g) * 2 + {0, 1}] =
    * {sum * 2^24, sum of squares * 2^20} in fixed point. Each lane converts the fp32
-   * sums of its own slot and the rest is integer addition (shuffle tree + one
-   * atomic per (clip-row, group) and warp), so the totals are exact and do not
+   * sums of its own slot and the rest is integer addition (per-lane running sums,
+   * hardware warp reductions, one atomic per (clip-row, group) and warp), so the
+   * totals are exact and do not
    * depend on tile shape, batch position or sharding. The buffer must be ZERO when
    * the first producer of a step runs (lm2a_ingest_x clears a region for this). */
   void* stats;
@@ -131,6 +132,12 @@ typedef struct lm2a_conv_desc {
    * upsampling first. tp = 2 * in_up_tp, t_valid = 2 * in_up_t. 0 = off.        */
   int32_t in_up_tp;
   int32_t in_up_t;
+  /* K walk order of launches without an operand transform: 0 = taps outer, channel
+   * blocks inner (default, fastest); 1 = channel blocks outer, taps inner - the order
+   * the in_gn_* / in_up_* launches accumulate in, so that a plain launch over a
+   * pre-normalised / pre-upsampled slab reproduces them bit for bit.              */
+  int32_t k_order;
+  int32_t _pad0;
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);

@@ -322,89 +322,59 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         for (int c = 0; c < NC; ++c)
           if (c >= keys) s[c] = -INFINITY;
       }
-      // Fast path (every tile but the first): exponentiate against the stale running max right
-      // away and let the row sum tell whether that was legitimate. p >= 0, so sum <= 2^8 implies
-      // every p <= 2^8, i.e. no score exceeds the stale max by more than the rescale threshold -
-      // exactly the condition under which the exact path below would not have touched the max.
-      // The 64 max operations, their reduction and the compare leave the common path; a tile that
-      // fails the test (the first tiles of a row, peaked rows) is redone by the exact path, so the
-      // result is bit-identical to always taking it. NaN scores fail the test too.
-      uint32_t pk[NC / 2];
-      float tile_sum = 0.f;
-      bool exact = j == 0;
-      if (!exact) {
-        float suma[4] = {0.f, 0.f, 0.f, 0.f};
+      float mxa[4] = {s[0], s[1], s[2], s[3]};  // four independent chains
 #pragma unroll
-        for (int c = 0; c < NC / 8; ++c) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float p0 = ex2_approx(s[c * 8 + 2 * i] - m_used);
-            const float p1 = ex2_approx(s[c * 8 + 2 * i + 1] - m_used);
-            suma[i] += p0 + p1;
-            pk[c * 4 + i] = pack_bf16x2(p0, p1);
-          }
-        }
-        tile_sum = (suma[0] + suma[1]) + (suma[2] + suma[3]);
-        exact = __any_sync(0xffffffffu, !(tile_sum <= 256.0f));
+      for (int c = 4; c < NC; c += 4) {
+        mxa[0] = fmaxf(mxa[0], s[c]);
+        mxa[1] = fmaxf(mxa[1], s[c + 1]);
+        mxa[2] = fmaxf(mxa[2], s[c + 2]);
+        mxa[3] = fmaxf(mxa[3], s[c + 3]);
       }
-      if (exact) {
-        float mxa[4] = {s[0], s[1], s[2], s[3]};  // four independent chains
-#pragma unroll
-        for (int c = 4; c < NC; c += 4) {
-          mxa[0] = fmaxf(mxa[0], s[c]);
-          mxa[1] = fmaxf(mxa[1], s[c + 1]);
-          mxa[2] = fmaxf(mxa[2], s[c + 2]);
-          mxa[3] = fmaxf(mxa[3], s[c + 3]);
-        }
-        const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
+      const float mx = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3]));
 
-        // lazy rescale: keep the stale max while the new one is within 2^8 of it
-        const bool grow = mx > m_used + kRescaleThreshold;
-        float corr = 1.0f;
-        if (grow) {
-          corr = ex2_approx(m_used - mx);  // first tile: exp2(-inf) = 0
-          m_used = mx;
-          l_run *= corr;
+      // lazy rescale: keep the stale max while the new one is within 2^8 of it
+      const bool grow = mx > m_used + kRescaleThreshold;
+      float corr = 1.0f;
+      if (grow) {
+        corr = ex2_approx(m_used - mx);  // first tile: exp2(-inf) = 0
+        m_used = mx;
+        l_run *= corr;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        mbar_wait(pv_done((j - 1) % PB), (uint32_t)((j - 1) / PB) & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int c0 = 0; c0 < DH; c0 += 32) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_o + lane_off + c0, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
+          tmem_st_32x32(tmem_o + lane_off + c0, ov);
         }
-        if (j > 0 && __any_sync(0xffffffffu, grow)) {
-          mbar_wait(pv_done((j - 1) % PB), (uint32_t)((j - 1) / PB) & 1u);
-          tc_fence_after_sync();
-#pragma unroll
-          for (int c0 = 0; c0 < DH; c0 += 32) {
-            uint32_t ov[32];
-            tmem_ld_32x32(tmem_o + lane_off + c0, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
-            tmem_st_32x32(tmem_o + lane_off + c0, ov);
-          }
-          tmem_st_wait();
-        }
-        float suma[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < NC / 8; ++c) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float p0 = ex2_approx(s[c * 8 + 2 * i] - m_used);
-            const float p1 = ex2_approx(s[c * 8 + 2 * i + 1] - m_used);
-            suma[i] += p0 + p1;
-            pk[c * 4 + i] = pack_bf16x2(p0, p1);
-          }
-        }
-        tile_sum = (suma[0] + suma[1]) + (suma[2] + suma[3]);
+        tmem_st_wait();
       }
 
       // the P tile slot is free once P_{j-PB} V_{j-PB} has completed
       if (j >= PB) mbar_wait(pv_done(pb), (uint32_t)(j / PB - 1) & 1u);
       const uint32_t pbase = p_tile(pb) + p_row;
+      float suma[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < NC / 8; ++c) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = ex2_approx(s[c * 8 + 2 * i] - m_used);
+          const float p1 = ex2_approx(s[c * 8 + 2 * i + 1] - m_used);
+          suma[i] += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
         const uint32_t addr = pbase + (((uint32_t)c ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c * 4]),
-                     "r"(pk[c * 4 + 1]), "r"(pk[c * 4 + 2]), "r"(pk[c * 4 + 3])
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]),
+                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
       }
-      l_run += tile_sum;
+      l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
       fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive(p_full(pb));

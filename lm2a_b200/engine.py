@@ -344,7 +344,10 @@ class UNetPlan:
         flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
         self._h1, self._q, self._o = flat(), flat(), flat()
         self._flat = flat
-        self._norm = None   # only for clips too short for the conv's operand transform
+        self._norm = None   # normalised operands of the launches that do not transform in-kernel
+        # widest operand (channels) normalised / upsampled inside the consuming conv
+        self.xf_max_c = int(os.environ.get("LM2A_XF_MAX_C", "512"))
+        self.up_xf_max_c = int(os.environ.get("LM2A_UP_XF_MAX_C", "512"))
         # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
         # kernel (ingest_x) clears; the epilogues accumulate exact integer sums into it
         self.arena = ops.StatsArena(dev, (2 * pm.n_groupnorms + 16) * rows * pm.max_groups * 2)
@@ -447,11 +450,16 @@ class UNetPlan:
         return st
 
     def _gn_operand(self, x, x_ld, x_off, x_st, gn, nr, tp, tv, c):
-        """Input of a conv that follows GroupNorm + SiLU: (slab, ld, element offset, in_gn). The
-        normalisation runs inside the conv (operand transform); clips too short for it go
-        through a stand-alone gn_apply into a scratch slab."""
+        """Input of a conv that follows GroupNorm + SiLU: (slab, ld, element offset, in_gn).
+        Narrow operands (c <= xf_max_c) are normalised inside the conv (operand transform: the
+        launch is load- / latency-bound there and the transform is free); wide operands feed
+        MMA-bound GEMMs, where the transform's shared-memory traffic costs more than one
+        streaming gn_apply pass in front of a plain launch (measured per level on B200, see
+        DESIGN.md). Both paths evaluate the same arithmetic from the same exact sums: the
+        choice does not change a bit of the result. Clips too short for the transform also take
+        the stand-alone pass."""
         gm, bt, groups, eps = gn
-        if ops.in_gn_supported(tp, groups):
+        if c <= self.xf_max_c and ops.in_gn_supported(tp, groups):
             return x, x_ld, x_off, (x_st, gm, bt, eps, True)
         if self._norm is None:
             self._norm = [self._flat(), self._flat()]
@@ -765,11 +773,21 @@ class UNetPlan:
             dim = pm.dims[lvl]
             t_up = 2 * g.T[lvl + 1]
             assert t_up <= g.T[lvl]
-            # UpSampleConv: the x2 linear interpolation happens in the conv's operand path (the
-            # transform warps build each operand block from the low-resolution slab)
-            self._conv([Seg(cur, cur_c, cur_c, TAPS_K3, g.M[lvl + 1])], wu, bu, dim, g.M[lvl],
-                       g.Tp[lvl], t_up, self.cat[lvl], 2 * dim, stats=self.cat_st[lvl].view(0, 0),
-                       up2x=(g.Tp[lvl + 1], g.T[lvl + 1]))
+            # UpSampleConv: narrow levels interpolate x2 in the conv's operand path (the
+            # transform warps build each operand block from the low-resolution slab); wide levels
+            # (MMA-bound up-conv) take one streaming upsample pass and a plain launch. Same
+            # arithmetic either way.
+            if cur_c <= self.up_xf_max_c:
+                self._conv([Seg(cur, cur_c, cur_c, TAPS_K3, g.M[lvl + 1])], wu, bu, dim, g.M[lvl],
+                           g.Tp[lvl], t_up, self.cat[lvl], 2 * dim,
+                           stats=self.cat_st[lvl].view(0, 0), up2x=(g.Tp[lvl + 1], g.T[lvl + 1]))
+            else:
+                xup = self._view(self._h1, g.M[lvl], cur_c)
+                self._add(ops.upsample2x, cur, cur_c, xup, cur_c, rows, g.Tp[lvl + 1],
+                          g.T[lvl + 1], g.Tp[lvl], cur_c, meta={"kind": "upsample2x", "flops": 0})
+                self._conv([Seg(xup, cur_c, cur_c, TAPS_K3, g.M[lvl])], wu, bu, dim, g.M[lvl],
+                           g.Tp[lvl], t_up, self.cat[lvl], 2 * dim,
+                           stats=self.cat_st[lvl].view(0, 0))
             cur, cur_ld, cur_c, cur_st = self.cat[lvl], 2 * dim, 2 * dim, self.cat_st[lvl]
             for bi, p in enumerate(blocks):
                 out = self._view(self._pp[pp], g.M[lvl], p.cout)

@@ -101,10 +101,15 @@ def test_geometry_and_plan():
     bp = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu"))
     assert abs(bp.flops() / 2 / 1e9 - 28.23) < 0.02
     assert abs(sum(m.get("flops_executed", m["flops"]) for _, _, m in bp.ops) / 2 / 1e9 - 29.58) < 0.02
-    # production CFG step (B = 32, uncond shortcut, shared leading rows): 71 launches
+    # production CFG step (B = 32, uncond shortcut, shared leading rows): operands up to 512
+    # channels are normalised / upsampled inside their conv (17 + 1 launches), the wider ones
+    # (MMA-bound GEMMs) by 14 streaming gn_apply and 2 upsample2x passes in front of plain launches
     cfgp = UNetPlan(big, 64, 516, 516, 33, 2, True, torch.device("cpu"), uniform_t=True,
                     uncond_rows=32)
-    assert len(cfgp.ops) == 68 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
+    ck = [m["kind"] for _, _, m in cfgp.ops]
+    assert len(cfgp.ops) == 84 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
+    assert ck.count("gn_apply") == 14 and ck.count("upsample2x") == 2
+    assert sum(1 for _, _, m in cfgp.ops if m.get("in_gn")) == 17
     with pytest.raises(RuntimeError, match="multiples of 64"):
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 

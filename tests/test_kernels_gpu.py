@@ -296,7 +296,8 @@ def _gn_input_case(ops, r, t, tp, cin, cout, groups, taps, r0, cta_group, block_
     segs2 = [ops.Seg(norm, cin, cin, taps, nr * tp, chan_off=r0 * tp * cin)] + segs[1:]
     out2 = torch.full((r * tp, cout), 7.0, dtype=BF16, device="cuda")
     d2 = ops.make_conv_desc(segs2, wk, pad_bias(b, n_pad), cout, nr * tp, tp, t, out2, cout,
-                            out_chan_off=r0 * tp * cout, block_n=block_n, cta_group=cta_group)
+                            out_chan_off=r0 * tp * cout, block_n=block_n, cta_group=cta_group,
+                            k_order=1)
     ops.conv1d(d2)
     torch.cuda.synchronize()
     assert torch.equal(out, out2), "operand transform differs from gn_apply + conv"
@@ -359,7 +360,7 @@ def test_conv_fused_upsampling(ops, r, t_in, cin, cout, block_n, cta_group):
     out2 = torch.full((r * tp_out, cout), 7.0, dtype=BF16, device="cuda")
     d2 = ops.make_conv_desc([ops.Seg(up, cin, cin, ops.TAPS_K3, r * tp_out)], pack_w(w),
                             pad_bias(b, n_pad), cout, r * tp_out, tp_out, t_up, out2, cout,
-                            stats=st2, block_n=block_n, cta_group=cta_group)
+                            stats=st2, block_n=block_n, cta_group=cta_group, k_order=1)
     ops.conv1d(d2)
     torch.cuda.synchronize()
     assert torch.equal(out, out2), "fused upsampling differs from upsample2x + conv"

@@ -74,7 +74,7 @@ for name, r, t, tp, cin, cout, taps, skip_c, in_gn in SHAPES:
         xs = (torch.randn(m, skip_c, device=dev) * 0.5).to(BF16)
         segs.append(ops.Seg(xs, skip_c, skip_c, ops.TAPS_K1, m))
     out = torch.zeros(m, cout, dtype=BF16, device=dev)
-    st_out = ops.Stats(r, cout, 8, dev)
+    st_out = None if os.environ.get("BENCH_NO_STATS") == "1" else ops.Stats(r, cout, 8, dev)
     gn = None
     if in_gn:
         st = ops.Stats(r, cin, 8, dev)

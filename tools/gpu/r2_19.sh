@@ -1,0 +1,9 @@
+#!/bin/bash
+O=gpurun_out/r2_19; mkdir -p $O; rm -f gpurun_out/test_metrics.jsonl
+step() { local name=$1 to=$2; shift 2; timeout $to "$@" > $O/$name.log 2>&1; local rc=$?; echo "$name exit $rc" | tee -a $O/summary.txt; tail -3 $O/$name.log; return $rc; }
+timeout 60 python tools/probe/run_probe.py > $O/probe.txt 2>&1; cat $O/probe.txt
+step kernels 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x || exit 0
+timeout 200 python tools/bench_conv.py base > $O/base.txt 2>&1; cat $O/base.txt
+timeout 300 python tools/profile_plan.py 32 > $O/plan.csv 2> $O/plan.err; tail -2 $O/plan.err
+step unet 400 python -m pytest tests/test_unet_gpu.py tests/test_fullsize_gpu.py -q -m gpu -x
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu > $O/bench.json 2> $O/bench.err; echo "bench exit $?" | tee -a $O/summary.txt; cut -c1-300 $O/bench.json; tail -3 $O/bench.err
