@@ -142,6 +142,33 @@ typedef struct lm2a_conv_desc {
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);
 
+/* ---- fp32 validation path -------------------------------------------------- */
+/* The same launch plan on fp32 slabs and fp32 weights with plain CUDA-core kernels
+ * (csrc/ref_f32.cu): selected by UNet1D_ultimate(..., precision="fp32") to check the
+ * single-step eps prediction against the reference's fp32 PyTorch path at 1e-4
+ * relative (BASELINE.json tolerance (i)). Not a performance path. lm2a_conv1d_f32
+ * takes the SAME descriptor as lm2a_conv1d_bf16 with every slab / weight / residual
+ * pointer addressing fp32 data (LM2A_OUT_BF16_SLAB then means "fp32 slab"); input
+ * GroupNorm + SiLU (exact expf) and x2 upsampling are evaluated on the fly, the
+ * output sums use the same fixed-point format. block_n / cta_group / k_order are
+ * ignored. lm2a_cross_attn_f32 reads K | V straight from the projection output
+ * kv_s fp32 [slots*lk, kv_ld] (K at channel 0, V at channel e).               */
+int lm2a_conv1d_f32(void* stream, const lm2a_conv_desc* d);
+int lm2a_cross_attn_f32(void* stream, const float* q, int32_t q_ld, float* o,
+                        int32_t o_ld, const float* kv_motion, const float* kv_text,
+                        int32_t kv_ld, const int32_t* kv_slot, int32_t slots,
+                        int32_t rows, int32_t tp, int32_t t_valid, int32_t lk,
+                        int32_t e, int32_t heads, int32_t n_streams);
+int lm2a_bias_add_f32(void* stream, const float* x, int32_t x_ld, float* y,
+                      int32_t y_ld, const float* bias, int64_t slots, int32_t tp,
+                      int32_t t_valid, int32_t c, void* stats, int32_t stats_pitch,
+                      int32_t stats_cg, int32_t stats_c0);
+int lm2a_ingest_x_f32(void* stream, const float* x, float* slab, int32_t batch,
+                      int32_t copies, int32_t c, int32_t t, int32_t tp, int32_t ld,
+                      void* zero, int64_t zero_bytes);
+int lm2a_ingest_seq_f32(void* stream, const float* x, float* slab, int32_t rows,
+                        int32_t t, int32_t c, int32_t tp, int32_t ld);
+
 /* ---- GroupNorm + SiLU over a slab -------------------------------------- */
 /* x,y: bf16 slabs [R, tp, ld*]; stats over t < t_valid and c/groups channels */
 int lm2a_gn_silu_bf16(void* stream, const void* x, int32_t x_ld, void* y,
@@ -173,6 +200,23 @@ int lm2a_cross_attn_bf16(void* stream, const void* q, int32_t q_ld, void* o,
                          const int32_t* kv_slot, int32_t slots, int32_t rows,
                          int32_t tp, int32_t t_valid, int32_t lk, int32_t e,
                          int32_t heads);
+/* Attention of per-head queries against the RAW condition sequence itself, for
+ * blocks whose head dim equals the condition width (128): every head h of stream
+ * s computes softmax(q'_h C_s^T) C_s with C_s bf16 [slots*lk, cond_ld] (first 128
+ * channels), q' / o bf16 slabs with head h of stream s at channel (s*heads + h)*128.
+ * The caller folds W_k,h into the query projection and W_v,h into the output
+ * projection (K_h = C W_k,h^T + b_k: the bias shifts all scores of a row equally
+ * and cancels in the softmax; V_h = C W_v,h^T + b_v: rows of softmax sum to 1), see
+ * engine.py pack_block. Replaces the same reference lines as lm2a_cross_attn_bf16
+ * (models/cross_attention.py:50-61) with 16x less key/value traffic. lk must satisfy
+ * lm2a_cross_attn_cond_supported (the condition tile lives in shared memory).    */
+int lm2a_cross_attn_cond_supported(int32_t lk);
+int lm2a_cross_attn_cond_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                              int32_t o_ld, const void* cond_motion,
+                              const void* cond_text, int32_t cond_ld,
+                              const int32_t* kv_slot, int32_t slots, int32_t rows,
+                              int32_t tp, int32_t t_valid, int32_t lk, int32_t heads,
+                              int32_t n_streams);
 /* Same, for the first n_streams (1 or 2) condition streams only: n_streams = 1
  * runs the motion stream alone (q / o use their first e channels). Used when the
  * lyrics stream is constant in time — the reference's preprocessing tiles ONE

@@ -44,6 +44,17 @@ SIGNATURES = {
     "lm2a_launch_count": (c_int64, []),
     "lm2a_reset_launch_count": (None, []),
     "lm2a_conv1d_bf16": (c_int32, [c_void_p, ctypes.POINTER(ConvDesc)]),
+    "lm2a_conv1d_f32": (c_int32, [c_void_p, ctypes.POINTER(ConvDesc)]),
+    "lm2a_cross_attn_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                      c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                      c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "lm2a_bias_add_f32": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                    c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32,
+                                    c_int32]),
+    "lm2a_ingest_x_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, c_void_p, c_int64]),
+    "lm2a_ingest_seq_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                      c_int32, c_int32]),
     "lm2a_gn_silu_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
                                     c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_float, c_int32]),
@@ -55,6 +66,10 @@ SIGNATURES = {
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                                c_int32, c_void_p, c_int32, c_int32, c_int32,
                                                c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "lm2a_cross_attn_cond_supported": (c_int32, [c_int32]),
+    "lm2a_cross_attn_cond_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                            c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                            c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
     "lm2a_transpose_kv_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                          c_int32, c_int32]),
     "lm2a_time_mlp": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblm2a_b200.so")
-SOURCES = ["api.cu", "conv_gemm.cu", "gn_silu.cu", "attention_tc.cu", "elementwise.cu",
-           "step_update.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "gn_silu.cu", "attention_tc.cu", "attention_res.cu", "elementwise.cu",
+           "step_update.cu", "ref_f32.cu"]
 
 
 def _nvcc():
@@ -26,14 +26,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defs=()):
+    """out / defs: a probe build (extra -D flags) into another file, objects in a scratch dir."""
+    if out is not None:
+        return _build(out, list(defs), verbose, os.path.join(os.path.dirname(out), "obj"))
     if not force and not needs_build():
         return LIB
+    return _build(LIB, os.environ.get("LM2A_NVCC_DEFS", "").split(), verbose, CSRC)
+
+
+def _build(lib, extra, verbose, objdir):
+    os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    extra = os.environ.get("LM2A_NVCC_DEFS", "").split()   # e.g. -DLM2A_CONV_TIMING (probe builds)
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
                "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", *extra,
                "-c", os.path.join(CSRC, src), "-o", obj]
@@ -45,10 +52,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out.decode())
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + [
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + [
         "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

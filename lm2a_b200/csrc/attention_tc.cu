@@ -480,6 +480,12 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
 }
 
 }  // namespace
+
+// attention_res.cu: keys / values resident in shared memory (d_h = 32 / 64 when they fit)
+int cross_attn_resident(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld,
+                        const void* k_m, const void* vt_m, const void* k_t, const void* vt_t,
+                        int k_ld, int vt_ld, const int32_t* kv_slot, int slots, int rows, int tp,
+                        int t_valid, int lk, int e, int heads, int n_streams);
 }  // namespace lm2a
 
 extern "C" int lm2a_cross_attn_streams_bf16(void* stream, const void* q, int32_t q_ld, void* o,
@@ -509,6 +515,12 @@ extern "C" int lm2a_cross_attn_streams_bf16(void* stream, const void* q, int32_t
                "cross_attn: tensors must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int dh = e / heads;
+  {
+    const int rc = cross_attn_resident(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text,
+                                       k_ld, vt_ld, kv_slot, slots, rows, tp, t_valid, lk, e,
+                                       heads, n_streams);
+    if (rc >= 0) return rc;   // -1: shape not covered by the resident kernel
+  }
 #define LM2A_ATTN_CASE(D)                                                                     \
   case D:                                                                                     \
     return launch_attn<D>(st, q, q_ld, o, o_ld, k_motion, vt_motion, k_text, vt_text, k_ld,   \

@@ -107,6 +107,7 @@ struct ConvArgs {
   int share_taps;             // 1: one A block serves all taps (row-shifted views); 0: one
                               //    128-slot box per tap
   int tap_outer;              // plain launches: K walk order (1: tap outer, channel block inner)
+  int dbg_stats;              // timing experiments only: 1 = sums without atomics, 2 = atomics only
   int dbg_noshift;            // timing experiments only: every tap reads the unshifted view
   int dbg_noxform;            // timing experiments only: transform warps pass blocks through
 };
@@ -804,7 +805,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             const bool mine = in_range && r == rr;
             const long long a = warp_sum_ll(mine ? st_a1 : 0ll);
             const long long b = warp_sum_ll(mine ? st_a2 : 0ll);
-            if (lane == 0) {
+            if (lane == 0 && p.dbg_stats != 1) {
               unsigned long long* sp = p.stats + ((size_t)rr * p.stats_pitch + st_g) * 2;
               atomicAdd(sp, (unsigned long long)a);
               atomicAdd(sp + 1, (unsigned long long)b);
@@ -859,24 +860,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
             }
           }
         }
-        if (p.stats != nullptr) {
+        if (p.stats != nullptr && p.dbg_stats == 2) {
+          st_g = (p.stats_c0 + n) / p.stats_cg;
+          st_a1 += 1;
+        } else if (p.stats != nullptr) {
           // Sum / sum of squares of this lane's slot over each `gran`-channel sub-block (fp32,
           // fixed order: independent of where the slot sits in the batch), converted to fixed
           // point and added - exactly, as integers - to the lane's running sums of the current
           // group; a group is flushed (warp reduction + one atomic pair per clip-row) when the
           // walk over the warp's columns leaves it.
+          // (a lane is one slot: pad slots and slots past the slab hold finite values computed
+          // from zero / real operands, so they are summed like the others and dropped as a whole)
           float q1[4], q2[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float a = 0.f, b = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float x = valid ? f[q * 8 + j] : 0.f;
+              const float x = f[q * 8 + j];
               a += x;
               b = fmaf(x, x, b);
             }
-            q1[q] = a;
-            q2[q] = b;
+            q1[q] = valid ? a : 0.f;
+            q2[q] = valid ? b : 0.f;
           }
           const int nsub = 32 / gran;  // sub-blocks inside this 32-channel chunk
           if (nsub == 1) {
@@ -1082,6 +1088,11 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
   const bool up2x = d->in_up_t > 0;
   a.share_taps = (d->in_gn_stats != nullptr || up2x) ? 1 : 0;
   a.dbg_noshift = noshift_env;
+  static const int dbg_stats_env = [] {
+    const char* e = getenv("LM2A_CONV_DBG_STATS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  a.dbg_stats = dbg_stats_env;
   // K walk of plain launches: taps outer (default; measured 5-10 % faster on B200 at the
   // production shapes: W is read contiguously along K and the MMA-issuing thread's loop is
   // shorter) or channel blocks outer (k_order = 1: the order the operand-transform launches

@@ -63,15 +63,18 @@ def _conv_w(w, cin_pad=None):
     return out.reshape(cout, k * cin_pad)
 
 
+_PACK_DTYPE = [BF16]   # weight dtype of the pack in progress (fp32 for the validation path)
+
+
 def _finish(w, b, dev):
-    """Pad rows to a multiple of 128, cast: W -> bf16, bias -> fp32."""
+    """Pad rows to a multiple of 128, cast: W -> bf16 (fp32 on the validation path), bias -> fp32."""
     n = w.shape[0]
     n_pad = _pad_to(n, 128)
     wp = torch.zeros(n_pad, w.shape[1], dtype=torch.float64, device=w.device)
     wp[:n] = w
     bp = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
     bp[:n] = b
-    return wp.to(dev, BF16).contiguous(), bp.to(dev, torch.float32).contiguous()
+    return wp.to(dev, _PACK_DTYPE[0]).contiguous(), bp.to(dev, torch.float32).contiguous()
 
 
 def _gn(gn, dev):
@@ -167,6 +170,28 @@ def pack_block(blk, heads, dev, film_col):
             wof_m = torch.cat([wof_m, wskip], dim=1)
         p.wof_m, p.bof_m = _finish(wof_m, bof, dev)
         p.wof_t, p.zero_b = _finish(wf[:, e:] @ wo[1], torch.zeros_like(bof), dev)
+        # Head dim == condition width: K_h = C Wk_h^T + bk_h and V_h = C Wv_h^T + bv_h are images
+        # of the raw condition sequence C, so head h can attend to C itself (lm2a_cross_attn_cond):
+        #   scores  Q_h K_h^T = (Q_h Wk_h) C^T + (Q_h bk_h) 1^T   (second term: constant per row,
+        #                                                          cancels in the softmax)
+        #   output  P V_h = (P C) Wv_h^T + bv_h                    (rows of P sum to 1)
+        # Wk_h is folded into the (composed) query projection, Wv_h and bv_h into the output
+        # projection: no per-head K / V is read in the loop.
+        dh = e // heads
+        p.cond_fold = dh == 128 and dh == wkv[0].shape[1]
+        if p.cond_fold:
+            hs = [slice(h * dh, (h + 1) * dh) for h in range(heads)]
+            wqc = [torch.cat([wkv[s][:e][b].t() @ wq[s][b] for b in hs], dim=0) for s in (0, 1)]
+            bqc = [torch.cat([wkv[s][:e][b].t() @ bq[s][b] for b in hs], dim=0) for s in (0, 1)]
+            wqc_all, bqc_all = torch.cat(wqc, dim=0), torch.cat(bqc, dim=0)
+            p.wq2c, p.bq2c = _finish(wqc_all @ w2, wqc_all @ b2 + bqc_all, dev)
+            p.wq2c_m, p.bq2c_m = _finish(wqc[0] @ w2, wqc[0] @ b2 + bqc[0], dev)
+            wos = [wf[:, :e] @ wo[0], wf[:, e:] @ wo[1]]      # [cout, e] per stream
+            wofc = [torch.cat([wos[s][:, b] @ wkv[s][e:][b] for b in hs], dim=1) for s in (0, 1)]
+            bvc = [sum(wos[s][:, b] @ bkv[s][e:][b] for b in hs) for s in (0, 1)]
+            tail = [wskip] if has_skip else []
+            p.wofc, p.bofc = _finish(torch.cat(wofc + tail, dim=1), bof + bvc[0] + bvc[1], dev)
+            p.wofc_m, p.bofc_m = _finish(torch.cat([wofc[0]] + tail, dim=1), bof + bvc[0], dev)
     return p
 
 
@@ -325,11 +350,14 @@ class UNetPlan:
         self.uncond_rows = uncond_rows if use_cond else 0
         assert 0 <= self.uncond_rows < rows
         self.copies, self.use_cond, self.dev = copies, use_cond, dev
+        # fp32 validation path: fp32 slabs, CUDA-core kernels, every transform inside the conv
+        self.fp32 = getattr(pm, "wdt", BF16) == torch.float32
+        self.adt = torch.float32 if self.fp32 else BF16
         assert rows % copies == 0
         self.batch = rows // copies
         n_down = len(pm.dims)
         g = self.geo = Geometry(rows, t, n_down)
-        z = lambda m, c, dt=BF16: torch.zeros(m, c, dtype=dt, device=dev)  # noqa: E731
+        z = lambda m, c, dt=None: torch.zeros(m, c, dtype=dt or self.adt, device=dev)  # noqa: E731
 
         # static I/O
         self.x_in = torch.zeros(self.batch, pm.in_dim, t, dtype=torch.float32, device=dev)
@@ -341,13 +369,15 @@ class UNetPlan:
 
         # scratch slabs shared by all blocks (sized for the largest level)
         cmax = max(g.M[lvl] * pm.scratch_width(lvl) for lvl in range(n_down + 1))
-        flat = lambda: torch.zeros(cmax, dtype=BF16, device=dev)  # noqa: E731
+        flat = lambda: torch.zeros(cmax, dtype=self.adt, device=dev)  # noqa: E731
         self._h1, self._q, self._o = flat(), flat(), flat()
         self._flat = flat
         self._norm = None   # normalised operands of the launches that do not transform in-kernel
         # widest operand (channels) normalised / upsampled inside the consuming conv
         self.xf_max_c = int(os.environ.get("LM2A_XF_MAX_C", "512"))
         self.up_xf_max_c = int(os.environ.get("LM2A_UP_XF_MAX_C", "512"))
+        if self.fp32:
+            self.xf_max_c = self.up_xf_max_c = 1 << 30
         # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
         # kernel (ingest_x) clears; the epilogues accumulate exact integer sums into it
         self.arena = ops.StatsArena(dev, (2 * pm.n_groupnorms + 16) * rows * pm.max_groups * 2)
@@ -365,7 +395,8 @@ class UNetPlan:
             self.cond_t = z(nslots * lk, pm.cond_dim)
             for b in pm.attn_blocks:
                 self.kv.append((z(nslots * lk, 2 * b.e), z(nslots * lk, 2 * b.e)))
-                self.vt.append((z(nslots * b.e, self.lk_pad), z(nslots * b.e, self.lk_pad)))
+                self.vt.append((None, None) if self.fp32 else
+                               (z(nslots * b.e, self.lk_pad), z(nslots * b.e, self.lk_pad)))
         # two launch lists over the same buffers: the full one, and the variant used when the
         # lyrics stream is constant in time for every clip of the batch (what the reference's
         # preprocessing produces: ONE sentence embedding tiled over all frames,
@@ -377,7 +408,12 @@ class UNetPlan:
         self._ops_by_mode = {False: [], True: []}
         self.const_text = False
         self._building_ct = False
-        self.allow_const_text = os.environ.get("LM2A_CONST_STREAM", "1") != "0"
+        self.allow_const_text = (os.environ.get("LM2A_CONST_STREAM", "1") != "0"
+                                 and not self.fp32)
+        # blocks whose head dim equals the condition width attend to the raw condition slabs
+        self.cond_attn = (use_cond and not self.fp32
+                          and os.environ.get("LM2A_COND_ATTN", "1") != "0"
+                          and ops.cond_attn_supported(lk))
         # per attention block: fp32 [rows, 2 * cout] table (zero scale | per-clip shift), built by
         # ct_ops once per batch
         self.ct_tab = [None] * (len(pm.attn_blocks) if use_cond else 0)
@@ -434,8 +470,8 @@ class UNetPlan:
         meta = {"kind": "conv_gemm", "flops": flops, "flops_executed": executed,
                 "m": m, "n": n_valid, "k": k_total, "in_gn": k.get("in_gn") is not None,
                 "up2x": k.get("up2x") is not None}
-        self._add(ops.conv1d, ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k),
-                  meta=meta)
+        self._add(ops.conv1d_f32 if self.fp32 else ops.conv1d,
+                  ops.make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, *a, **k), meta=meta)
 
     def _stats(self, rows, lvl, c, groups):
         """Statistics buffer of a [rows, Tp_lvl, c] slab whose consumer normalises it in `groups`
@@ -459,7 +495,7 @@ class UNetPlan:
         choice does not change a bit of the result. Clips too short for the transform also take
         the stand-alone pass."""
         gm, bt, groups, eps = gn
-        if c <= self.xf_max_c and ops.in_gn_supported(tp, groups):
+        if c <= self.xf_max_c and (self.fp32 or ops.in_gn_supported(tp, groups)):
             return x, x_ld, x_off, (x_st, gm, bt, eps, True)
         if self._norm is None:
             self._norm = [self._flat(), self._flat()]
@@ -509,8 +545,9 @@ class UNetPlan:
             self._conv([Seg(xin, xin_ld, p.cin, TAPS_K1, m, xin_off)], p.wsk, p.bsk_c, p.cout, m,
                        tp, tv, out, out_ld, out_chan_off=out_off, stats=st)
         else:
-            self._add(ops.bias_add, xin, xin_ld, xin_off, out, out_ld, out_off, p.c_uncond, m, tp,
-                      tv, p.cout, st, meta={"kind": "bias_add", "flops": 0})
+            self._add(ops.bias_add_f32 if self.fp32 else ops.bias_add, xin, xin_ld, xin_off, out,
+                      out_ld, out_off, p.c_uncond, m, tp, tv, p.cout, st,
+                      meta={"kind": "bias_add", "flops": 0})
 
     def _make_ct_table(self, ai, p, kv_t):
         """Per-batch setup of attention block `ai` for the constant-lyrics launch list: the clip's
@@ -563,6 +600,25 @@ class UNetPlan:
         ai = self._attn_i
         self._attn_i += 1
         rows_valid = nr * tv
+        cond = self.cond_attn and p.cond_fold
+        cdim = self.pm.cond_dim
+
+        def attend(q, o, width, n_streams):
+            flops = n_streams * 4 * nr * tv * self.lk * e
+            if self.fp32:
+                self._add(ops.cross_attn_f32, q, width, o, width, kv_m, kv_t, 2 * e,
+                          ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads,
+                          n_streams, meta={"kind": "cross_attn", "flops": flops})
+            elif cond:
+                self._add(ops.cross_attn_cond, q, width, o, width, ops._ptr(self.cond_m),
+                          ops._ptr(self.cond_t), cdim, ops._ptr(self.kv_slot, r0), self.nslots, nr,
+                          tp, tv, self.lk, p.heads, n_streams,
+                          meta={"kind": "cross_attn", "flops": flops, "cond": True})
+            else:
+                self._add(ops.cross_attn, q, width, o, width, ops._ptr(kv_m), ops._ptr(vt_m),
+                          ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad,
+                          ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads,
+                          n_streams, meta={"kind": "cross_attn", "flops": flops})
         if self._building_ct:
             # motion stream only; the lyrics stream's contribution (Wf2 Wo_t) v_t is a per-clip
             # vector: a per-row epilogue shift of the output GEMM, read from the block's table
@@ -572,12 +628,11 @@ class UNetPlan:
             o = self._view(self._o, m, e)
             # algorithmic work of conv2 (6 T C^2) + one Q projection (2 T C^2) exceeds what the
             # composed GEMM executes (6 T C^2): credit the executed FLOPs
-            self._conv(main, p.wq2_m, p.bq2_m, e, m, tp, tv, q, e, in_gn=in_gn2)
-            self._add(ops.cross_attn, q, e, o, e, ops._ptr(kv_m), ops._ptr(vt_m),
-                      ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad,
-                      ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads, 1,
-                      meta={"kind": "cross_attn", "flops": 4 * nr * tv * self.lk * e})
-            self._conv([Seg(o, e, e, TAPS_K1, m)] + skip_seg, p.wof_m, p.bof_m, cout, m, tp, tv,
+            wq_, bq_ = (p.wq2c_m, p.bq2c_m) if cond else (p.wq2_m, p.bq2_m)
+            wo_, bo_ = (p.wofc_m, p.bofc_m) if cond else (p.wof_m, p.bof_m)
+            self._conv(main, wq_, bq_, e, m, tp, tv, q, e, in_gn=in_gn2)
+            attend(q, o, e, 1)
+            self._conv([Seg(o, e, e, TAPS_K1, m)] + skip_seg, wo_, bo_, cout, m, tp, tv,
                        out, out_ld, out_chan_off=oo, stats=ost, film=self.ct_tab[ai], film_col=0,
                        film_shift_off=cout, film_bcast=False, film_row=r0, **res)
             return
@@ -585,13 +640,12 @@ class UNetPlan:
         o = self._view(self._o, m, 2 * e)
         # the composed conv2 . [Q_motion | Q_lyrics] GEMM executes 2 * 2E * 3C MACs per slot where
         # the reference's conv2 followed by two Q projections needs 3C * C + 2E * C: credit that
-        self._conv(main, p.wq2, p.bq2, 2 * e, m, tp, tv, q, 2 * e, in_gn=in_gn2,
+        wq_, bq_ = (p.wq2c, p.bq2c) if cond else (p.wq2, p.bq2)
+        wo_, bo_ = (p.wofc, p.bofc) if cond else (p.wof, p.bof)
+        self._conv(main, wq_, bq_, 2 * e, m, tp, tv, q, 2 * e, in_gn=in_gn2,
                    flops_alg=2 * rows_valid * (3 * cout * cout + 2 * e * cout))
-        self._add(ops.cross_attn, q, 2 * e, o, 2 * e, ops._ptr(kv_m), ops._ptr(vt_m),
-                  ops._ptr(kv_t), ops._ptr(vt_t), 2 * e, self.lk_pad, ops._ptr(self.kv_slot, r0),
-                  self.nslots, nr, tp, tv, self.lk, e, p.heads,
-                  meta={"kind": "cross_attn", "flops": 2 * 4 * nr * tv * self.lk * e})
-        self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, p.wof, p.bof, cout, m, tp, tv,
+        attend(q, o, 2 * e, 2)
+        self._conv([Seg(o, 2 * e, 2 * e, TAPS_K1, m)] + skip_seg, wo_, bo_, cout, m, tp, tv,
                    out, out_ld, out_chan_off=oo, stats=ost, **res)
 
     # -- plan construction ----------------------------------------------------------------
@@ -604,11 +658,12 @@ class UNetPlan:
             n = self.nslots * self.lk
             for cond, w, b, dst, vt in ((self.cond_m, p.wkv_m, p.bkv_m, kv_m, vt_m),
                                         (self.cond_t, p.wkv_t, p.bkv_t, kv_t, vt_t)):
-                self.kv_ops.append((ops.conv1d, (ops.make_conv_desc(
+                self.kv_ops.append((ops.conv1d_f32 if self.fp32 else ops.conv1d, (ops.make_conv_desc(
                     [Seg(cond, pm.cond_dim, pm.cond_dim, TAPS_K1, n)], w, b, 2 * p.e, n,
                     self.lk, self.lk, dst, 2 * p.e),)))
-                self.kv_ops.append((ops.transpose_kv, (dst, 2 * p.e, p.e, vt, self.lk_pad,
-                                                       self.nslots, self.lk, p.e)))
+                if not self.fp32:   # (the fp32 attention reads V from the K | V slab itself)
+                    self.kv_ops.append((ops.transpose_kv, (dst, 2 * p.e, p.e, vt, self.lk_pad,
+                                                           self.nslots, self.lk, p.e)))
 
     def _build_legacy(self):
         """Launch list of the legacy UNet1D.forward (reference models/unet1d.py:113-154)."""
@@ -626,8 +681,9 @@ class UNetPlan:
                   pm.time_dim, pm.film_cols)
         self._side_op = False
         self._hold_join = True
-        self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
-                  self.t, g.Tp[0], pm.in_pad, self.arena)
+        self._add(ops.ingest_x_f32 if self.fp32 else ops.ingest_x, self.x_in, self.x_slab,
+                  self.batch, self.copies, pm.in_dim, self.t, g.Tp[0], pm.in_pad, self.arena,
+                  meta={"kind": "ingest_x", "flops": 0})
         cur = self._view(self._pp[0], g.M[0], pm.base)
         cur_st = self._stats(rows, 0, pm.base, 8)
         # CFG copies are identical up to the first (attention) block: input_proj runs on the cond
@@ -700,8 +756,9 @@ class UNetPlan:
         self._side_op = False
         self._hold_join = True
         # x -> bf16 slab (CFG row duplication happens here), in_proj
-        self._add(ops.ingest_x, self.x_in, self.x_slab, self.batch, self.copies, pm.in_dim,
-                  self.t, g.Tp[0], pm.in_pad, self.arena)
+        self._add(ops.ingest_x_f32 if self.fp32 else ops.ingest_x, self.x_in, self.x_slab,
+                  self.batch, self.copies, pm.in_dim, self.t, g.Tp[0], pm.in_pad, self.arena,
+                  meta={"kind": "ingest_x", "flops": 0})
         groups_of = lambda blk_gn: blk_gn[2]  # noqa: E731
         cur = self._view(self._pp[0], g.M[0], pm.base)
         first = pm.downs[0][0][0]
@@ -818,8 +875,9 @@ class UNetPlan:
         if tuple(motion_f.shape) != (n, lk, c) or tuple(text_f.shape) != (n, lk, c):
             raise RuntimeError(f"conditions must be ({n}, {lk}, {c}); got "
                                f"{tuple(motion_f.shape)} / {tuple(text_f.shape)}")
-        ops.ingest_seq(motion_f.contiguous().float(), self.cond_m, n, lk, c, lk, c)
-        ops.ingest_seq(text_f.contiguous().float(), self.cond_t, n, lk, c, lk, c)
+        ingest = ops.ingest_seq_f32 if self.fp32 else ops.ingest_seq
+        ingest(motion_f.contiguous().float(), self.cond_m, n, lk, c, lk, c)
+        ingest(text_f.contiguous().float(), self.cond_t, n, lk, c, lk, c)
         for fn, args in self.kv_ops:
             fn(*args)
         self.kv_slot.copy_(kv_slot.to(torch.int32))
@@ -847,6 +905,9 @@ class UNetPlan:
         slabs from cache slot `first_slot` on: CondProjection.project_raw writes the projected
         conditions straight into them; `build_kv` then builds the caches."""
         assert self.use_cond
+        if self.fp32:
+            raise RuntimeError("the fp32 validation path takes projected conditions through "
+                               "set_conditions (CondProjection.project_raw writes bf16 slabs)")
         o = first_slot * self.lk
         return self.cond_m[o:], self.cond_t[o:]
 
@@ -966,14 +1027,21 @@ def params_fingerprint(model):
 
 
 class UNetEngine:
-    def __init__(self, model):
+    def __init__(self, model, precision="bf16"):
         p = next(model.parameters())
         ops.require_device(p)
         self.dev = p.device
+        self.precision = precision
         self.fingerprint = params_fingerprint(model)
         legacy = hasattr(model, "input_proj")  # models/unet1d.py names vs unet1d_ultimate.py
-        with torch.cuda.device(self.dev):
-            self.pm = PackedLegacy(model, self.dev) if legacy else PackedModel(model, self.dev)
+        wdt = torch.float32 if precision == "fp32" else BF16
+        _PACK_DTYPE[0] = wdt
+        try:
+            with torch.cuda.device(self.dev):
+                self.pm = PackedLegacy(model, self.dev) if legacy else PackedModel(model, self.dev)
+        finally:
+            _PACK_DTYPE[0] = BF16
+        self.pm.wdt = wdt
         self.plans = {}
         self._cond_key = None
         self._cond_ref = None

@@ -269,7 +269,7 @@ class CfgSampler:
         fused (default for DDPM): the lm2a_cfg_step path, no library kernel in the graph."""
         p = self.plan
         if fused is None:
-            fused = self.ddim is None
+            fused = self.ddim is None and not p.fp32
         key = (self.gw, p.const_text, fused)
         self.fused = fused
         if key in self._graphs:
@@ -342,7 +342,7 @@ class CfgSampler:
         else:
             self.set_conditions(motion_f, text_f)
         injected = noises is not None
-        fused = self.ddim is None and not injected
+        fused = self.ddim is None and not injected and not p.fp32   # (fp32 validation path: unfused)
         if fused or x_init is None:
             self.set_clip_seeds(clip_seeds)
         if x_init is None:

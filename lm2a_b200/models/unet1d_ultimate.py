@@ -111,8 +111,15 @@ class UNet1D_ultimate(nn.Module):
     def __init__(self, in_dim: int = 80, base_dim: int = 128,
                  dim_mults: Tuple[int, ...] = (1, 2, 4), cond_dim: int = 128,
                  time_emb_dim: int = 256, num_res_blocks: int = 2, mid_blocks: int = 3,
-                 attn_heads: int = 4):
+                 attn_heads: int = 4, precision: str = "bf16"):
+        """precision (not a reference argument; keyword-only in spirit): "bf16" = the tcgen05
+        production path (reference tolerance 2e-2), "fp32" = the fp32 validation path on CUDA
+        cores (csrc/ref_f32.cu; single-step eps within 1e-4 of the reference's fp32 PyTorch
+        forward). set_precision() switches an existing model."""
         super().__init__()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
         self.in_dim, self.base_dim, self.dim_mults = in_dim, base_dim, tuple(dim_mults)
         self.cond_dim, self.time_emb_dim = cond_dim, time_emb_dim
         self.num_res_blocks, self.attn_heads = num_res_blocks, attn_heads
@@ -163,8 +170,16 @@ class UNet1D_ultimate(nn.Module):
         if self._engine is not None and self._engine.fingerprint != params_fingerprint(self):
             self._engine = None
         if self._engine is None:
-            self._engine = UNetEngine(self)
+            self._engine = UNetEngine(self, precision=self.precision)
         return self._engine
+
+    def set_precision(self, precision: str):
+        """"bf16" (production) or "fp32" (validation path); re-packs the weights on next use."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision != self.precision:
+            self.precision, self._engine = precision, None
+        return self
 
     def refresh(self):
         """Drop the packed weights (they are re-packed from the parameters on the next use)."""

@@ -135,7 +135,7 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
     upsampling (align_corners) is computed inside the conv's operand path."""
     d = ConvDesc()
     for i, s in enumerate(segs):
-        d.seg[i].x = s.slab.data_ptr() + s.chan_off * 2
+        d.seg[i].x = s.slab.data_ptr() + s.chan_off * s.slab.element_size()
         d.seg[i].rows = s.rows
         d.seg[i].ld = s.ld
         d.seg[i].cin = s.cin
@@ -152,7 +152,7 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
         d.film_ld = 0 if film_bcast else film.shape[1]  # 0: one table row for all clip-rows
         d.film_shift_off = film_shift_off
     if residual is not None:
-        d.residual = residual.data_ptr() + res_chan_off * 2
+        d.residual = residual.data_ptr() + res_chan_off * residual.element_size()
         d.res_ld = res_ld
     d.out_mode = out_mode
     d.out = out.data_ptr() + out_chan_off * out.element_size()
@@ -186,6 +186,39 @@ def conv1d(desc):
     _lib.check(_lib.load().lm2a_conv1d_bf16(_stream(), ctypes.byref(desc)), "lm2a_conv1d_bf16")
 
 
+# ---- fp32 validation path (csrc/ref_f32.cu): same descriptors, fp32 slabs and weights ----------
+def conv1d_f32(desc):
+    _lib.check(_lib.load().lm2a_conv1d_f32(_stream(), ctypes.byref(desc)), "lm2a_conv1d_f32")
+
+
+def cross_attn_f32(q, q_ld, o, o_ld, kv_m, kv_t, kv_ld, kv_slot, slots, rows, tp, t_valid, lk, e,
+                   heads, n_streams=2):
+    _lib.check(_lib.load().lm2a_cross_attn_f32(
+        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, _ptr(kv_m), _ptr(kv_t), kv_ld,
+        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows, tp,
+        t_valid, lk, e, heads, n_streams), "lm2a_cross_attn_f32")
+
+
+def bias_add_f32(x, x_ld, x_off, y, y_ld, y_off, bias, slots, tp, t_valid, c, stats=None):
+    _lib.check(_lib.load().lm2a_bias_add_f32(
+        _stream(), _ptr(x, x_off), x_ld, _ptr(y, y_off), y_ld, _ptr(bias), slots, tp, t_valid, c,
+        ctypes.c_void_p(stats.ptr()) if stats is not None else None,
+        stats.groups if stats is not None else 0, stats.cg if stats is not None else 0,
+        stats.chan0 if stats is not None else 0), "lm2a_bias_add_f32")
+
+
+def ingest_x_f32(x, slab, batch, copies, c, t, tp, ld, zero=None):
+    zt = zero.used() if isinstance(zero, StatsArena) else zero
+    zbytes = 0 if zt is None else zt.numel() * zt.element_size()
+    _lib.check(_lib.load().lm2a_ingest_x_f32(_stream(), _ptr(x), _ptr(slab), batch, copies, c, t,
+                                             tp, ld, _ptr(zt), zbytes), "lm2a_ingest_x_f32")
+
+
+def ingest_seq_f32(x, slab, rows, t, c, tp, ld):
+    _lib.check(_lib.load().lm2a_ingest_seq_f32(_stream(), _ptr(x), _ptr(slab), rows, t, c, tp, ld),
+               "lm2a_ingest_seq_f32")
+
+
 def gn_silu(x, x_ld, y, y_ld, gamma, beta, rows, tp, t_valid, c, groups, eps=1e-5, silu=True,
             x_chan_off=0, y_chan_off=0):
     _lib.check(_lib.load().lm2a_gn_silu_bf16(
@@ -200,6 +233,20 @@ def cross_attn(q, q_ld, o, o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, kv_slot, slo
         _stream(), _ptr(q, q_off), q_ld, _ptr(o, o_off), o_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld,
         kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows,
         tp, t_valid, lk, e, heads, n_streams), "lm2a_cross_attn_bf16")
+
+
+def cond_attn_supported(lk):
+    """Whether lm2a_cross_attn_cond_bf16 can keep `lk` condition frames resident."""
+    return bool(_lib.load().lm2a_cross_attn_cond_supported(int(lk)))
+
+
+def cross_attn_cond(q, q_ld, o, o_ld, cond_m, cond_t, cond_ld, kv_slot, slots, rows, tp, t_valid,
+                    lk, heads, n_streams=2, q_off=0, o_off=0):
+    """softmax(q'_h C^T) C per head against the raw condition slabs (head dim = cond width = 128)."""
+    _lib.check(_lib.load().lm2a_cross_attn_cond_bf16(
+        _stream(), _ptr(q, q_off), q_ld, _ptr(o, o_off), o_ld, cond_m, cond_t, cond_ld,
+        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows, tp,
+        t_valid, lk, heads, n_streams), "lm2a_cross_attn_cond_bf16")
 
 
 def transpose_kv(src, src_ld, src_off, dst, dst_ld, slots, lk, c):

@@ -431,6 +431,25 @@ def test_bias_add_stats(ops, r, t, tp, c, groups):
     (128, 4, 260, 64, 1.0), (384, 4, 129, 60, 1.0), (512, 8, 258, 300, 6.0), (256, 8, 261, 100, 1.0),
 ])
 def test_cross_attention_core(ops, e, heads, t, lk, qgain):
+    _attention_core_case(ops, e, heads, t, lk, qgain)
+
+
+@pytest.mark.parametrize("e,heads,t,lk,qgain", [
+    (256, 8, 516, 516, 1.0), (512, 8, 258, 516, 1.0), (256, 8, 100, 77, 1.0), (128, 4, 33, 64, 1.0),
+    (256, 8, 200, 300, 6.0), (512, 8, 258, 300, 6.0), (128, 4, 260, 64, 1.0), (256, 8, 261, 100, 1.0),
+    (512, 8, 130, 1100, 1.0),
+])
+def test_cross_attention_core_resident_kernel(ops, monkeypatch, e, heads, t, lk, qgain):
+    """The opt-in resident-K/V kernel (attention_res.cu, LM2A_ATTN_RESIDENT=1) for d_h = 32 / 64:
+    full + tail tiles split over CTAs, two tile slots, P through tensor memory."""
+    monkeypatch.setenv("LM2A_ATTN_RESIDENT", "1")
+    from lm2a_b200 import ops as _o
+    before = _o.launch_count()
+    _attention_core_case(ops, e, heads, t, lk, qgain)
+    assert _o.launch_count() > before
+
+
+def _attention_core_case(ops, e, heads, t, lk, qgain):
     r, slots, tp = 3, 2, t + 2
     dh = e // heads
     q = rnd(r, 2 * e, t, seed=30) * qgain
@@ -462,6 +481,45 @@ def test_cross_attention_core(ops, e, heads, t, lk, qgain):
         p = torch.softmax(qq @ k.transpose(-1, -2), dim=-1)
         ref = (p @ v).transpose(1, 2).reshape(r, t, e).permute(0, 2, 1)
         assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"attention stream {s}")
+
+
+@pytest.mark.parametrize("heads,t,lk,qgain", [
+    (8, 64, 516, 1.0),      # production level 3: two heads per 128-row tile
+    (8, 129, 516, 1.0),     # production level 2: 8 full tiles + one tile of the 8 leftover rows
+    (8, 258, 300, 1.0),     # two full tiles per head, 2-row tails packed 8 heads to a tile
+    (4, 33, 64, 1.0),       # 64-row sub-blocks, two heads per tile; one key chunk
+    (3, 100, 77, 1.0),      # odd head count: a tail tile with an unused sub-block
+    (8, 70, 200, 6.0),      # peaked softmax: the running max grows, O is rescaled
+    (2, 516, 640, 1.0),     # four full tiles per head, the largest resident key count
+    (8, 17, 16, 1.0),       # a single 16-key chunk; 32-row sub-blocks
+])
+def test_cross_attention_cond(ops, heads, t, lk, qgain):
+    """lm2a_cross_attn_cond_bf16: every head attends to the raw condition sequence itself,
+    softmax(q'_h C^T) C (head dim = condition width = 128), vs fp32 torch."""
+    r, slots, tp, dh = 3, 2, t + 2, 128
+    e = heads * dh
+    assert ops.cond_attn_supported(lk) and not ops.cond_attn_supported(700)
+    q = rnd(r, 2 * e, t, seed=33) * qgain
+    cm = rnd(slots * lk, dh, seed=34).to(BF16)
+    ct = rnd(slots * lk, dh, seed=35).to(BF16)
+    kv_slot = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
+    scale = 1.0 / math.sqrt(dh)
+    qs = to_slab(q * (scale * 1.4426950408889634), tp)
+    for n_streams in (2, 1):
+        o = torch.full((r * tp, 2 * e), 3.0, dtype=BF16, device="cuda")
+        ops.cross_attn_cond(qs, 2 * e, o, 2 * e, ops._ptr(cm), ops._ptr(ct), dh, kv_slot, slots, r,
+                            tp, t, lk, heads, n_streams)
+        torch.cuda.synchronize()
+        got = from_slab(o, r, tp, t, 2 * e)
+        for s, c in enumerate((cm, ct)[:n_streams]):
+            cf = c.float().view(slots, lk, dh)[kv_slot.long()]            # [r, lk, dh]
+            qq = qs.float().view(r, tp, 2 * e)[:, :t, s * e:(s + 1) * e] / 1.4426950408889634
+            qq = qq.reshape(r, t, heads, dh).transpose(1, 2)              # [r, h, t, dh]
+            p = torch.softmax(qq @ cf[:, None].transpose(-1, -2), dim=-1)
+            ref = (p @ cf[:, None]).transpose(1, 2).reshape(r, t, e).permute(0, 2, 1)
+            assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"cond attention stream {s}")
+        if n_streams == 1:
+            assert bool((o.view(r, tp, 2 * e)[:, :, e:] == 3.0).all()), "stream 1 was touched"
 
 
 @pytest.mark.parametrize("r,t,tp,c,groups", [(2, 129, 130, 1536, 8), (3, 50, 52, 768, 8),

@@ -56,6 +56,32 @@ def test_short_trajectory_vs_oracle(gw):
         assert cos > 0.999, f"clip {b}: frame cosine {cos:.6f}"
 
 
+def test_fp32_trajectory_vs_oracle():
+    """precision="fp32" through the sampler (CFG doubling, uncond shortcut, injected noise): an
+    8-step guided trajectory within 1e-4 relative of the fp32 oracle's, clip by clip."""
+    _need_gpu()
+    from lm2a_b200.models import GaussianDiffusion, UNet1D_ultimate
+    cfg = orc.UNetConfig(80, 64, (1, 2, 4), 128, 256, 2, 3, 2)
+    sd = orc.random_state_dict(cfg, 6)
+    net = UNet1D_ultimate(80, 64, (1, 2, 4), 128, 256, 2, 3, 2, precision="fp32")
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    steps, bsz, t_len, lk = 8, 3, 100, 60
+    g = torch.Generator().manual_seed(123)
+    x0 = torch.randn(bsz, 80, t_len, generator=g)
+    mf = torch.randn(bsz, lk, 128, generator=g)
+    tf = torch.randn(bsz, lk, 128, generator=g)
+    noises = torch.randn(steps - 1, bsz, 80, t_len, generator=g)
+    diff = GaussianDiffusion(net, timesteps=steps, device="cuda")
+    got = diff.sample_cfg((bsz, 80, t_len), mf.cuda(), tf.cuda(), 2.1, x_init=x0.cuda(),
+                          noises=noises.cuda())
+    with torch.no_grad():
+        ref = orc.sample_loop(sd, cfg, mf, tf, (bsz, 80, t_len), steps, 2.1, x0, list(noises))
+    for b in range(bsz):
+        err = _rel(got[b], ref[b])
+        assert err < 1e-4, f"clip {b}: fp32 trajectory rel-L2 {err:.3e}"
+
+
 def test_graph_replay_equals_eager_and_is_shard_invariant():
     """Default sampling: the CUDA-Graph path (update kernel with in-kernel Philox noise, timestep
     advanced on device) and the same launches issued eagerly give bit-identical trajectories;

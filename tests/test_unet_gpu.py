@@ -11,6 +11,7 @@ import lm2a_oracle as orc
 
 pytestmark = pytest.mark.gpu
 TOL_BF16 = 2e-2
+TOL_FP32 = 1e-4    # BASELINE.json north_star: single-step eps within 1e-4 relative in fp32
 
 
 def _cfg_from(arr):
@@ -18,12 +19,12 @@ def _cfg_from(arr):
     return orc.UNetConfig(a[0], a[1], tuple(a[7:]), a[2], a[3], a[4], a[5], a[6])
 
 
-def _model(cfg, sd):
+def _model(cfg, sd, precision="bf16"):
     from lm2a_b200.models import UNet1D_ultimate
     net = UNet1D_ultimate(in_dim=cfg.in_dim, base_dim=cfg.base_dim, dim_mults=cfg.dim_mults,
                           cond_dim=cfg.cond_dim, time_emb_dim=cfg.time_emb_dim,
                           num_res_blocks=cfg.num_res_blocks, mid_blocks=cfg.mid_blocks,
-                          attn_heads=cfg.attn_heads)
+                          attn_heads=cfg.attn_heads, precision=precision)
     assert list(net.state_dict().keys()) == list(sd.keys())
     net.load_state_dict(sd, strict=True)
     return net.to("cuda").eval()
@@ -54,6 +55,54 @@ def test_forward_matches_reference_golden(golden_dir, name):
     assert err_nc < TOL_BF16, f"{name}: no-cond eps rel-L2 {err_nc:.3e}"
     # repeat call reuses the cached plan and K/V cache and must be deterministic
     assert torch.equal(net(x, t, mf, tf), eps)
+
+
+@pytest.mark.parametrize("name", ["unet_b64", "unet_default", "unet_production"])
+def test_fp32_forward_matches_reference_golden(golden_dir, name):
+    """precision="fp32" (csrc/ref_f32.cu: the same launch plan and weight folds on fp32 slabs with
+    CUDA-core kernels) against the reference's own fp32 outputs: north_star tolerance (i),
+    single-step eps within 1e-4 relative."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = _cfg_from(d["cfg"])
+    net = _model(cfg, orc.random_state_dict(cfg, int(d["seed"])), precision="fp32")
+    x = torch.from_numpy(d["x"]).cuda()
+    t = torch.from_numpy(d["t"]).cuda()
+    mf, tf = torch.from_numpy(d["motion_f"]).cuda(), torch.from_numpy(d["text_f"]).cuda()
+    eps = net(x, t, mf, tf)
+    torch.cuda.synchronize()
+    err = _rel(eps, torch.from_numpy(d["eps"]))
+    assert err < TOL_FP32, f"{name}: fp32 eps rel-L2 {err:.3e}"
+    err_nc = _rel(net(x, t), torch.from_numpy(d["eps_nocond"]))
+    assert err_nc < TOL_FP32, f"{name}: fp32 no-cond eps rel-L2 {err_nc:.3e}"
+    mx = float((eps.cpu() - torch.from_numpy(d["eps"])).abs().max() / torch.from_numpy(d["eps"]).abs().max())
+    assert mx < 5 * TOL_FP32, f"{name}: fp32 eps max-abs / max {mx:.3e}"
+    # switching the same model back to the production path re-packs the weights
+    net.set_precision("bf16")
+    assert _rel(net(x, t, mf, tf), torch.from_numpy(d["eps"])) < TOL_BF16
+
+
+def test_fp32_guided_step_full_length_vs_oracle():
+    """Production architecture, T = Lk = 516, CFG-style rows, precision="fp32": eps within 1e-4 of
+    the fp32 CPU oracle; and two guided DDPM steps through the sampler's (unfused) fp32 path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = orc.UNetConfig.production()
+    sd = orc.random_state_dict(cfg, 5)
+    net = _model(cfg, sd, precision="fp32")
+    g = torch.Generator().manual_seed(77)
+    x1 = torch.randn(1, 80, 516, generator=g)
+    mf1 = torch.randn(1, 516, 128, generator=g)
+    tf1 = torch.randn(1, 516, 128, generator=g)
+    x = torch.cat([x1, x1])
+    mf, tf = torch.cat([mf1 * 0, mf1]), torch.cat([tf1 * 0, tf1])
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        ref = orc.unet_forward(sd, cfg, x, t, mf, tf)
+    eps = net(x.cuda(), t.cuda(), mf.cuda(), tf.cuda())
+    err = _rel(eps, ref)
+    assert err < TOL_FP32, f"fp32 eps rel-L2 {err:.3e}"
 
 
 def test_forward_full_length_vs_oracle():

@@ -14,6 +14,7 @@ LEVELS = [(256, 516), (512, 258), (1024, 129), (1024, 64)]
 lvl = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+COND = len(sys.argv) > 4 and sys.argv[4] == "cond"   # heads attend to the raw condition slabs
 e, t = LEVELS[lvl]
 heads, lk = 8, 516
 tp = [520, 260, 130, 65][lvl]
@@ -30,7 +31,15 @@ for a, b in zip(kv, vt):
 kv_slot = torch.arange(1, B + 1, dtype=torch.int32, device=dev)
 
 
+cond = [(torch.randn(slots * lk, 128, generator=g, device=dev)).to(torch.bfloat16) for _ in range(2)]
+
+
 def run():
+    if COND:
+        assert e // heads == 128
+        ops.cross_attn_cond(q, 2 * e, o, 2 * e, ops._ptr(cond[0]), ops._ptr(cond[1]), 128, kv_slot,
+                            slots, B, tp, t, lk, heads)
+        return
     ops.cross_attn(q, 2 * e, o, 2 * e, ops._ptr(kv[0]), ops._ptr(vt[0]), ops._ptr(kv[1]),
                    ops._ptr(vt[1]), 2 * e, lk_pad, kv_slot, slots, B, tp, t, lk, e, heads)
 

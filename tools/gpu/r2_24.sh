@@ -1,0 +1,12 @@
+#!/bin/bash
+O=gpurun_out/r2_24; mkdir -p $O
+step() { local name=$1 to=$2; shift 2; timeout $to "$@" > $O/$name.log 2>&1; local rc=$?; echo "$name exit $rc" | tee -a $O/summary.txt; tail -8 $O/$name.log; return $rc; }
+step attn 200 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "cross_attention" || exit 0
+for l in 0 1; do timeout 60 python tools/bench_attn.py $l 32 20; done 2>&1 | tee $O/bench.txt
+for l in 2 3; do timeout 60 python tools/bench_attn.py $l 32 20 cond; done 2>&1 | tee -a $O/bench.txt
+for nz in 2 3; do LM2A_ATTN_NZ=$nz timeout 60 python tools/bench_attn.py 0 32 20; done 2>&1 | tee -a $O/bench.txt
+for nz in 2 3; do LM2A_ATTN_NZ=$nz timeout 60 python tools/bench_attn.py 1 32 20; done 2>&1 | tee -a $O/bench.txt
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:cross_attn_res --launch-skip 3 --launch-count 1 -o $O/attn_res_l0 -f python tools/bench_attn.py 0 32 2 > $O/ncu0.log 2>&1; tail -2 $O/ncu0.log
+for m in 0 1 2; do LM2A_CONV_DBG_STATS=$m timeout 200 python tools/bench_conv.py stats$m raw; done 2>&1 | tee $O/conv_stats.txt
+BENCH_NO_STATS=1 timeout 200 python tools/bench_conv.py nostats raw 2>&1 | tee -a $O/conv_stats.txt
+for a in "0" "1" "2 32 5 cond" "3 32 5 cond"; do LM2A_LIB_PATH=tools/probe/liblm2a_b200_probe.so timeout 100 python tools/attn_probe.py run $a; done 2>&1 | tee $O/attn_probe.txt
