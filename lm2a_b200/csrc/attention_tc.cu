@@ -10,11 +10,13 @@
 //   warp 4     TMA producer: Q tile once + a ring of K tiles and a ring of V^T tiles (separate
 //              rings: a K slot is free as soon as S_j is done, a V slot only after P_j V_j)
 //   warp 5     tcgen05.mma issuer (one thread): S_j = Q K_j^T into a double-buffered TMEM
-//              tile, O += P_j V_j with P_j read from shared memory; S_{j+1} is issued
-//              before P_j V_j so the tensor pipe works while the softmax warps run
+//              tile, O += P_j V_j with P_j read from TENSOR MEMORY (.ts operand form: the
+//              softmax warps write the bf16 probabilities over the S tile they came from - no
+//              shared-memory round trip, no proxy fence); S_{j+1} is issued before P_j V_j so
+//              the tensor pipe works while the softmax warps run
 //   warps 0-3  softmax: one query row per thread (TMEM lane), tcgen05.ld of S, running
 //              max with lazy rescaling (O in TMEM is only corrected when the row max grows
-//              by more than 2^8), exp2, row sum, P -> bf16 -> 128B-swizzled shared tile;
+//              by more than 2^8), exp2, row sum, P -> bf16 pairs -> tcgen05.st;
 //              finally O / l -> bf16 slab
 // Query tails (T = 516 / 258 / 129 leave 4 / 2 / 1 rows in a tile of their own): handing those
 // rows to the producer warps of the full tiles (CUDA-core and mma.sync variants, commit
@@ -53,12 +55,12 @@ struct AttnSmem {
   static constexpr int kQBytes = kBQ * DH * 2;
   static constexpr int kKBytes = kBK * DH * 2;
   static constexpr int kVBytes = DH * kBK * 2;
-  static constexpr int kPBytes = kBQ * kBK * 2;
-  // dh = 128: two K + two V stages and one P tile keep a CTA at 112 KB so that two fit an SM;
+  static constexpr int kPBytes = 0;   // P_j lives in tensor memory (over its S tile)
+  // dh = 128: two K + two V stages keep a CTA at 96 KB so that two fit an SM;
   // dh = 384: Q alone is 96 KB, one stage each (208 KB)
   static constexpr int kKStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
   static constexpr int kVStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
-  static constexpr int kPBufs = DH > 64 ? 1 : 2;
+  static constexpr int kPBufs = 2;    // p_full / pv_done barrier pairs (one per S buffer)
   static constexpr int kPOff = kQBytes;
   static constexpr int kKOff = kPOff + kPBufs * kPBytes;
   static constexpr int kVOff = kKOff + kKStages * kKBytes;
@@ -102,6 +104,28 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: P_j is read from tensor memory, where the softmax warps wrote
+// it over the S tile it was computed from (packed bf16 pairs: 8 columns per 16 keys)
+__device__ __forceinline__ void umma_bf16_ts_tc(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7])
+      : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -123,7 +147,6 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t q_base = smem_base;
-  auto p_tile = [&](int b) { return smem_base + L::kPOff + b * L::kPBytes; };
   auto k_tile = [&](int s) { return smem_base + L::kKOff + s * L::kKBytes; };
   auto v_tile = [&](int s) { return smem_base + L::kVOff + s * L::kVBytes; };
   const uint32_t bar_base = smem_base + L::kBarOff;
@@ -250,15 +273,15 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tc_fence_after_sync();
         const int keys = min(kBK, lk - jj * kBK);
         const int ksteps = (keys + 15) >> 4;
-        const uint64_t adesc = umma_desc_kmajor(p_tile(pb), false);
+        const uint32_t p_tmem = tmem_base + (uint32_t)(jj & 1) * kBK;   // P_jj over S_jj
         const uint64_t bdesc = umma_desc_kmajor(v_tile(st), false);
 #pragma unroll
         for (int c = 0; c < L::kVBoxes; ++c) {
           // rows [c * kVBoxRows, ...) of the V^T tile -> O columns of the same range
           const uint64_t bd = bdesc + (uint64_t)((c * L::kVBoxRows * kBK * 2) >> 4);
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ss(tmem_o + c * L::kVBoxRows, adesc + 2u * k, bd + 2u * k, idesc_pv,
-                         (jj | k) != 0 ? 1u : 0u);
+            umma_bf16_ts_tc(tmem_o + c * L::kVBoxRows, p_tmem + 8u * k, bd + 2u * k, idesc_pv,
+                            (jj | k) != 0 ? 1u : 0u);
         }
         umma_commit(v_empty(st));
         umma_commit(pv_done(pb));
@@ -293,8 +316,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const uint32_t p_row = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
 
-    auto softmax_tile = [&](auto nc_tag, int j) {
+    // MASK: only the last key tile of a row can hold keys past Lk; the other tiles carry no
+    // masking code at all (the compiler turns a guarded mask into 64 unconditional selects:
+    // a quarter of the loop's instructions)
+    auto softmax_tile = [&](auto nc_tag, auto mask_tag, int j) {
       constexpr int NC = decltype(nc_tag)::value;   // S columns (keys) of this tile: 64 or 16
+      constexpr bool MASK = decltype(mask_tag)::value;
       const int b = j & 1, pb = j % PB;
       mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
       tc_fence_after_sync();
@@ -316,8 +343,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
 #pragma unroll
         for (int c = 0; c < 16; ++c) s[c] = __uint_as_float(v0[c]);
       }
-      const int keys = lk - j * kBK;
-      if (keys < NC) {
+      if constexpr (MASK) {
+        const int keys = lk - j * kBK;
 #pragma unroll
         for (int c = 0; c < NC; ++c)
           if (c >= keys) s[c] = -INFINITY;
@@ -355,34 +382,31 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_st_wait();
       }
 
-      // the P tile slot is free once P_{j-PB} V_{j-PB} has completed
-      if (j >= PB) mbar_wait(pv_done(pb), (uint32_t)(j / PB - 1) & 1u);
-      const uint32_t pbase = p_tile(pb) + p_row;
+      // P_j overwrites the S tile it was computed from (this thread's own row; the S values are
+      // in registers). S_{j+2}, the next product into this buffer, is issued after P_j V_j and
+      // tcgen05.mma executes in issue order, so nothing else has to be waited for.
       float suma[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[NC / 2];
 #pragma unroll
-      for (int c = 0; c < NC / 8; ++c) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p0 = ex2_approx(s[c * 8 + 2 * i] - m_used);
-          const float p1 = ex2_approx(s[c * 8 + 2 * i + 1] - m_used);
-          suma[i] += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
-        }
-        const uint32_t addr = pbase + (((uint32_t)c ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]),
-                     "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                     : "memory");
+      for (int c = 0; c < NC / 2; ++c) {
+        const float p0 = ex2_approx(s[2 * c] - m_used);
+        const float p1 = ex2_approx(s[2 * c + 1] - m_used);
+        suma[c & 3] += p0 + p1;
+        pk[c] = pack_bf16x2(p0, p1);
       }
       l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
-      fence_proxy_async_smem();
+      if constexpr (NC == 64) tmem_st_32x32(tmem_base + lane_off + b * kBK, pk);
+      else tmem_st_32x8(tmem_base + lane_off + b * kBK, pk);
+      tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(p_full(pb));
     };
-    const int wide_tiles = short_last ? ntiles - 1 : ntiles;
+    using W64 = std::integral_constant<int, kBK>;
+    using W16 = std::integral_constant<int, 16>;
 #pragma unroll 1
-    for (int j = 0; j < wide_tiles; ++j) softmax_tile(std::integral_constant<int, kBK>{}, j);
-    if (short_last) softmax_tile(std::integral_constant<int, 16>{}, ntiles - 1);
+    for (int j = 0; j < ntiles - 1; ++j) softmax_tile(W64{}, std::false_type{}, j);
+    if (short_last) softmax_tile(W16{}, std::true_type{}, ntiles - 1);
+    else softmax_tile(W64{}, std::true_type{}, ntiles - 1);
 
     // ---- finalise: O / l -> bf16 slab
     mbar_wait(o_full, 0);

@@ -374,7 +374,7 @@ class UNetPlan:
         self._flat = flat
         self._norm = None   # normalised operands of the launches that do not transform in-kernel
         # widest operand (channels) normalised / upsampled inside the consuming conv
-        self.xf_max_c = int(os.environ.get("LM2A_XF_MAX_C", "512"))
+        self.xf_max_c = int(os.environ.get("LM2A_XF_MAX_C", "256"))
         self.up_xf_max_c = int(os.environ.get("LM2A_UP_XF_MAX_C", "512"))
         if self.fp32:
             self.xf_max_c = self.up_xf_max_c = 1 << 30
@@ -487,11 +487,12 @@ class UNetPlan:
 
     def _gn_operand(self, x, x_ld, x_off, x_st, gn, nr, tp, tv, c):
         """Input of a conv that follows GroupNorm + SiLU: (slab, ld, element offset, in_gn).
-        Narrow operands (c <= xf_max_c) are normalised inside the conv (operand transform: the
-        launch is load- / latency-bound there and the transform is free); wide operands feed
-        MMA-bound GEMMs, where the transform's shared-memory traffic costs more than one
-        streaming gn_apply pass in front of a plain launch (measured per level on B200, see
-        DESIGN.md). Both paths evaluate the same arithmetic from the same exact sums: the
+        Narrow operands (c <= xf_max_c = 256: level 0) are normalised inside the conv (operand
+        transform: the launch is load- / latency-bound there and the transform is free); wider
+        operands feed MMA-bound GEMMs, where the transform's shared-memory traffic costs more
+        than one streaming gn_apply pass in front of a plain launch (measured per level on B200:
+        1.938 ms/step with the threshold at 256, 1.957 at 512, 2.19 with every operand
+        transformed in-kernel). Both paths evaluate the same arithmetic from the same exact sums: the
         choice does not change a bit of the result. Clips too short for the transform also take
         the stand-alone pass."""
         gm, bt, groups, eps = gn

@@ -83,12 +83,13 @@ def test_geometry_and_plan():
     pm = PackedModel(net, torch.device("cpu"))
     plan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
     kinds = [m["kind"] for _, _, m in plan.ops]
-    # every GroupNorm + SiLU runs inside the conv that consumes it (operand transform): 31 of
-    # the 47 GEMM launches carry one, no stand-alone normalisation launch is left
-    assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 0
-    assert sum(1 for _, _, m in plan.ops if m.get("in_gn")) == 31
+    # at base 64 every GroupNorm + SiLU up to 256 channels runs inside the conv that consumes it
+    # (operand transform): 30 of the 47 GEMM launches carry one; the single wider operand (the
+    # 512-channel concat slab of the deepest up block) takes a streaming gn_apply pass
+    assert kinds.count("conv_gemm") == 47 and kinds.count("gn_apply") == 1
+    assert sum(1 for _, _, m in plan.ops if m.get("in_gn")) == 30
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
-    assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 59
+    assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 60
     # the x2 interpolation of the three UpSampleConvs runs inside their convs
     assert kinds.count("upsample2x") == 0 and sum(1 for _, _, m in plan.ops if m.get("up2x")) == 3
     # (clips too short for the operand transform would fall back to the stand-alone gn_apply
@@ -101,15 +102,17 @@ def test_geometry_and_plan():
     bp = UNetPlan(big, 2, 516, 516, 2, 2, True, torch.device("cpu"))
     assert abs(bp.flops() / 2 / 1e9 - 28.23) < 0.02
     assert abs(sum(m.get("flops_executed", m["flops"]) for _, _, m in bp.ops) / 2 / 1e9 - 29.58) < 0.02
-    # production CFG step (B = 32, uncond shortcut, shared leading rows): operands up to 512
-    # channels are normalised / upsampled inside their conv (17 + 1 launches), the wider ones
-    # (MMA-bound GEMMs) by 14 streaming gn_apply and 2 upsample2x passes in front of plain launches
+    # production CFG step (B = 32, uncond shortcut, shared leading rows): operands of 256 channels
+    # (level 0) are normalised / upsampled inside their conv (9 + 1 launches), the wider ones
+    # (MMA-bound GEMMs) by 22 streaming gn_apply and 2 upsample2x passes in front of plain
+    # launches; the five d_h = 128 attention blocks attend to the raw condition slabs
     cfgp = UNetPlan(big, 64, 516, 516, 33, 2, True, torch.device("cpu"), uniform_t=True,
                     uncond_rows=32)
     ck = [m["kind"] for _, _, m in cfgp.ops]
-    assert len(cfgp.ops) == 84 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
-    assert ck.count("gn_apply") == 14 and ck.count("upsample2x") == 2
-    assert sum(1 for _, _, m in cfgp.ops if m.get("in_gn")) == 17
+    assert len(cfgp.ops) == 92 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
+    assert ck.count("gn_apply") == 22 and ck.count("upsample2x") == 2
+    assert sum(1 for _, _, m in cfgp.ops if m.get("in_gn")) == 9
+    assert sum(1 for _, _, m in cfgp.ops if m.get("cond")) == 5
     with pytest.raises(RuntimeError, match="multiples of 64"):
         PackedModel(UNet1D_ultimate(80, 16, (1, 2, 4), 32, 32, 2, 3, 4), torch.device("cpu"))
 
