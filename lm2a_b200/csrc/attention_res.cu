@@ -10,14 +10,14 @@
 //
 // One CTA = one K/V group (clip-row, stream, head) - or, in COND mode, one (clip-row, stream)
 // whose 8 heads all attend to the same operand - times a 1/nz share of its query tiles:
-//   warp 8      TMA producer: K chunks (64 keys each, one mbarrier per chunk so the first S
+//   producer    one warp, TMA: K chunks (64 keys each, one mbarrier per chunk so the first S
 //               product starts when the first chunk lands), V^T chunks, then the Q tiles
-//   warps 9-10  tcgen05.mma issuers, one thread per tile slot: S_j = Q K_j^T into a
+//   issuers     one warp (one thread) per tile slot, tcgen05.mma: S_j = Q K_j^T into a
 //               double-buffered TMEM tile per slot; O += P_j V_j with P_j read from TENSOR
 //               MEMORY (the .ts operand form: the softmax warps write the bf16 probabilities
 //               over the S tile they were computed from - no shared-memory round trip, no proxy
 //               fence); S_{j+1} is issued before P_j V_j
-//   warps 0-3   softmax of tile slot 0, warps 4-7 of slot 1: one query row per thread, running
+//   softmax     four warps per tile slot: one query row per thread, running
 //               max with lazy rescaling, exp2, row sum, P -> bf16 -> tcgen05.st; at the end of a
 //               tile O / l -> bf16 slab. Two warps per scheduler keep the MUFU pipe fed.
 // TMEM (512 columns): per slot S[0] 64 | S[1] 64 | O up to 128.
@@ -57,8 +57,8 @@ namespace {
 
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
-constexpr int kSlots = 2;
-constexpr int kResThreads = 32 * 11;   // 8 softmax warps, TMA producer, two MMA issuers
+// per tile slot: 4 softmax warps and one MMA-issuing warp; one TMA producer warp per CTA
+__host__ __device__ constexpr int res_threads(int slots) { return 32 * (5 * slots + 1); }
 constexpr int kMaxChunks = 20;         // keys resident: up to 1280
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kQBoxRows = 16;          // rows per Q TMA box (tail tiles pack heads in 16-row units)
@@ -173,8 +173,11 @@ __device__ __forceinline__ TileInfo decode_tile(const ResArgs& p, int hpg, int t
   return t;
 }
 
-template <int DH, bool COND>
-__global__ void __launch_bounds__(kResThreads, 1)
+// SLOTS: query tiles in flight per CTA. 2 (one CTA per SM, all 512 TMEM columns) when the
+// resident operand fills the SM (COND, d_h = 64); 1 with two CTAs per SM where two operands fit
+// (d_h = 32: 88 KB each), so that the CTAs hide each other's prologue, loads and tail tiles.
+template <int DH, bool COND, int SLOTS>
+__global__ void __launch_bounds__(res_threads(SLOTS), SLOTS == 1 ? 2 : 1)
 cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
                       const __grid_constant__ CUtensorMap tmKm,
                       const __grid_constant__ CUtensorMap tmKt,
@@ -186,6 +189,8 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
   const uint32_t smem_base = smem_u32(smem_raw);
   // layout: Q[2] | K panels (k_rows rows each) | V^T chunks | barriers
   const uint32_t k_panel_bytes = (uint32_t)p.k_rows * C::kRowBytes;
+  constexpr int kSlots = SLOTS;
+  constexpr int kProdWarp = 4 * SLOTS;       // warps [0, 4 SLOTS): softmax; then producer; then issuers
   const uint32_t k_base = smem_base + kSlots * C::kQBytes;
   const uint32_t v_base = k_base + C::kPanels * k_panel_bytes;
   const uint32_t bar_base = v_base + (uint32_t)p.nchunks * C::kVChunkBytes;
@@ -215,7 +220,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
   const int my_tiles = z < n_tiles ? (n_tiles - z + p.nz - 1) / p.nz : 0;
   const int nch = p.nchunks;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == kProdWarp && lane == 0) {
     if ((smem_base & 1023u) != 0) {
       printf("lm2a: attention shared memory base not 1024-byte aligned\n");
       __trap();
@@ -241,8 +246,8 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
     mbar_fence_init();
   }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 512);
+  if (warp == kProdWarp + 1) {
+    tmem_alloc(tmem_slot, 256u * SLOTS);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -264,7 +269,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == 8) {
+  if (warp == kProdWarp) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0 && my_tiles > 0) {
       const int slot = p.kv_slot[r];
@@ -296,7 +301,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
       };
       load_k(0);
       load_q(0, z);
-      if (my_tiles > 1) load_q(1, z + p.nz);
+      if (kSlots > 1 && my_tiles > 1) load_q(1, z + p.nz);
       for (int j = 1; j < nch; ++j) load_k(j);
       if (!COND) {
         for (int j = 0; j < nch; ++j) {
@@ -307,18 +312,18 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
       }
       // remaining Q tiles: slot sl is reloaded once the last S product of its tile is done
       for (int i = kSlots; i < my_tiles; ++i) {
-        const int sl = i & 1;
-        mbar_wait(q_free(sl), (uint32_t)((i >> 1) - 1) & 1u);
+        const int sl = i % kSlots;
+        mbar_wait(q_free(sl), (uint32_t)(i / kSlots - 1) & 1u);
         load_q(sl, z + i * p.nz);
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp > kProdWarp) {
     // ------------------------------------------- MMA issuers: warp 9 -> slot 0, warp 10 -> slot 1
     // One thread per tile slot, so neither slot waits behind the other's barriers, and a lean
     // loop: every descriptor is precomputed and advanced by a constant per chunk (the issuing
     // thread's own instruction latency is on the critical path S_j -> softmax -> P_j V_j).
-    const int sl = warp - 9;
-    const int slot_tiles = my_tiles > sl ? (my_tiles - sl + 1) >> 1 : 0;
+    const int sl = warp - kProdWarp - 1;
+    const int slot_tiles = my_tiles > sl ? (my_tiles - sl + kSlots - 1) / kSlots : 0;
     if (lane == 0 && slot_tiles > 0) {
       constexpr uint32_t kMajorB = COND ? (1u << 16) : 0u;   // P.V: B = C read MN-major
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
@@ -425,12 +430,12 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
     const int row = wq * 32 + lane;      // query row of the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     uint32_t phs0 = 0, phs1 = 0;   // parity of the current s_full / pv_done phase per S buffer
-    const int my_slot_tiles = my_tiles > sl ? (my_tiles - sl + 1) >> 1 : 0;
+    const int my_slot_tiles = my_tiles > sl ? (my_tiles - sl + kSlots - 1) / kSlots : 0;
 #ifdef LM2A_ATTN_TIMING
     long long t_sw = 0, t_loop = 0, t_pb = 0, t_ld = 0, t_st = 0, n_chunks = 0;
 #endif
     for (int it = 0; it < my_slot_tiles; ++it) {
-      const int ti = z + (2 * it + sl) * p.nz;
+      const int ti = z + (kSlots * it + sl) * p.nz;
       const TileInfo t = decode_tile(p, hpg, ti);
       const int g = row / t.rb;
       const int tq = t.q0 + (row - g * t.rb);
@@ -599,9 +604,9 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kProdWarp + 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256u * SLOTS);
   }
 }
 
@@ -634,7 +639,7 @@ struct ResPlan {
 
 // Shared-memory footprint of the resident operands; false when the keys do not fit (the
 // caller falls back to the streaming kernel). No device query: usable for planning on the host.
-template <int DH, bool COND>
+template <int DH, bool COND, int SLOTS>
 bool res_fits(int lk, ResPlan* out) {
   using C = ResCfg<DH, COND>;
   ResArgs& a = out->a;
@@ -642,7 +647,7 @@ bool res_fits(int lk, ResPlan* out) {
   if (lk <= 0 || a.nchunks > kMaxChunks) return false;
   a.short_last = (lk - (a.nchunks - 1) * kBK) <= 16 ? 1 : 0;
   a.k_rows = a.nchunks * kBK;   // the last chunk's box is always 64 rows
-  const long long smem = (long long)kSlots * C::kQBytes +
+  const long long smem = (long long)SLOTS * C::kQBytes +
                          (long long)C::kPanels * a.k_rows * C::kRowBytes +
                          (long long)a.nchunks * C::kVChunkBytes + 8ll * (2 * kMaxChunks + 24) + 16;
   if (smem > 227 * 1024) return false;
@@ -651,9 +656,9 @@ bool res_fits(int lk, ResPlan* out) {
 }
 
 // Tile enumeration and the CTA split of one launch.
-template <int DH, bool COND>
+template <int DH, bool COND, int SLOTS>
 bool res_plan(int rows, int n_streams, int heads, int t_valid, int lk, ResPlan* out) {
-  if (!res_fits<DH, COND>(lk, out)) return false;
+  if (!res_fits<DH, COND, SLOTS>(lk, out)) return false;
   ResArgs& a = out->a;
   const int hpg = COND ? heads : 1;
   a.n_full = t_valid / kBQ;
@@ -674,13 +679,13 @@ bool res_plan(int rows, int n_streams, int heads, int t_valid, int lk, ResPlan* 
     return e != nullptr ? atoi(e) : 0;
   }();
   const long long groups = (long long)rows * out->groups_y;
-  const int sms = num_sms() > 0 ? num_sms() : 148;
+  const int sms = (num_sms() > 0 ? num_sms() : 148) * (SLOTS == 1 ? 2 : 1);   // resident CTAs
   int best = 1;
   double best_cost = -1.0;
   for (int nz = 1; nz <= n_tiles; ++nz) {
     const long long waves = (groups * nz + sms - 1) / sms;
     const int per = (n_tiles + nz - 1) / nz;
-    const double cost = (double)waves * ((per + 1) / 2 + 0.3);
+    const double cost = (double)waves * ((per + SLOTS - 1) / SLOTS + 0.3) * (SLOTS == 1 ? 0.5 : 1.0);
     if (best_cost < 0 || cost < best_cost - 1e-9) {
       best_cost = cost;
       best = nz;
@@ -690,12 +695,12 @@ bool res_plan(int rows, int n_streams, int heads, int t_valid, int lk, ResPlan* 
   return true;
 }
 
-template <int DH, bool COND>
+template <int DH, bool COND, int SLOTS>
 int launch_res(cudaStream_t st, const ResPlan& pl, const void* q, int q_ld, const void* k_m,
                const void* vt_m, const void* k_t, const void* vt_t, int k_ld, int vt_ld, int slots,
                int rows, int tp, int lk, int e, int ekv, int n_streams) {
   using C = ResCfg<DH, COND>;
-  auto kern = cross_attn_res_kernel<DH, COND>;
+  auto kern = cross_attn_res_kernel<DH, COND, SLOTS>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured))
     LM2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -720,7 +725,7 @@ int launch_res(cudaStream_t st, const ResPlan& pl, const void* q, int q_ld, cons
       return 1;
   }
   dim3 grid(pl.a.nz, pl.groups_y, rows);
-  LM2A_CUDA_OK(launch_kernel(kern, grid, dim3(kResThreads), (size_t)pl.smem_bytes, st, tq, tkm, tkt,
+  LM2A_CUDA_OK(launch_kernel(kern, grid, dim3(res_threads(SLOTS)), (size_t)pl.smem_bytes, st, tq, tkm, tkt,
                              tvm, tvt, pl.a));
   LM2A_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -748,8 +753,16 @@ int cross_attn_resident(cudaStream_t st, const void* q, int q_ld, void* o, int o
   const int dh = e / heads;
   ResPlan pl{};
   bool ok = false;
-  if (dh == 32) ok = res_plan<32, false>(rows, n_streams, heads, t_valid, lk, &pl);
-  else if (dh == 64) ok = res_plan<64, false>(rows, n_streams, heads, t_valid, lk, &pl);
+  // d_h = 32: two single-slot CTAs per SM when two operand sets fit (else one two-slot CTA)
+  bool two_ctas = false;
+  if (dh == 32) {
+    ResPlan probe{};
+    two_ctas = res_fits<32, false, 1>(lk, &probe) && 2 * probe.smem_bytes + 4096 <= 227 * 1024;
+    ok = two_ctas ? res_plan<32, false, 1>(rows, n_streams, heads, t_valid, lk, &pl)
+                  : res_plan<32, false, 2>(rows, n_streams, heads, t_valid, lk, &pl);
+  } else if (dh == 64) {
+    ok = res_plan<64, false, 2>(rows, n_streams, heads, t_valid, lk, &pl);
+  }
   if (!ok) return -1;
   pl.a.o = reinterpret_cast<__nv_bfloat16*>(o);
   pl.a.o_ld = o_ld;
@@ -760,11 +773,14 @@ int cross_attn_resident(cudaStream_t st, const void* q, int q_ld, void* o, int o
   pl.a.heads = heads;
   pl.a.e = e;
   pl.a.ekv = e;
+  if (dh == 32 && two_ctas)
+    return launch_res<32, false, 1>(st, pl, q, q_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, slots, rows,
+                                    tp, lk, e, e, n_streams);
   if (dh == 32)
-    return launch_res<32, false>(st, pl, q, q_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, slots, rows,
-                                 tp, lk, e, e, n_streams);
-  return launch_res<64, false>(st, pl, q, q_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, slots, rows, tp,
-                               lk, e, e, n_streams);
+    return launch_res<32, false, 2>(st, pl, q, q_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, slots, rows,
+                                    tp, lk, e, e, n_streams);
+  return launch_res<64, false, 2>(st, pl, q, q_ld, k_m, vt_m, k_t, vt_t, k_ld, vt_ld, slots, rows,
+                                  tp, lk, e, e, n_streams);
 }
 
 }  // namespace lm2a
@@ -780,7 +796,7 @@ extern "C" int lm2a_attn_timing_read(unsigned long long* out16) {
 extern "C" int lm2a_cross_attn_cond_supported(int32_t lk) {
   using namespace lm2a;
   ResPlan pl{};
-  return res_fits<128, true>(lk, &pl) ? 1 : 0;
+  return res_fits<128, true, 2>(lk, &pl) ? 1 : 0;
 }
 
 extern "C" int lm2a_cross_attn_cond_bf16(void* stream, const void* q, int32_t q_ld, void* o,
@@ -807,7 +823,7 @@ extern "C" int lm2a_cross_attn_cond_bf16(void* stream, const void* q, int32_t q_
                  reinterpret_cast<uintptr_t>(cond_text)) & 15) == 0,
                "cross_attn_cond: tensors must be 16-byte aligned");
   ResPlan pl{};
-  LM2A_REQUIRE((res_plan<DH, true>(rows, n_streams, heads, t_valid, lk, &pl)),
+  LM2A_REQUIRE((res_plan<DH, true, 2>(rows, n_streams, heads, t_valid, lk, &pl)),
                "cross_attn_cond: %d keys do not fit in shared memory (see "
                "lm2a_cross_attn_cond_supported)", lk);
   pl.a.o = reinterpret_cast<__nv_bfloat16*>(o);
@@ -819,7 +835,7 @@ extern "C" int lm2a_cross_attn_cond_bf16(void* stream, const void* q, int32_t q_
   pl.a.heads = heads;
   pl.a.e = e;
   pl.a.ekv = 0;
-  return launch_res<DH, true>(reinterpret_cast<cudaStream_t>(stream), pl, q, q_ld, cond_motion,
+  return launch_res<DH, true, 2>(reinterpret_cast<cudaStream_t>(stream), pl, q, q_ld, cond_motion,
                               nullptr, cond_text, nullptr, cond_ld, 0, slots, rows, tp, lk, e, 0,
                               n_streams);
 }

@@ -8,7 +8,7 @@ import json
 import sys
 
 FAMILIES = ["conv_gemm", "cross_attn", "gn_apply", "gn_silu", "film_kernel", "time_mlp", "ingest_x",
-            "ingest_seq", "upsample2x", "cfg_posterior", "bias_add", "transpose_kv"]
+            "ingest_seq", "upsample2x", "cfg_posterior", "cfg_step", "philox", "bias_add", "transpose_kv"]
 UNIT = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3,
         "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
