@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 11
+#define LM2A_ABI_VERSION 10
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -137,15 +137,7 @@ typedef struct lm2a_conv_desc {
    * the in_gn_* / in_up_* launches accumulate in, so that a plain launch over a
    * pre-normalised / pre-upsampled slab reproduces them bit for bit.              */
   int32_t k_order;
-  /* Split-K (plain launches only: no in_gn_* / in_up_*, k_order = 0): 2 = a cluster of
-   * two CTAs per 128-slot output tile, each accumulating half of the K blocks; the
-   * second hands its fp32 partial tile to the first through split_ws (L2) and the
-   * first adds it - own half first, then the peer's: a fixed order - before the normal
-   * epilogue. For launches with too few tiles to fill the chip (2 * tiles <= SMs) and a
-   * long K. split_ws: fp32, ceil(m / 128) * (n_pad / block_n) * 128 * block_n floats,
-   * 16-byte aligned, private to the launches of one stream. 0 / 1 = off.             */
-  int32_t split_k;
-  void* split_ws;
+  int32_t _pad0;
 } lm2a_conv_desc;
 
 int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d);

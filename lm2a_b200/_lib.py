@@ -29,10 +29,10 @@ class ConvDesc(ctypes.Structure):
                 ("in_gn_stats", c_void_p), ("in_gn_gamma", c_void_p), ("in_gn_beta", c_void_p),
                 ("in_gn_pitch", c_int32), ("in_gn_groups", c_int32), ("in_gn_eps", c_float),
                 ("in_gn_silu", c_int32), ("in_up_tp", c_int32), ("in_up_t", c_int32),
-                ("k_order", c_int32), ("split_k", c_int32), ("split_ws", c_void_p)]
+                ("k_order", c_int32), ("_pad0", c_int32)]
 
 
-ABI_VERSION = 11
+ABI_VERSION = 10
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 

@@ -107,9 +107,6 @@ struct ConvArgs {
   int share_taps;             // 1: one A block serves all taps (row-shifted views); 0: one
                               //    128-slot box per tap
   int tap_outer;              // plain launches: K walk order (1: tap outer, channel block inner)
-  int split_k;                // 2: a cluster of two CTAs per tile, each walking half of the K blocks
-  int kb_half;                // K blocks of the first half (split_k == 2)
-  float* split_ws;            // fp32 partial tiles of the second CTA: [tile][128 x BLOCK_N]
   int dbg_stats;              // timing experiments only: 1 = sums without atomics, 2 = atomics only
   int dbg_noshift;            // timing experiments only: every tap reads the unshifted view
   int dbg_noxform;            // timing experiments only: transform warps pass blocks through
@@ -142,7 +139,7 @@ struct SmemLayout {
   static constexpr int kMrOffset = kGammaOffset + (XF == 1 ? 2 * kMaxGnChannels * 4 : 0);
   static constexpr int kRowInfoOffset = kMrOffset + (XF == 1 ? kMaxGnEntries * 8 : 0);
   static constexpr int kBarOffset = kRowInfoOffset + (XF == 1 ? kASlotRows * 4 : 0);
-  static constexpr int kNumBars = 4 * kAStages + 2 * kBStages + 4 + 1;   // + split-K hand-off
+  static constexpr int kNumBars = 4 * kAStages + 2 * kBStages + 4;
   static constexpr int kBytes = kBarOffset + 8 * kNumBars + 16 + 1024;  // + tmem slot + align
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
 };
@@ -200,10 +197,8 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // segment's tensor map. on_b(shift, kb): tap view `shift` rows into the A block, W K-block kb.
 // share_taps == 0: every tap gets a 128-slot box of its own (row0 = the tap's shift, view 0).
 template <typename FA, typename FB>
-__device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_b, int kb_lo = 0,
-                                          int kb_hi = 0x7fffffff) {
+__device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_b) {
   int kb_base = 0;
-  int kbi = 0;   // running K-block index of the tap-outer walk (split-K range [kb_lo, kb_hi))
 #pragma unroll 1
   for (int seg = 0; seg < 2; ++seg) {
     const int cblk = p.seg_cblk[seg];
@@ -223,8 +218,7 @@ __device__ __forceinline__ void walk_tile(const ConvArgs& p, FA&& on_a, FB&& on_
           choff = (tap == 0 || tap == 2) ? p.seg_half[seg] : 0;
         }
 #pragma unroll 1
-        for (int cb = 0; cb < cblk; ++cb, ++kbi) {
-          if (kbi < kb_lo || kbi >= kb_hi) continue;
+        for (int cb = 0; cb < cblk; ++cb) {
           on_a(seg, cb, row0, choff + cb * kBlockK);
           on_b(0, kb_base + tap * cblk + cb);
         }
@@ -306,7 +300,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   auto tfull_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 2 + s); };
   auto x_done = [&](int s) { return bar_base + 8u * (3 * NA + 2 * NB + 4 + s); };
-  const uint32_t split_bar = bar_base + 8u * (L::kNumBars - 1);
   const uint32_t tmem_slot = bar_base + 8u * L::kNumBars;
   auto a_slot = [&](int s) { return smem_base + L::kAOffset + s * L::kASlot; };
   auto b_slot = [&](int s) { return smem_base + L::kBOffset + s * L::kBSlotBytes; };
@@ -315,14 +308,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
-  // split-K (CG = 1 only): a cluster of two CTAs shares every tile; `part` 1 walks the second
-  // half of the K blocks and hands its fp32 partial to part 0 through L2
-  const bool split = CG == 1 && p.split_k == 2;
-  const int part = split ? (int)cluster_ctarank() : 0;
-  const int kb_lo = part ? p.kb_half : 0;
-  const int kb_hi = (split && part == 0) ? p.kb_half : 0x7fffffff;
-  const int unit = (CG == 2 || split) ? (int)blockIdx.x >> 1 : (int)blockIdx.x;   // tile-walking unit
-  const int num_units = (CG == 2 || split) ? (int)gridDim.x >> 1 : (int)gridDim.x;
+  const int unit = CG == 2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x;       // tile-walking unit
+  const int num_units = CG == 2 ? (int)gridDim.x >> 1 : (int)gridDim.x;
   // XF launches hand every A block to the transform warps (a_full -> transform / pass-through
   // -> a_ready); plain launches let the TMA complete straight on the barrier the MMA waits on
   constexpr bool xform = XF == 1;
@@ -347,7 +334,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 32 * kEpiWarps * CG);
     }
-    mbar_init(split_bar, 32 * kEpiWarps);
     mbar_fence_init();
   }
   constexpr uint32_t tmem_cols = 2u * BLOCK_N;
@@ -370,7 +356,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     }
   }
   tc_fence_before_sync();
-  if (CG == 2 || split) cluster_sync_all(); else __syncthreads();   // (split: peer barrier is live)
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -395,7 +381,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                   mbar_expect_tx(b_full(s), bytes);
                   tma_load_2d(b_slot(s), &tmB, kb * kBlockK, n0, b_full(s));
                 }
-              }, kb_lo, kb_hi);
+              });
   }
   pdl_wait();
   pdl_launch_dependents();
@@ -454,7 +440,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                 sb = 0;
                 pb ^= 1u;
               }
-            }, kb_lo, kb_hi);
+            });
       }
     }
   } else if (warp == 1) {
@@ -506,7 +492,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
                 sb = 0;
                 pb ^= 1u;
               }
-            }, kb_lo, kb_hi);
+            });
         if (a_open) {
           if (CG == 2) umma_commit_cg2(a_empty(cur_a)); else umma_commit(a_empty(cur_a));
         }
@@ -764,7 +750,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
     const int gmask = p.stats_cg | p.stats_c0;
     const int gran = gmask % 32 == 0 ? 32 : (gmask % 16 == 0 ? 16 : 8);
 
-    uint32_t acc = 0, acc_phase = 0, split_it = 0;
+    uint32_t acc = 0, acc_phase = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_tile0 = (tile / p.n_tiles) * (kBlockM * CG) + cta_rank * kBlockM;
       const long long m = (long long)m_tile0 + row;
@@ -809,35 +795,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quad * 32) << 16);
-      // split-K: this warp's [32 slots][BLOCK_N / 2 columns] block of the tile's fp32 partial,
-      // one 128-byte line per lane and 32-column chunk
-      float* ws_lane = nullptr;
-      if (split) {
-        ws_lane = p.split_ws + ((size_t)tile * kEpiWarps + ew) * (32 * kHalfN) + (size_t)lane * 32;
-        if (part == 1) {
-          // second half of K: raw accumulator -> workspace, then release it to the peer CTA
-#pragma unroll 1
-          for (int c0 = 0; c0 < kHalfN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + half * kHalfN + c0, v);
-            tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(ws_lane + (size_t)(c0 / 32) * (32 * 32));
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          }
-          tc_fence_before_sync();
-          mbar_arrive(tempty_bar(acc));
-          mbar_arrive_cluster(mapa_shared(split_bar, 0));   // release.cluster: partial is visible
-          acc ^= 1u;
-          if (acc == 0) acc_phase ^= 1u;
-          ++split_it;
-          continue;
-        }
-        mbar_wait_cluster(split_bar, split_it & 1u);        // acquire.cluster
-        ++split_it;
-      }
 
       // GroupNorm sums of the output: per-lane exact integer sums of the group being walked
       int st_g = -1;
@@ -865,23 +822,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         tmem_ld_32x32(taddr + c0, v);
         float f[32];
         const uint32_t tcol = tab_base + (uint32_t)(c0 - half * kHalfN) * 8u;
-        float4 pp[8];
-        if (split) {   // the peer's half-K partial of this chunk (L2; written before its release)
-          const float4* src = reinterpret_cast<const float4*>(
-              ws_lane + (size_t)((c0 - half * kHalfN) / 32) * (32 * 32));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pp[j] = __ldcg(src + j);
-        }
         tmem_ld_wait();
-        if (split) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + pp[j].x);
-            v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + pp[j].y);
-            v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + pp[j].z);
-            v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + pp[j].w);
-          }
-        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float4 ab;
@@ -1065,7 +1006,6 @@ int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
   return 0;
 }
 
-// args.split_k == 2 (CG = 1 launches only): clusters of two CTAs, one tile per cluster and pass
 template <int BLOCK_N, int CG, int XF>
 int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
            const CUtensorMap& b, const CUtensorMap& o, const ConvArgs& args) {
@@ -1076,11 +1016,10 @@ int launch(cudaStream_t stream, const CUtensorMap& a0, const CUtensorMap& a1,
     LM2A_CUDA_OK(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kBytes));
   const int tiles = args.m_tiles * args.n_tiles;
-  const int csz = (CG == 1 && args.split_k == 2) ? 2 : CG;   // CTAs per tile-walking unit
-  const int units = num_sms() / csz;  // CTAs, CTA pairs (CG = 2) or split-K clusters that fit
-  const int grid = (tiles < units ? tiles : units) * csz;
+  const int units = num_sms() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) that fit the chip
+  const int grid = (tiles < units ? tiles : units) * CG;
   LM2A_CUDA_OK(launch_kernel_cluster(kern, dim3(grid), dim3(num_threads(XF != 0, CG)), L::kBytes, stream,
-                                     (unsigned)csz, a0, a1, b, o, args));
+                                     (unsigned)CG, a0, a1, b, o, args));
   count_launch();
   return 0;
 }
@@ -1251,11 +1190,6 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
       cg = c.cg;
     }
   }
-  if (d->split_k == 2) {
-    // split-K: one CTA per 128-slot tile and K half; the widest tile the output allows
-    cg = 1;
-    if (d->block_n == 0) block_n = d->n_pad % 256 == 0 ? 256 : 128;
-  }
   LM2A_REQUIRE((block_n == 128 || block_n == 256) && d->n_pad % block_n == 0,
                "conv1d: block_n=%d incompatible with n_pad=%d", block_n, d->n_pad);
   LM2A_REQUIRE(cg == 1 || cg == 2, "conv1d: cta_group=%d (0 = auto, 1 or 2)", cg);
@@ -1353,20 +1287,6 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
       encode_2d_out(&tmOut, d->out, (uint64_t)d->n_valid, (uint64_t)d->m, (uint64_t)d->out_ld))
     return 1;
   const int xf = a.gn_stats != nullptr ? 1 : (a.up_src != nullptr ? 2 : 0);
-  LM2A_REQUIRE(d->split_k == 0 || d->split_k == 1 || d->split_k == 2, "conv1d: split_k=%d", d->split_k);
-  if (d->split_k == 2) {
-    LM2A_REQUIRE(xf == 0 && a.tap_outer == 1,
-                 "conv1d: split_k needs a plain launch in the default K order (no operand "
-                 "transform, k_order = 0)");
-    LM2A_REQUIRE(d->split_ws != nullptr && (reinterpret_cast<uintptr_t>(d->split_ws) & 15) == 0,
-                 "conv1d: split_k needs a 16-byte aligned fp32 workspace of m_tiles * n_tiles * "
-                 "128 * block_n floats");
-    const int nkb = k_total / kBlockK;
-    LM2A_REQUIRE(nkb >= 2, "conv1d: split_k needs at least two K blocks");
-    a.split_k = 2;
-    a.kb_half = (nkb + 1) / 2;
-    a.split_ws = reinterpret_cast<float*>(d->split_ws);
-  }
 #define LM2A_CONV_LAUNCH(BN, CGV)                                                         \
   (xf == 1 ? launch<BN, CGV, 1>(st, tmA[0], tmA[1], tmB, tmOut, a)                        \
            : (xf == 2 ? launch<BN, CGV, 2>(st, tmA[0], tmA[1], tmB, tmOut, a)             \

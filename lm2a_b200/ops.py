@@ -126,7 +126,7 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
                    film=None, film_col=0, film_shift_off=0, film_bcast=False, film_row=0,
                    residual=None, res_ld=0,
                    res_chan_off=0, out_mode=OUT_BF16_SLAB, block_n=0, stats=None, cta_group=0,
-                   in_gn=None, up2x=None, k_order=0, split_ws=None):
+                   in_gn=None, up2x=None, k_order=0):
     """Builds the (reusable) descriptor of one lm2a_conv1d_bf16 launch. Keeps the tensors
     alive by attaching them to the descriptor object.
     in_gn = (Stats view of segs[0]'s slab, gamma, beta, eps, silu): GroupNorm (+ SiLU) applied to
@@ -172,9 +172,7 @@ def make_conv_desc(segs, w, bias, n_valid, m, tp, t_valid, out, out_ld, out_chan
     if up2x is not None:
         d.in_up_tp, d.in_up_t = up2x
     d.k_order = k_order   # 1: accumulate in the operand-transform launches' order (bit-for-bit)
-    if split_ws is not None:   # fp32 workspace: split K over a cluster of two CTAs per tile
-        d.split_k, d.split_ws = 2, split_ws.data_ptr()
-    d._keep = (segs, w, bias, film, residual, out, stats, in_gn, split_ws)
+    d._keep = (segs, w, bias, film, residual, out, stats, in_gn)
     return d
 
 

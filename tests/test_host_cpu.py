@@ -31,8 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_conv_desc_struct_matches_header_layout():
     from lm2a_b200 import _lib
     assert ctypes.sizeof(_lib.ConvSeg) == 32
-    assert ctypes.sizeof(_lib.ConvDesc) == 240 and _lib.ConvDesc.k_order.offset == 224
-    assert _lib.ConvDesc.split_ws.offset == 232
+    assert ctypes.sizeof(_lib.ConvDesc) == 232 and _lib.ConvDesc.k_order.offset == 224
     assert _lib.ConvDesc.out.offset == 136 and _lib.ConvDesc.m.offset == 80
     assert _lib.ConvDesc.stats.offset == 152 and _lib.ConvDesc.in_gn_stats.offset == 176
 
