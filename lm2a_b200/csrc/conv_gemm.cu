@@ -79,6 +79,7 @@ struct ConvArgs {
   int seg_cblk[2];   // cin / 64 per segment
   int seg_taps[2];   // LM2A_TAPS_*
   int seg_half[2];   // K4S2: channel offset of the odd slot inside a slot pair
+  int num_kb;        // 64-deep K blocks per output tile (all segments and taps)
   int m_tiles, n_tiles;
   long long m;
   int tp, t_valid, n_valid;
@@ -453,6 +454,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0,
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         uint32_t started = 0;   // 0 until the first MMA of the tile (which overwrites D)
+        if constexpr (XF == 0) {
+          // Plain launches: every stage holds one A box and its W box, consumed strictly in
+          // ring order - the issuing thread does not need to know segments or taps. Its own
+          // instruction stream sits between two barrier hand-offs of every K block, so the loop
+          // is as short as it gets: descriptors advance by a constant per stage.
+          constexpr uint64_t kStageStep = (uint64_t)(L::kASlot >> 4);
+          constexpr uint64_t kBStageStep = (uint64_t)(L::kBSlotBytes >> 4);
+          const uint64_t adesc0 = umma_desc_sw128_kmajor(a_slot(0));
+          const uint64_t bdesc0 = umma_desc_sw128_kmajor(b_slot(0));
+#pragma unroll 1
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(b_full(sb), pb);
+            tc_fence_after_sync();
+            const uint64_t adesc = adesc0 + (uint64_t)sb * kStageStep;
+            const uint64_t bdesc = bdesc0 + (uint64_t)sb * kBStageStep;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (CG == 2)
+                umma_bf16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, started);
+              else
+                umma_bf16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, started);
+              started = 1u;
+            }
+            if (CG == 2) umma_commit_cg2(b_empty(sb)); else umma_commit(b_empty(sb));
+            if (++sb == NB) {
+              sb = 0;
+              pb ^= 1u;
+            }
+          }
+          if (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+          acc ^= 1u;
+          if (acc == 0) acc_phase ^= 1u;
+          continue;
+        }
         uint32_t cur_a = 0;
         bool a_open = false;
         walk_tile(
@@ -1206,6 +1241,7 @@ extern "C" int lm2a_conv1d_bf16(void* stream, const lm2a_conv_desc* d) {
     tmA[0] = tmB;
     if (d->seg[1].x == nullptr) tmA[1] = tmB;
   }
+  a.num_kb = k_total / kBlockK;
   a.m_tiles = (int)((d->m + kBlockM * cg - 1) / (kBlockM * cg));
   a.n_tiles = d->n_pad / block_n;
   a.m = d->m;
