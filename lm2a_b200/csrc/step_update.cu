@@ -38,23 +38,35 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// standard normal for element (ch, t) of a clip at counter word `step`
+// the four standard normals of counter block (ch, t / 4) of a clip at counter word `step`:
+// components 0 / 1 = Box-Muller (cos, sin) of (r.x, r.y), components 2 / 3 of (r.z, r.w)
+__device__ __forceinline__ void philox_normal4(uint2 key, int ch, int tq, int t4, uint32_t step,
+                                               float (&z)[4]) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)(ch * t4 + tq), step, 0u, 0u), key);
+  const uint32_t a[2] = {r.x, r.z}, b[2] = {r.y, r.w};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // u in (0, 1): 24 random bits + half a step, exactly representable in fp32
+    const float u1 = __fmaf_rn((float)(a[h] >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+    const float u2 = __fmaf_rn((float)(b[h] >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    z[2 * h] = rad * cs;
+    z[2 * h + 1] = rad * sn;
+  }
+}
+// standard normal for element (ch, t)
 __device__ __forceinline__ float philox_normal(uint2 key, int ch, int t, int t4, uint32_t step) {
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)(ch * t4 + (t >> 2)), step, 0u, 0u), key);
-  const int comp = t & 3;
-  const uint32_t a = comp < 2 ? r.x : r.z, b = comp < 2 ? r.y : r.w;
-  // u in (0, 1): 24 random bits + half a step, exactly representable in fp32
-  const float u1 = __fmaf_rn((float)(a >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
-  const float u2 = __fmaf_rn((float)(b >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
-  const float rad = sqrtf(-2.0f * logf(u1));
-  float sn, cs;
-  sincospif(2.0f * u2, &sn, &cs);
-  return rad * ((comp & 1) ? sn : cs);
+  float z[4];
+  philox_normal4(key, ch, t >> 2, t4, step, z);
+  return z[t & 3];
 }
 
-// One CTA = one clip x 32 consecutive slots x all channels (the tile lm2a_ingest_x uses): reads
-// are coalesced along t per channel, the updated tile is transposed through shared memory into
-// channels-last bf16 slab rows.
+// One CTA = one clip x 32 consecutive slots x all channels (the tile lm2a_ingest_x uses). A
+// thread owns (channel, group of four consecutive slots) items: one Philox block yields the four
+// normals it needs, x / eps move as 16-byte vectors when T is a multiple of 4; the updated tile
+// is transposed through shared memory into channels-last bf16 slab rows written 16 bytes at a time.
 __global__ void __launch_bounds__(256)
 cfg_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
                 const float* __restrict__ noise, const unsigned long long* __restrict__ clip_seed,
@@ -72,7 +84,6 @@ cfg_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
   __shared__ float tile[32][129];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long t_now = t_dev[b];
   const float4 co = __ldg(reinterpret_cast<const float4*>(sched) + t_now);
   const float coef1 = co.x, coef2 = co.y, sigma = co.z;
@@ -84,39 +95,85 @@ cfg_step_kernel(float* __restrict__ x, const float* __restrict__ eps,
   }
   const int t4 = (T + 3) >> 2;
   const size_t clip = (size_t)c * T;
-  const int t = t0 + tx;
-  for (int ch = ty; ch < c; ch += 8) {
-    float xn = 0.f;
-    if (t < T) {
-      const size_t i = (size_t)b * clip + (size_t)ch * T + t;
-      float e;
-      if (guided) {
-        const float eu = __ldg(eps + i), ec = __ldg(eps + i + (size_t)batch * clip);
-        const float d = clamp_nan(__fsub_rn(ec, eu), -5.0f, 5.0f);
-        e = clamp_nan(__fadd_rn(eu, __fmul_rn(gw, d)), -10.0f, 10.0f);
+  const bool vec = (T & 3) == 0;   // rows of x / eps are 16-byte aligned
+  // items: (channel, slot group): 8 groups of four slots per tile, groups fastest (coalesced)
+  for (int it = threadIdx.x; it < c * 8; it += 256) {
+    const int ch = it >> 3, g = it & 7;
+    const int tb = t0 + g * 4;
+    float xn[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tb < T) {
+      const size_t i0 = (size_t)b * clip + (size_t)ch * T + tb;
+      const int nv = min(4, T - tb);
+      float xv[4] = {0.f, 0.f, 0.f, 0.f}, eu[4] = {0.f, 0.f, 0.f, 0.f}, ec[4] = {0.f, 0.f, 0.f, 0.f};
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) {
+        const float4 a = *reinterpret_cast<const float4*>(x + i0);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(eps + i0));
+        eu[0] = e0.x; eu[1] = e0.y; eu[2] = e0.z; eu[3] = e0.w;
+        if (guided) {
+          const float4 e1 = __ldg(reinterpret_cast<const float4*>(eps + i0 + (size_t)batch * clip));
+          ec[0] = e1.x; ec[1] = e1.y; ec[2] = e1.z; ec[3] = e1.w;
+        }
+        if (add_noise && noise != nullptr) {
+          const float4 n4 = __ldg(reinterpret_cast<const float4*>(noise + i0));
+          nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+        }
       } else {
-        e = __ldg(eps + i);
+        for (int k = 0; k < nv; ++k) {
+          xv[k] = x[i0 + k];
+          eu[k] = __ldg(eps + i0 + k);
+          if (guided) ec[k] = __ldg(eps + i0 + k + (size_t)batch * clip);
+          if (add_noise && noise != nullptr) nz[k] = __ldg(noise + i0 + k);
+        }
       }
-      float nz = 0.f;
-      if (add_noise)
-        nz = noise != nullptr ? __ldg(noise + i) : philox_normal(key, ch, t, t4, (uint32_t)t_now);
-      xn = __fadd_rn(__fmul_rn(coef1, __fsub_rn(x[i], __fmul_rn(coef2, e))), __fmul_rn(sigma, nz));
-      x[i] = xn;
-      if (eps_out != nullptr) eps_out[i] = e;
+      if (add_noise && noise == nullptr) philox_normal4(key, ch, tb >> 2, t4, (uint32_t)t_now, nz);
+      float ev[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float e = eu[k];
+        if (guided) {
+          const float d = clamp_nan(__fsub_rn(ec[k], eu[k]), -5.0f, 5.0f);
+          e = clamp_nan(__fadd_rn(eu[k], __fmul_rn(gw, d)), -10.0f, 10.0f);
+        }
+        ev[k] = e;
+        xn[k] = __fadd_rn(__fmul_rn(coef1, __fsub_rn(xv[k], __fmul_rn(coef2, e))),
+                          __fmul_rn(sigma, nz[k]));
+        if (k >= nv) xn[k] = 0.f;
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(x + i0) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        if (eps_out != nullptr)
+          *reinterpret_cast<float4*>(eps_out + i0) = make_float4(ev[0], ev[1], ev[2], ev[3]);
+      } else {
+        for (int k = 0; k < nv; ++k) {
+          x[i0 + k] = xn[k];
+          if (eps_out != nullptr) eps_out[i0 + k] = ev[k];
+        }
+      }
     }
-    tile[tx][ch] = xn;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tile[g * 4 + k][ch] = xn[k];
   }
   if (slab != nullptr) {
     __syncthreads();
-    for (int tl = ty; tl < 32; tl += 8) {
+    // 16-byte chunks of 8 channels: ld / 8 chunks per slot
+    const int cpr = ld >> 3;
+    for (int it = threadIdx.x; it < 32 * cpr; it += 256) {
+      const int tl = it / cpr, cg8 = (it - tl * cpr) * 8;
       const int ts = t0 + tl;
-      if (ts >= tp) break;
-      for (int cc = tx; cc < ld; cc += 32) {
-        const float v = (cc < c && ts < T) ? tile[tl][cc] : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        for (int k = 0; k < copies; ++k)
-          slab[((size_t)(k * batch + b) * tp + ts) * ld + cc] = h;
+      if (ts >= tp) continue;
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c0 = cg8 + 2 * e;
+        const float v0 = (c0 < c && ts < T) ? tile[tl][c0] : 0.f;
+        const float v1 = (c0 + 1 < c && ts < T) ? tile[tl][c0 + 1] : 0.f;
+        w[e] = pack_bf16x2(v0, v1);
       }
+      const uint4 q = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int k = 0; k < copies; ++k)
+        *reinterpret_cast<uint4*>(slab + ((size_t)(k * batch + b) * tp + ts) * ld + cg8) = q;
     }
   }
   if (advance) {
@@ -172,8 +229,10 @@ extern "C" int lm2a_cfg_step(void* stream, float* x, const float* eps, const flo
   LM2A_REQUIRE((reinterpret_cast<uintptr_t>(sched) & 15) == 0,
                "cfg_step: the schedule table must be 16-byte aligned");
   if (slab != nullptr) {
-    LM2A_REQUIRE(copies > 0 && tp >= t && ld >= c && ld <= 128,
-                 "cfg_step: bad slab geometry (copies=%d tp=%d ld=%d)", copies, tp, ld);
+    LM2A_REQUIRE(copies > 0 && tp >= t && ld >= c && ld <= 128 && ld % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(slab) & 15) == 0,
+                 "cfg_step: bad slab geometry (copies=%d tp=%d ld=%d; ld %% 8 == 0, 16-byte base)",
+                 copies, tp, ld);
   }
   LM2A_REQUIRE(zero_bytes >= 0 && zero_bytes % 16 == 0 &&
                    (zero_bytes == 0 || (zero != nullptr &&
