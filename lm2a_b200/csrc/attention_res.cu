@@ -520,16 +520,8 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
               res_tmem_st32(tm_o(sl) + lane_off + c0, ov);
             }
           }
-          float suma[4] = {0.f, 0.f, 0.f, 0.f};
           uint32_t pk[NC / 2];
-#pragma unroll
-          for (int c = 0; c < NC / 2; ++c) {
-            const float p0 = res_ex2(s[2 * c] - m_used);
-            const float p1 = res_ex2(s[2 * c + 1] - m_used);
-            suma[c & 3] += p0 + p1;
-            pk[c] = pack_bf16x2(p0, p1);
-          }
-          l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
+          l_run += softmax_probs<NC, MASK>(s, m_used, pk);   // exp2 over the XU and FMA pipes
           // a dedicated P buffer is free once P_{j-2} V_{j-2} (the previous phase of this
           // buffer's barrier) has completed; within a tile only - tiles end on o_full
           LM2A_T0(tpb);

@@ -38,12 +38,25 @@ namespace {
 
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
-constexpr int kThreads = 192;  // 4 softmax warps, TMA producer, MMA issuer
+// d_h = 32: THREE CTAs per SM. The softmax warps need ~136 registers, so three CTAs of 192 threads
+// do not fit the register file (two earlier attempts capped the registers instead: spills, or S
+// re-read from TMEM in halves - both slower). Instead the CTA is launched as two warpgroups at
+// 80 registers per thread and re-balanced with setmaxnreg: the softmax warpgroup grows to 136,
+// the producer / issuer warpgroup (two of its warps only pad the warpgroup) shrinks to 24.
+// 12 softmax warps per SM instead of 8: the kernel is latency-bound (ncu: XU pipe 42 % busy,
+// 1.46 IPC per SM, a quarter of the softmax warps' samples waiting for the first S tile of
+// their CTA), not MUFU-bound - moving a quarter of the exp2 to the FMA pipe changed nothing.
+#ifndef LM2A_ATTN_TRI
+#define LM2A_ATTN_TRI 1
+#endif
 constexpr uint32_t kTmemColsS = 128;  // two 64-column S tiles
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int DH>
 struct AttnSmem {
+  static constexpr bool kTri = LM2A_ATTN_TRI && DH == 32;   // three CTAs per SM (see above)
+  static constexpr int kThreads = kTri ? 256 : 192;  // 4 softmax warps, TMA producer, MMA issuer
+  static constexpr int kCtasPerSm = kTri ? 3 : 2;
   static constexpr int kPanelW = DH % 64 == 0 ? 64 : 32;  // channel panels of the Q / K tiles
   static constexpr int kPanels = DH / kPanelW;
   static constexpr bool kSw64 = kPanelW == 32;
@@ -69,7 +82,8 @@ struct AttnSmem {
   static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
   // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
   // third is never scheduled
-  static constexpr int kBytes = kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded;
+  // (kTri: the register file admits exactly three 256-thread CTAs at 80 registers)
+  static constexpr int kBytes = kTri ? kNeeded : (kNeeded < 80 * 1024 ? 80 * 1024 : kNeeded);
   static_assert(DH % 32 == 0 && DH >= 32 && DH <= 384, "head dim");
   static_assert(kBytes <= 227 * 1024, "shared memory budget");
   // TMEM: S = 128 columns + O = DH columns rounded up to a power of two; dh > 256 takes the
@@ -133,7 +147,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int DH>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(AttnSmem<DH>::kThreads, AttnSmem<DH>::kCtasPerSm)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmKm,
                      const __grid_constant__ CUtensorMap tmKt,
@@ -221,7 +235,10 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   pdl_wait();
   pdl_launch_dependents();
 
+  // kTri: each role's code is dominated by its own setmaxnreg (ptxas budgets the registers of a
+  // region from the setmaxnreg that dominates it); warps 6, 7 only complete the warpgroup
   if (warp == 4) {
+    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     // ------------------------------------------------------------- TMA producer
     // Q, then K_{j+1} before V_j: a K slot frees when S_{j+1-KS} is done, a V slot when
     // P_{j-VS} V_{j-VS} is done, which happen in this order
@@ -261,6 +278,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       }
     }
   } else if (warp == 5) {
+    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
@@ -308,7 +326,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       issue_pv(ntiles - 1);
       umma_commit(o_full);
     }
-  } else if (warp < valid_warps) {
+  } else if (warp > 5) {
+    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  } else {
+    if constexpr (L::kTri) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    if (warp < valid_warps) {
     // ------------------------------------------------------------------ softmax
     const int row = warp * 32 + lane;  // TMEM lane == query row of the tile
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
@@ -385,16 +407,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       // P_j overwrites the S tile it was computed from (this thread's own row; the S values are
       // in registers). S_{j+2}, the next product into this buffer, is issued after P_j V_j and
       // tcgen05.mma executes in issue order, so nothing else has to be waited for.
-      float suma[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[NC / 2];
-#pragma unroll
-      for (int c = 0; c < NC / 2; ++c) {
-        const float p0 = ex2_approx(s[2 * c] - m_used);
-        const float p1 = ex2_approx(s[2 * c + 1] - m_used);
-        suma[c & 3] += p0 + p1;
-        pk[c] = pack_bf16x2(p0, p1);
-      }
-      l_run += (suma[0] + suma[1]) + (suma[2] + suma[3]);
+      l_run += softmax_probs<NC, MASK>(s, m_used, pk);   // exp2 split over the XU and FMA pipes
       if constexpr (NC == 64) tmem_st_32x32(tmem_base + lane_off + b * kBK, pk);
       else tmem_st_32x8(tmem_base + lane_off + b * kBK, pk);
       tmem_st_wait();
@@ -430,6 +444,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
           *reinterpret_cast<uint4*>(op + c0 + c) = q;
         }
       }
+    }
     }
   }
 
@@ -495,7 +510,7 @@ int launch_attn(cudaStream_t st, const void* q, int q_ld, void* o, int o_ld, con
                  L::kVBoxRows, false))
     return 1;
   dim3 grid((t_valid + kBQ - 1) / kBQ, n_streams * heads, rows);
-  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kThreads), smem_bytes, st, tq, tkm, tkt, tvm, tvt,
+  LM2A_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(L::kThreads), smem_bytes, st, tq, tkm, tkt, tvm, tvt,
                                           reinterpret_cast<__nv_bfloat16*>(o), o_ld, kv_slot, tp,
                                           t_valid, lk, e, heads));
   LM2A_CUDA_OK(cudaGetLastError());

@@ -442,6 +442,102 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return __bfloat1622float2(h);
 }
 
+// ---------------------------------------------------------------- softmax probabilities
+// p_c = exp2(s_c - m) for one query row's NC scores of a key tile, packed to bf16 pairs, and
+// their fp32 sum (reference models/cross_attention.py:50-61: the softmax inside
+// nn.MultiheadAttention; log2(e)/sqrt(d_h) is folded into W_q, so it is a bare exp2).
+// The attention kernels are bound by the XU pipe (MUFU.EX2: 4 lanes/clk per scheduler = 8 cycles
+// per warp instruction, 64 per thread and key tile) while the FMA pipe idles. LM2A_SOFTMAX_POLY =
+// k in 0..4: of every four score PAIRS, k are evaluated on the FMA pipe instead - round to
+// nearest integer n with the 1.5 * 2^23 trick, degree-3 polynomial for 2^f on f = x - n in
+// [-0.5, 0.5] (max relative error 7.5e-5, 50x below the bf16 rounding of P that follows), n
+// added into the exponent field - as packed f32x2 instructions (FADD2 / FFMA2: two lanes per
+// issue slot), so that the loop's issue rate stays below the MUFU time it removes.
+#ifndef LM2A_SOFTMAX_POLY
+#define LM2A_SOFTMAX_POLY 1
+#endif
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_sub(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 2^x for a pair, x <= 8 (lazy-rescale bound); x below -126 is clamped (result 2^-126 ~ 0)
+__device__ __forceinline__ void exp2_pair_fma(float x0, float x1, float& p0, float& p1) {
+  constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: x + kMagic rounds x to an integer
+  const uint64_t x = f32x2_pack(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t magic = f32x2_pack(kMagic, kMagic);
+  const uint64_t t = f32x2_add(x, magic);            // low mantissa bits = n (two's complement)
+  const uint64_t f = f32x2_sub(x, f32x2_sub(t, magic));
+  uint64_t p = f32x2_fma(f32x2_pack(0.0551716611f, 0.0551716611f), f,
+                         f32x2_pack(0.2426111251f, 0.2426111251f));
+  p = f32x2_fma(p, f, f32x2_pack(0.6932609677f, 0.6932609677f));
+  p = f32x2_fma(p, f, f32x2_pack(0.9999280572f, 0.9999280572f));
+  float t0, t1, q0, q1;
+  f32x2_unpack(t, t0, t1);
+  f32x2_unpack(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// MASKED tiles (scores may be -inf) stay on the MUFU path
+template <int NC, bool MASKED>
+__device__ __forceinline__ float softmax_probs(const float (&s)[NC], float m,
+                                               uint32_t (&pk)[NC / 2]) {
+  constexpr int kPoly = MASKED ? 0 : LM2A_SOFTMAX_POLY;
+  if constexpr (kPoly == 0) {
+    float suma[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) {
+      const float p0 = ex2_approx_ftz(s[2 * c] - m);
+      const float p1 = ex2_approx_ftz(s[2 * c + 1] - m);
+      suma[c & 3] += p0 + p1;
+      pk[c] = pack_bf16x2(p0, p1);
+    }
+    return (suma[0] + suma[1]) + (suma[2] + suma[3]);
+  } else {
+    const uint64_t m2 = f32x2_pack(m, m);
+    uint64_t sum2[2] = {0ull, 0ull};
+#pragma unroll
+    for (int c = 0; c < NC / 2; ++c) {
+      float x0, x1, p0, p1;
+      f32x2_unpack(f32x2_sub(f32x2_pack(s[2 * c], s[2 * c + 1]), m2), x0, x1);
+      if ((c & 3) < kPoly) {
+        exp2_pair_fma(x0, x1, p0, p1);
+      } else {
+        p0 = ex2_approx_ftz(x0);
+        p1 = ex2_approx_ftz(x1);
+      }
+      sum2[c & 1] = f32x2_add(sum2[c & 1], f32x2_pack(p0, p1));
+      pk[c] = pack_bf16x2(p0, p1);
+    }
+    float a, b;
+    f32x2_unpack(f32x2_add(sum2[0], sum2[1]), a, b);
+    return a + b;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -376,6 +376,9 @@ class UNetPlan:
         # widest operand (channels) normalised / upsampled inside the consuming conv
         self.xf_max_c = int(os.environ.get("LM2A_XF_MAX_C", "256"))
         self.up_xf_max_c = int(os.environ.get("LM2A_UP_XF_MAX_C", "512"))
+        # launches of at most this many slots (M) take the in-kernel transform at any width: they
+        # fill half of the SMs and are bound by operand ingest, not by the MMA (0 = off)
+        self.xf_max_m = int(os.environ.get("LM2A_XF_MAX_M", "0"))
         if self.fp32:
             self.xf_max_c = self.up_xf_max_c = 1 << 30
         # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
@@ -496,7 +499,8 @@ class UNetPlan:
         choice does not change a bit of the result. Clips too short for the transform also take
         the stand-alone pass."""
         gm, bt, groups, eps = gn
-        if c <= self.xf_max_c and (self.fp32 or ops.in_gn_supported(tp, groups)):
+        if ((c <= self.xf_max_c or nr * tp <= self.xf_max_m)
+                and (self.fp32 or ops.in_gn_supported(tp, groups))):
             return x, x_ld, x_off, (x_st, gm, bt, eps, True)
         if self._norm is None:
             self._norm = [self._flat(), self._flat()]
