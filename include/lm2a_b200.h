@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define LM2A_ABI_VERSION 10
+#define LM2A_ABI_VERSION 11
 
 /* ---- library ---------------------------------------------------------- */
 int lm2a_abi_version(void);
@@ -231,6 +231,25 @@ int lm2a_cross_attn_streams_bf16(void* stream, const void* q, int32_t q_ld,
                                  int32_t slots, int32_t rows, int32_t tp,
                                  int32_t t_valid, int32_t lk, int32_t e,
                                  int32_t heads, int32_t n_streams);
+/* The n_tail <= 8 query rows t0 .. t0 + n_tail - 1 of every (clip-row, stream, head)
+ * on the CUDA cores: the rows that T mod 128 leaves over (4 / 2 / 1 at T = 516 / 258 /
+ * 129). In the tensor-core kernels they cost a CTA slot (or, on the condition slab, a
+ * serial round) of their own; the launch plan runs this kernel on a parallel graph
+ * branch and gives the tensor-core launch t_valid = t0 (whole tiles only). q / o as
+ * in lm2a_cross_attn_streams_bf16 (dh = e / heads in {32, 64, 128}); keys AND values
+ * row-major: k_s / v_s bf16 [slots*lk, k_ld / v_ld], head h at channel h*dh
+ * (shared_kv = 0: the K and V halves of the projection output) or every head at
+ * channels [0, dh) (shared_kv = 1: the raw condition slab of lm2a_cross_attn_cond_bf16
+ * for both, e = heads*128). Probabilities stay fp32 (no bf16 rounding of P); sums in a
+ * fixed order (no atomics). Same reference lines: models/cross_attention.py:50-61.  */
+int lm2a_cross_attn_tail_bf16(void* stream, const void* q, int32_t q_ld, void* o,
+                              int32_t o_ld, const void* k_motion,
+                              const void* v_motion, const void* k_text,
+                              const void* v_text, int32_t k_ld, int32_t v_ld,
+                              const int32_t* kv_slot, int32_t slots, int32_t rows,
+                              int32_t tp, int32_t t0, int32_t n_tail, int32_t lk,
+                              int32_t e, int32_t heads, int32_t n_streams,
+                              int32_t shared_kv);
 /* per-clip V cache transpose: src [slots*lk, src_ld] (c channels) ->
  * dst [slots*c, dst_ld] (lk keys); c multiple of 32.                        */
 int lm2a_transpose_kv_bf16(void* stream, const void* src, int32_t src_ld,

@@ -32,7 +32,7 @@ class ConvDesc(ctypes.Structure):
                 ("k_order", c_int32), ("_pad0", c_int32)]
 
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 TAPS_K1, TAPS_K3, TAPS_K4S2 = 0, 1, 2
 OUT_BF16_SLAB, OUT_F32_NCT = 0, 1
 
@@ -70,6 +70,11 @@ SIGNATURES = {
     "lm2a_cross_attn_cond_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                             c_void_p, c_void_p, c_int32, c_void_p, c_int32,
                                             c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "lm2a_cross_attn_tail_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                            c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                            c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                            c_int32]),
     "lm2a_transpose_kv_bf16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                          c_int32, c_int32]),
     "lm2a_time_mlp": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblm2a_b200.so")
-SOURCES = ["api.cu", "conv_gemm.cu", "gn_silu.cu", "attention_tc.cu", "attention_res.cu", "elementwise.cu",
+SOURCES = ["api.cu", "conv_gemm.cu", "gn_silu.cu", "attention_tc.cu", "attention_res.cu", "attention_tail.cu", "elementwise.cu",
            "step_update.cu", "ref_f32.cu"]
 
 

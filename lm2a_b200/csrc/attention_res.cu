@@ -71,6 +71,7 @@ struct ResArgs {
   int e;         // channels per stream of the q / o slabs (heads * DH)
   int ekv;       // rows per cache slot of the V^T operand (per-head mode: heads * DH)
   int nz;        // CTAs sharing a group's tiles
+  int split_tail;  // 1: the group's tail tiles run in a CTA of their own (the last of the nz)
   int n_full;    // full 128-row tiles per head
   int rb;        // rows per head in a tail tile (16, 32, 64 or 128)
   int gpt;       // heads per tail tile
@@ -210,14 +211,31 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxChunks + 2 * 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.z;
+  // grid (group, clip-row, z): the z index varies slowest, so the CTAs of the last z - with
+  // split_tail the light ones - are dispatched after all others
+  const int r = blockIdx.y;
   const int hpg = COND ? p.heads : 1;                 // heads per K/V group
-  const int stream = COND ? (int)blockIdx.y : (int)blockIdx.y / p.heads;
-  const int hg = COND ? 0 : (int)blockIdx.y % p.heads;  // the group's head (per-head mode)
+  const int stream = COND ? (int)blockIdx.x : (int)blockIdx.x / p.heads;
+  const int hg = COND ? 0 : (int)blockIdx.x % p.heads;  // the group's head (per-head mode)
   const int n_tiles = hpg * p.n_full + p.n_tail;
-  // this CTA's tiles: z, z + nz, ...
-  const int z = blockIdx.x;
-  const int my_tiles = z < n_tiles ? (n_tiles - z + p.nz - 1) / p.nz : 0;
+  // this CTA's tiles: t_start, t_start + t_stride, ... Normally the nz CTAs of a group take its
+  // tiles round-robin. split_tail: nz - 1 CTAs share the full tiles, the last CTA takes the tail
+  // tiles (T mod 128 rows of every head: a few rows per tile, one softmax warp active) - that
+  // CTA is short and runs on an SM the single-wave grid leaves idle, instead of costing one of
+  // the other CTAs a serial round of its own
+  const int z = blockIdx.z;
+  int t_start = z, t_stride = p.nz, my_tiles = z < n_tiles ? (n_tiles - z + p.nz - 1) / p.nz : 0;
+  if (p.split_tail) {
+    const int n_main = hpg * p.n_full, nzm = p.nz - 1;
+    if (z == nzm) {
+      t_start = n_main;
+      t_stride = 1;
+      my_tiles = p.n_tail;
+    } else {
+      t_stride = nzm;
+      my_tiles = z < n_main ? (n_main - z + nzm - 1) / nzm : 0;
+    }
+  }
   const int nch = p.nchunks;
 
   if (warp == kProdWarp && lane == 0) {
@@ -300,8 +318,8 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
                       (COND ? 0 : hg * DH) + pn * C::kPW, slot * p.lk + j * kBK, k_full(j));
       };
       load_k(0);
-      load_q(0, z);
-      if (kSlots > 1 && my_tiles > 1) load_q(1, z + p.nz);
+      load_q(0, t_start);
+      if (kSlots > 1 && my_tiles > 1) load_q(1, t_start + t_stride);
       for (int j = 1; j < nch; ++j) load_k(j);
       if (!COND) {
         for (int j = 0; j < nch; ++j) {
@@ -314,7 +332,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
       for (int i = kSlots; i < my_tiles; ++i) {
         const int sl = i % kSlots;
         mbar_wait(q_free(sl), (uint32_t)(i / kSlots - 1) & 1u);
-        load_q(sl, z + i * p.nz);
+        load_q(sl, t_start + i * t_stride);
       }
     }
   } else if (warp > kProdWarp) {
@@ -435,7 +453,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
     long long t_sw = 0, t_loop = 0, t_pb = 0, t_ld = 0, t_st = 0, n_chunks = 0;
 #endif
     for (int it = 0; it < my_slot_tiles; ++it) {
-      const int ti = z + (kSlots * it + sl) * p.nz;
+      const int ti = t_start + (kSlots * it + sl) * t_stride;
       const TileInfo t = decode_tile(p, hpg, ti);
       const int g = row / t.rb;
       const int tq = t.q0 + (row - g * t.rb);
@@ -684,6 +702,36 @@ bool res_plan(int rows, int n_streams, int heads, int t_valid, int lk, ResPlan* 
     }
   }
   a.nz = (forced_nz > 0 && forced_nz <= n_tiles) ? forced_nz : best;
+  a.split_tail = 0;
+  // Tail tiles in a CTA of their own (see the kernel): worth it when the CTAs of the full tiles
+  // form a single wave that leaves SMs idle, and the light CTAs (a tail tile costs ~0.3 of a
+  // full round; fixed cost of a CTA as above) get through those SMs within the main CTAs' time.
+  // LM2A_ATTN_SPLIT_TAIL: 0 never (default), 1 cost model, 2 whenever possible (tests); read per
+  // call. Measured neutral on B200 at the production shape (T = 129, 8 heads, B = 32: 43.6 vs
+  // 43.3 us): the tail tile spreads its 8 valid rows (one per head, 16-row sub-blocks) over all
+  // four softmax warps and a chunk's time is latency, not work - a "light" CTA takes as long as
+  // a full round, and four waves of them on the 20 idle SMs last as long as the main CTAs.
+  const char* sev = getenv("LM2A_ATTN_SPLIT_TAIL");
+  const int split_mode = sev != nullptr ? atoi(sev) : 0;
+  const int n_main = hpg * a.n_full;
+  if (split_mode == 2) best_cost = 1e30;
+  if (split_mode != 0 && forced_nz == 0 && SLOTS > 1 && a.n_tail > 0 && n_main > 0) {
+    for (int nzm = 1; nzm <= n_main; ++nzm) {
+      const long long main_ctas = groups * nzm;
+      if (main_ctas >= sms) break;
+      const long long free_sms = sms - main_ctas;
+      const int per = (n_main + nzm - 1) / nzm;
+      const double main_cost = (per + SLOTS - 1) / SLOTS + 0.3;
+      const double light = 0.3 * ((a.n_tail + SLOTS - 1) / SLOTS) + 0.3;
+      const double light_cost = (double)((groups + free_sms - 1) / free_sms) * light;
+      const double cost = main_cost > light_cost ? main_cost : light_cost;
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        a.nz = nzm + 1;
+        a.split_tail = 1;
+      }
+    }
+  }
   return true;
 }
 
@@ -716,7 +764,7 @@ int launch_res(cudaStream_t st, const ResPlan& pl, const void* q, int q_ld, cons
                        false))
       return 1;
   }
-  dim3 grid(pl.a.nz, pl.groups_y, rows);
+  dim3 grid(pl.groups_y, rows, pl.a.nz);
   LM2A_CUDA_OK(launch_kernel(kern, grid, dim3(res_threads(SLOTS)), (size_t)pl.smem_bytes, st, tq, tkm, tkt,
                              tvm, tvt, pl.a));
   LM2A_CUDA_OK(cudaGetLastError());

@@ -453,8 +453,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // [-0.5, 0.5] (max relative error 7.5e-5, 50x below the bf16 rounding of P that follows), n
 // added into the exponent field - as packed f32x2 instructions (FADD2 / FFMA2: two lanes per
 // issue slot), so that the loop's issue rate stays below the MUFU time it removes.
+// Measured on B200 (profiles/r2_attn_tri_poly.txt): k = 1 is neutral (84.0 -> 83.6 us at d_h = 32,
+// 72.9 -> 72.7 with three CTAs per SM), k = 2 / 3 slower (85.9 / 90.2 us): the softmax warps are
+// latency-bound, not XU-bound (ncu: XU pipe 42 % busy, 0.36 IPC per scheduler). Default 0.
 #ifndef LM2A_SOFTMAX_POLY
-#define LM2A_SOFTMAX_POLY 1
+#define LM2A_SOFTMAX_POLY 0
 #endif
 __device__ __forceinline__ float ex2_approx_ftz(float x) {
   float y;

@@ -379,6 +379,12 @@ class UNetPlan:
         # launches of at most this many slots (M) take the in-kernel transform at any width: they
         # fill half of the SMs and are bound by operand ingest, not by the MMA (0 = off)
         self.xf_max_m = int(os.environ.get("LM2A_XF_MAX_M", "0"))
+        # leftover query rows of the attention launches on the CUDA cores (parallel branch)
+        # (opt-in: measured slower in the step - 26 / 46 / 25 us per launch at levels 0 / 1 / 2 for
+        # work that saves the tensor-core launches 11 / 16 / 12 us, and its CTAs take registers
+        # the tensor-core CTAs need; the condition-slab kernel gives its tail tile a CTA of its
+        # own instead, attention_res.cu split_tail)
+        self.attn_tail = os.environ.get("LM2A_ATTN_TAIL", "0") == "1"
         if self.fp32:
             self.xf_max_c = self.up_xf_max_c = 1 << 30
         # every GroupNorm statistics buffer of the plan lives in one arena that the step's first
@@ -610,6 +616,36 @@ class UNetPlan:
 
         def attend(q, o, width, n_streams):
             flops = n_streams * 4 * nr * tv * self.lk * e
+            # T mod 128 query rows (4 / 2 / 1 at T = 516 / 258 / 129) on the CUDA cores, on the
+            # parallel branch next to the tensor-core launch, which then covers whole tiles only
+            # (in that kernel the leftover rows cost a CTA slot - on the condition slab a serial
+            # round - of their own); joined in front of the output GEMM
+            tail = tv % 128
+            if (self.attn_tail and not self.fp32 and self.use_side_stream and 0 < tail <= 8 < tv
+                    and e // p.heads in (32, 64, 128)):
+                # keys / values row-major: the condition slabs, or the K | V projection output
+                if cond:
+                    km = vm = ops._ptr(self.cond_m)
+                    kt = vt = ops._ptr(self.cond_t)
+                    ld = cdim
+                else:
+                    km, vm, kt, vt = (ops._ptr(kv_m), ops._ptr(kv_m, e), ops._ptr(kv_t),
+                                      ops._ptr(kv_t, e))
+                    ld = 2 * e
+                self._side_op = True
+                self._add(ops.cross_attn_tail, q, width, o, width, km, vm, kt, vt, ld, ld,
+                          ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv - tail, tail, self.lk,
+                          e, p.heads, n_streams, cond,
+                          meta={"kind": "cross_attn_tail", "flops": 0})
+                self._side_op = False
+                hold, self._hold_join = self._hold_join, True
+                attend_rows(q, o, width, n_streams, tv - tail, flops)
+                self._hold_join = hold
+                self._force_join = True    # the next main launch reads the tail rows of o
+                return
+            attend_rows(q, o, width, n_streams, tv, flops)
+
+        def attend_rows(q, o, width, n_streams, tv, flops):
             if self.fp32:
                 self._add(ops.cross_attn_f32, q, width, o, width, kv_m, kv_t, 2 * e,
                           ops._ptr(self.kv_slot, r0), self.nslots, nr, tp, tv, self.lk, e, p.heads,

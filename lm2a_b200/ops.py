@@ -249,6 +249,17 @@ def cross_attn_cond(q, q_ld, o, o_ld, cond_m, cond_t, cond_ld, kv_slot, slots, r
         t_valid, lk, heads, n_streams), "lm2a_cross_attn_cond_bf16")
 
 
+def cross_attn_tail(q, q_ld, o, o_ld, k_m, v_m, k_t, v_t, k_ld, v_ld, kv_slot, slots, rows, tp,
+                    t0, n_tail, lk, e, heads, n_streams=2, shared_kv=False):
+    """The n_tail (<= 8) query rows from t0 on, per (clip-row, stream, head), on the CUDA cores:
+    the rows T mod 128 leaves over. Keys and values row-major [slots*lk, ld] (pointers);
+    shared_kv: every head reads channels [0, dh) (the raw condition slabs)."""
+    _lib.check(_lib.load().lm2a_cross_attn_tail_bf16(
+        _stream(), _ptr(q), q_ld, _ptr(o), o_ld, k_m, v_m, k_t, v_t, k_ld, v_ld,
+        kv_slot if isinstance(kv_slot, ctypes.c_void_p) else _ptr(kv_slot), slots, rows, tp, t0,
+        n_tail, lk, e, heads, n_streams, 1 if shared_kv else 0), "lm2a_cross_attn_tail_bf16")
+
+
 def transpose_kv(src, src_ld, src_off, dst, dst_ld, slots, lk, c):
     _lib.check(_lib.load().lm2a_transpose_kv_bf16(_stream(), _ptr(src, src_off), src_ld, _ptr(dst),
                                                   dst_ld, slots, lk, c), "lm2a_transpose_kv_bf16")

@@ -70,7 +70,7 @@ def test_cpu_tensors_are_refused():
         net(torch.zeros(1, 80, 64), torch.zeros(1, dtype=torch.long))
 
 
-def test_geometry_and_plan():
+def test_geometry_and_plan(monkeypatch):
     from lm2a_b200.engine import Geometry, PackedModel, UNetPlan
     from lm2a_b200.models import UNet1D_ultimate
     g = Geometry(64, 516, 3)
@@ -90,6 +90,20 @@ def test_geometry_and_plan():
     assert sum(1 for _, _, m in plan.ops if m.get("in_gn")) == 30
     assert kinds.count("cross_attn") == 9 and len(plan.kv_ops) == 36
     assert kinds[:3] == ["time_mlp", "film", "ingest_x"] and len(plan.ops) == 60
+    # opt-in (LM2A_ATTN_TAIL=1): T = 132 leaves 4 query rows over at level 0; the two level-0
+    # attention blocks put them on the CUDA cores, on the parallel branch next to the tensor-core
+    # launch (whole tiles only), joined in front of the output GEMM
+    monkeypatch.setenv("LM2A_ATTN_TAIL", "1")
+    tplan = UNetPlan(pm, 4, 132, 132, 3, 2, True, torch.device("cpu"))
+    monkeypatch.delenv("LM2A_ATTN_TAIL")
+    tk = [m["kind"] for _, _, m in tplan.ops]
+    tails = [i for i, k in enumerate(tk) if k == "cross_attn_tail"]
+    assert len(tails) == 2 and len(tplan.ops) == 62
+    for i in tails:
+        (_, targs, tmeta), (_, margs, mmeta), (_, _, nmeta) = tplan.ops[i], tplan.ops[i + 1], tplan.ops[i + 2]
+        assert tmeta.get("side") and mmeta["kind"] == "cross_attn" and not mmeta.get("join")
+        assert nmeta["kind"] == "conv_gemm" and nmeta.get("join")
+        assert targs[-7:-5] == (128, 4) and margs[-5] == 128    # t0, n_tail | t_valid of the main launch
     # the x2 interpolation of the three UpSampleConvs runs inside their convs
     assert kinds.count("upsample2x") == 0 and sum(1 for _, _, m in plan.ops if m.get("up2x")) == 3
     # (clips too short for the operand transform would fall back to the stand-alone gn_apply
@@ -110,6 +124,7 @@ def test_geometry_and_plan():
                     uncond_rows=32)
     ck = [m["kind"] for _, _, m in cfgp.ops]
     assert len(cfgp.ops) == 92 and abs(cfgp.flops() / 1e9 - 1185.0) < 0.5
+    assert ck.count("cross_attn_tail") == 0 and ck.count("cross_attn") == 9
     assert ck.count("gn_apply") == 22 and ck.count("upsample2x") == 2
     assert sum(1 for _, _, m in cfgp.ops if m.get("in_gn")) == 9
     assert sum(1 for _, _, m in cfgp.ops if m.get("cond")) == 5

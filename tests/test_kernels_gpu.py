@@ -493,9 +493,13 @@ def _attention_core_case(ops, e, heads, t, lk, qgain):
     (2, 516, 640, 1.0),     # four full tiles per head, the largest resident key count
     (8, 17, 16, 1.0),       # a single 16-key chunk; 32-row sub-blocks
 ])
-def test_cross_attention_cond(ops, heads, t, lk, qgain):
+@pytest.mark.parametrize("split", ["0", "2"])
+def test_cross_attention_cond(ops, monkeypatch, heads, t, lk, qgain, split):
     """lm2a_cross_attn_cond_bf16: every head attends to the raw condition sequence itself,
-    softmax(q'_h C^T) C (head dim = condition width = 128), vs fp32 torch."""
+    softmax(q'_h C^T) C (head dim = condition width = 128), vs fp32 torch. split: the tail tiles
+    (T mod 128 rows) in a CTA of their own (LM2A_ATTN_SPLIT_TAIL: never / whenever possible; the
+    default is a cost model)."""
+    monkeypatch.setenv("LM2A_ATTN_SPLIT_TAIL", split)
     r, slots, tp, dh = 3, 2, t + 2, 128
     e = heads * dh
     assert ops.cond_attn_supported(lk) and not ops.cond_attn_supported(700)
@@ -520,6 +524,77 @@ def test_cross_attention_cond(ops, heads, t, lk, qgain):
             assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"cond attention stream {s}")
         if n_streams == 1:
             assert bool((o.view(r, tp, 2 * e)[:, :, e:] == 3.0).all()), "stream 1 was touched"
+
+
+@pytest.mark.parametrize("e,heads,t,lk,qgain,cond", [
+    (256, 8, 516, 516, 1.0, False),    # production level 0: 4 leftover rows, d_h = 32
+    (512, 8, 258, 516, 1.0, False),    # level 1: 2 rows, d_h = 64
+    (1024, 8, 129, 516, 1.0, True),    # level 2 on the condition slab: 1 row
+    (1024, 8, 129, 516, 1.0, False),   # the same block with per-head K / V (d_h = 128)
+    (256, 8, 136, 77, 6.0, False),     # 8 rows, odd Lk, peaked softmax
+    (512, 4, 261, 300, 1.0, True),     # condition mode, 5 rows: one head per CTA
+    (384, 3, 131, 100, 1.0, True),     # condition mode, 3 rows x 2 heads per CTA, odd head count
+])
+def test_cross_attention_tail_rows(ops, e, heads, t, lk, qgain, cond):
+    """lm2a_cross_attn_tail_bf16 (the T mod 128 query rows on the CUDA cores) next to the
+    tensor-core launch over the whole tiles: together they cover every row; vs fp32 torch."""
+    r, slots, tp = 3, 2, t + 2
+    dh = e // heads
+    t0, n_tail = t // 128 * 128, t % 128
+    q = rnd(r, 2 * e, t, seed=36) * qgain
+    kv_slot = torch.tensor([1, 0, 1], dtype=torch.int32, device="cuda")
+    qs = to_slab(q * (1.4426950408889634 / math.sqrt(dh)), tp)
+    lk_pad = (lk + 7) // 8 * 8
+    if cond:
+        assert dh == 128
+        src = [rnd(slots * lk, dh, seed=37 + i).to(BF16) for i in range(2)]
+    else:
+        src = [rnd(slots * lk, 2 * e, seed=37 + i).to(BF16) for i in range(2)]
+        vts = []
+        for kv in src:
+            vt = torch.zeros(slots * e, lk_pad, dtype=BF16, device="cuda")
+            ops.transpose_kv(kv, 2 * e, e, vt, lk_pad, slots, lk, e)
+            vts.append(vt)
+    for n_streams in (2, 1):
+        o = torch.full((r * tp, 2 * e), 3.0, dtype=BF16, device="cuda")
+        if cond:
+            ops.cross_attn_cond(qs, 2 * e, o, 2 * e, ops._ptr(src[0]), ops._ptr(src[1]), dh, kv_slot,
+                                slots, r, tp, t0, lk, heads, n_streams)
+            ops.cross_attn_tail(qs, 2 * e, o, 2 * e, ops._ptr(src[0]), ops._ptr(src[0]),
+                                ops._ptr(src[1]), ops._ptr(src[1]), dh, dh, kv_slot, slots, r, tp,
+                                t0, n_tail, lk, e, heads, n_streams, True)
+        else:
+            ops.cross_attn(qs, 2 * e, o, 2 * e, ops._ptr(src[0]), ops._ptr(vts[0]), ops._ptr(src[1]),
+                           ops._ptr(vts[1]), 2 * e, lk_pad, kv_slot, slots, r, tp, t0, lk, e, heads,
+                           n_streams)
+            # keys and values row-major: the K and V halves of the projection output
+            ops.cross_attn_tail(qs, 2 * e, o, 2 * e, ops._ptr(src[0]), ops._ptr(src[0], e),
+                                ops._ptr(src[1]), ops._ptr(src[1], e), 2 * e, 2 * e, kv_slot, slots,
+                                r, tp, t0, n_tail, lk, e, heads, n_streams, False)
+        torch.cuda.synchronize()
+        got = from_slab(o, r, tp, t, 2 * e)
+        for s in range(n_streams):
+            if cond:
+                cf = src[s].float().view(slots, lk, dh)[kv_slot.long()]
+                k = v = cf[:, None]
+            else:
+                kvf = src[s].float().view(slots, lk, 2 * e)[kv_slot.long()]
+                k = kvf[:, :, :e].view(r, lk, heads, dh).transpose(1, 2)
+                v = kvf[:, :, e:].view(r, lk, heads, dh).transpose(1, 2)
+            qq = qs.float().view(r, tp, 2 * e)[:, :t, s * e:(s + 1) * e] / 1.4426950408889634
+            qq = qq.reshape(r, t, heads, dh).transpose(1, 2)
+            p = torch.softmax(qq @ k.transpose(-1, -2), dim=-1)
+            ref = (p @ v).transpose(1, 2).reshape(r, t, e).permute(0, 2, 1)
+            assert_close(got[:, s * e:(s + 1) * e, t0:], ref[:, :, t0:], 6e-3, f"tail rows, stream {s}")
+            assert_close(got[:, s * e:(s + 1) * e], ref, 1e-2, f"tiles + tail rows, stream {s}")
+        ov = o.view(r, tp, 2 * e)
+        assert bool((ov[:, t:, :] == 3.0).all()), "rows past T were touched"
+        if n_streams == 1:
+            assert bool((ov[:, :, e:] == 3.0).all()), "stream 1 was touched"
+    with pytest.raises(RuntimeError, match="bad geometry"):
+        ops.cross_attn_tail(qs, 2 * e, o, 2 * e, ops._ptr(src[0]), ops._ptr(src[0]), ops._ptr(src[1]),
+                            ops._ptr(src[1]), dh if cond else 2 * e, dh if cond else 2 * e, kv_slot,
+                            slots, r, tp, t0, 9, lk, e, heads, 2, cond)
 
 
 @pytest.mark.parametrize("r,t,tp,c,groups", [(2, 129, 130, 1536, 8), (3, 50, 52, 768, 8),

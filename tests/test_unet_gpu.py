@@ -105,11 +105,15 @@ def test_fp32_guided_step_full_length_vs_oracle():
     assert err < TOL_FP32, f"fp32 eps rel-L2 {err:.3e}"
 
 
-def test_forward_full_length_vs_oracle():
+@pytest.mark.parametrize("attn_tail", ["0", "1"])
+def test_forward_full_length_vs_oracle(monkeypatch, attn_tail):
     """Production architecture at the canonical clip length T = Lk = 516 with CFG-style rows
-    (uncond = zeroed conditions, sample.py:155-163) against the fp32 oracle."""
+    (uncond = zeroed conditions, sample.py:155-163) against the fp32 oracle. attn_tail = 1: the
+    opt-in launch plan with the T mod 128 query rows of the attention launches on the CUDA cores
+    (lm2a_cross_attn_tail_bf16 on the parallel branch; levels 0 / 1 / 2 leave 4 / 2 / 1 rows)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    monkeypatch.setenv("LM2A_ATTN_TAIL", attn_tail)
     cfg = orc.UNetConfig.production()
     sd = orc.random_state_dict(cfg, 5)
     net = _model(cfg, sd)
