@@ -54,7 +54,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 template <int DH>
 struct AttnSmem {
-  static constexpr bool kTri = LM2A_ATTN_TRI && DH == 32;   // three CTAs per SM (see above)
+  static constexpr bool kTri = LM2A_ATTN_TRI && (DH == 32 || DH == 64);   // three CTAs per SM
+  // d_h = 64: S (2 x 64 columns) + O (64) = 192 tensor-memory columns per CTA would only admit two
+  // CTAs. Three fit with ONE S buffer, a separate 32-column P buffer and O behind S (64 + 64 in a
+  // 128-column allocation, + 32): the softmax warps release S as soon as it is in registers
+  // (s_free), so S_{j+1} is still computed under the exp2 work of chunk j; P_j waits for
+  // P_{j-1} V_{j-1} (issued a whole chunk earlier).
+  static constexpr bool kSingleS = kTri && DH == 64;
   static constexpr int kThreads = kTri ? 256 : 192;  // 4 softmax warps, TMA producer, MMA issuer
   static constexpr int kCtasPerSm = kTri ? 3 : 2;
   static constexpr int kPanelW = DH % 64 == 0 ? 64 : 32;  // channel panels of the Q / K tiles
@@ -73,12 +79,12 @@ struct AttnSmem {
   // dh = 384: Q alone is 96 KB, one stage each (208 KB)
   static constexpr int kKStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
   static constexpr int kVStages = DH > 256 ? 1 : (DH > 64 ? 2 : 3);
-  static constexpr int kPBufs = 2;    // p_full / pv_done barrier pairs (one per S buffer)
+  static constexpr int kPBufs = kSingleS ? 1 : 2;   // p_full / pv_done pairs (one per P buffer)
   static constexpr int kPOff = kQBytes;
   static constexpr int kKOff = kPOff + kPBufs * kPBytes;
   static constexpr int kVOff = kKOff + kKStages * kKBytes;
   static constexpr int kBarOff = kVOff + kVStages * kVBytes;
-  static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 1;
+  static constexpr int kNumBars = 1 + 2 * kKStages + 2 * kVStages + 2 + 2 * kPBufs + 2;
   static constexpr int kNeeded = kBarOff + 8 * kNumBars + 8;
   // two CTAs per SM (register budget of the softmax warps): ask for enough shared memory that a
   // third is never scheduled
@@ -90,6 +96,7 @@ struct AttnSmem {
   // whole 512 columns in one allocation (S first, O behind it)
   static constexpr bool kOneAlloc = DH > 256;
   static constexpr uint32_t kTmemColsO = DH <= 32 ? 32 : DH <= 64 ? 64 : DH <= 128 ? 128 : 256;
+  static constexpr uint32_t kTmemColsP = 32;   // kSingleS: the second allocation holds P
 };
 
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr, bool sw64) {
@@ -174,7 +181,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + b); };
   auto pv_done = [&](int b) { return bar_base + 8u * (3 + 2 * KS + 2 * VS + PB + b); };
   const uint32_t o_full = bar_base + 8u * (3 + 2 * KS + 2 * VS + 2 * PB);
-  const uint32_t tmem_slot = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);  // S, then O (+4 B)
+  const uint32_t s_free = bar_base + 8u * (4 + 2 * KS + 2 * VS + 2 * PB);     // kSingleS only
+  const uint32_t tmem_slot = bar_base + 8u * (5 + 2 * KS + 2 * VS + 2 * PB);  // S, then O (+4 B)
+  constexpr bool kSingleS = L::kSingleS;
   constexpr uint32_t kTmemColsO = L::kTmemColsO;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,6 +222,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       mbar_init(pv_done(b), 1);
     }
     mbar_init(o_full, 1);
+    mbar_init(s_free, 32 * valid_warps);
     mbar_fence_init();
   }
   if (warp == 5) {
@@ -220,17 +230,24 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       tmem_alloc(tmem_slot, 512);
     } else {
       tmem_alloc(tmem_slot, kTmemColsS);
-      tmem_alloc(tmem_slot + 4, kTmemColsO);
+      tmem_alloc(tmem_slot + 4, kSingleS ? L::kTmemColsP : kTmemColsO);
     }
     tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  uint32_t tmem_base, tmem_o;
+  uint32_t tmem_base, tmem_o, tmem_p = 0;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (L::kOneAlloc) tmem_o = tmem_base + kTmemColsS;
   else asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_o) : "r"(tmem_slot + 4));
+  if (kSingleS) {   // S in columns [0, 64) and O in [64, 128) of the first allocation, P apart
+    tmem_p = tmem_o;
+    tmem_o = tmem_base + kBK;
+  }
+  // S buffer of chunk j and the parity of its s_full phase
+  auto s_buf = [&](int j) { return kSingleS ? 0 : (j & 1); };
+  auto s_par = [&](int j) { return (uint32_t)(kSingleS ? j : (j >> 1)) & 1u; };
   // everything above overlapped the previous kernel's tail; from here on we touch its output
   pdl_wait();
   pdl_launch_dependents();
@@ -291,7 +308,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tc_fence_after_sync();
         const int keys = min(kBK, lk - jj * kBK);
         const int ksteps = (keys + 15) >> 4;
-        const uint32_t p_tmem = tmem_base + (uint32_t)(jj & 1) * kBK;   // P_jj over S_jj
+        const uint32_t p_tmem =
+            kSingleS ? tmem_p : tmem_base + (uint32_t)(jj & 1) * kBK;   // P_jj over S_jj
         const uint64_t bdesc = umma_desc_kmajor(v_tile(st), false);
 #pragma unroll
         for (int c = 0; c < L::kVBoxes; ++c) {
@@ -306,8 +324,10 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % KS, b = j & 1;
+        const int st = j % KS, b = s_buf(j);
         mbar_wait(k_full(st), (uint32_t)(j / KS) & 1u);
+        // one S buffer: S_{j-1} must be in the softmax warps' registers
+        if (kSingleS && j >= 1) mbar_wait(s_free, (uint32_t)(j - 1) & 1u);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -344,8 +364,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     auto softmax_tile = [&](auto nc_tag, auto mask_tag, int j) {
       constexpr int NC = decltype(nc_tag)::value;   // S columns (keys) of this tile: 64 or 16
       constexpr bool MASK = decltype(mask_tag)::value;
-      const int b = j & 1, pb = j % PB;
-      mbar_wait(s_full(b), (uint32_t)(j >> 1) & 1u);
+      const int b = s_buf(j), pb = j % PB;
+      mbar_wait(s_full(b), s_par(j));
       tc_fence_after_sync();
       float s[NC];
       if constexpr (NC == 64) {
@@ -364,6 +384,10 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 16; ++c) s[c] = __uint_as_float(v0[c]);
+      }
+      if constexpr (kSingleS) {   // S_j is in registers: S_{j+1} may overwrite the buffer
+        tc_fence_before_sync();
+        mbar_arrive(s_free);
       }
       if constexpr (MASK) {
         const int keys = lk - j * kBK;
@@ -409,8 +433,17 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       // tcgen05.mma executes in issue order, so nothing else has to be waited for.
       uint32_t pk[NC / 2];
       l_run += softmax_probs<NC, MASK>(s, m_used, pk);   // exp2 split over the XU and FMA pipes
-      if constexpr (NC == 64) tmem_st_32x32(tmem_base + lane_off + b * kBK, pk);
-      else tmem_st_32x8(tmem_base + lane_off + b * kBK, pk);
+      uint32_t p_addr = tmem_base + lane_off + b * kBK;
+      if constexpr (kSingleS) {
+        // the one P buffer is free once P_{j-1} V_{j-1} has read it (issued a chunk ago)
+        if (j >= 1) {
+          mbar_wait(pv_done(0), (uint32_t)(j - 1) & 1u);
+          tc_fence_after_sync();
+        }
+        p_addr = tmem_p + lane_off;
+      }
+      if constexpr (NC == 64) tmem_st_32x32(p_addr, pk);
+      else tmem_st_32x8(p_addr, pk);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive(p_full(pb));
@@ -456,7 +489,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       tmem_dealloc(tmem_base, 512);
     } else {
       tmem_dealloc(tmem_base, kTmemColsS);
-      tmem_dealloc(tmem_o, kTmemColsO);
+      if (kSingleS) tmem_dealloc(tmem_p, L::kTmemColsP);
+      else tmem_dealloc(tmem_o, kTmemColsO);
     }
   }
 }

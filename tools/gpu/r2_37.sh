@@ -1,0 +1,9 @@
+#!/bin/bash
+# d_h = 64 attention: three CTAs per SM with one S buffer + separate P buffer
+O=gpurun_out/r2_37; mkdir -p $O
+step() { local name=$1 to=$2; shift 2; timeout $to "$@" > $O/$name.log 2>&1; local rc=$?; echo "$name exit $rc" | tee -a $O/summary.txt; tail -4 $O/$name.log; return $rc; }
+step attn_tests 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "attention" || { tail -30 $O/attn_tests.log; exit 0; }
+for lvl in 0 1; do timeout 100 python tools/bench_attn.py $lvl 32 50 2>&1 | tail -1 | sed "s/^/tri+singleS /" | tee -a $O/attn.txt; done
+for lvl in 0 1; do LM2A_LIB_PATH=$PWD/tools/probe/tri0poly0/liblm2a_b200.so timeout 100 python tools/bench_attn.py $lvl 32 50 2>&1 | tail -1 | sed "s/^/two-CTA baseline /" | tee -a $O/attn.txt; done
+step unet_tests 900 python -m pytest tests/test_unet_gpu.py tests/test_sampler_gpu.py tests/test_legacy_gpu.py -q -m gpu -x || { tail -30 $O/unet_tests.log; exit 0; }
+timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu > $O/bench.json 2> $O/bench.err; echo "bench: $(cut -c1-200 $O/bench.json)"
