@@ -411,7 +411,7 @@ def run_b200(args):
 
         # ---- dominant kernel (tcgen05 implicit-GEMM conv) timed live, launch by launch
         plan.t_in.fill_(500)
-        prof = plan.profile(iters=5)
+        prof = plan.profile(iters=10)
         conv = [(m, s) for k, m, s in prof if k == "conv_gemm"]
         conv_s = sum(s for _, s in conv)
         conv_flops = sum(m["flops"] for m, _ in conv)

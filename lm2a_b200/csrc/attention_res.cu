@@ -58,7 +58,18 @@ namespace {
 constexpr int kBQ = 128;
 constexpr int kBK = 64;
 // per tile slot: 4 softmax warps and one MMA-issuing warp; one TMA producer warp per CTA
-__host__ __device__ constexpr int res_threads(int slots) { return 32 * (5 * slots + 1); }
+// Two-slot CTAs carry a twelfth, idle warp: the 8 softmax warps are two warpgroups, and
+// producer + two issuers + the idle warp a third, so the register file can be re-balanced with
+// setmaxnreg (launched at 168 registers per thread - what an 11-warp CTA is granted anyway,
+// warps being allocated in fours - the softmax warpgroups grow to 216, the third shrinks to 72):
+// the softmax / epilogue code of the d_h = 128 build spilled at 168 (ncu: its per-tile epilogue
+// stalled on local-memory reloads).
+__host__ __device__ constexpr int res_threads(int slots) {
+  return slots == 2 ? 32 * 12 : 32 * (5 * slots + 1);
+}
+#ifndef LM2A_RES_REBALANCE
+#define LM2A_RES_REBALANCE 1
+#endif
 constexpr int kMaxChunks = 20;         // keys resident: up to 1280
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 constexpr int kQBoxRows = 16;          // rows per Q TMA box (tail tiles pack heads in 16-row units)
@@ -287,7 +298,9 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
   pdl_wait();
   pdl_launch_dependents();
 
+  constexpr bool kRebalance = LM2A_RES_REBALANCE && SLOTS == 2;
   if (warp == kProdWarp) {
+    if constexpr (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // ------------------------------------------------------------- TMA producer
     if (lane == 0 && my_tiles > 0) {
       const int slot = p.kv_slot[r];
@@ -340,8 +353,10 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
     // One thread per tile slot, so neither slot waits behind the other's barriers, and a lean
     // loop: every descriptor is precomputed and advanced by a constant per chunk (the issuing
     // thread's own instruction latency is on the critical path S_j -> softmax -> P_j V_j).
-    const int sl = warp - kProdWarp - 1;
-    const int slot_tiles = my_tiles > sl ? (my_tiles - sl + kSlots - 1) / kSlots : 0;
+    if constexpr (kRebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int sl = warp - kProdWarp - 1;   // (== kSlots: the idle warp that completes the warpgroup)
+    const int slot_tiles =
+        (sl < kSlots && my_tiles > sl) ? (my_tiles - sl + kSlots - 1) / kSlots : 0;
     if (lane == 0 && slot_tiles > 0) {
       constexpr uint32_t kMajorB = COND ? (1u << 16) : 0u;   // P.V: B = C read MN-major
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
@@ -442,6 +457,7 @@ cross_attn_res_kernel(const __grid_constant__ CUtensorMap tmQ,
 #endif
     }
   } else {
+    if constexpr (kRebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax
     const int sl = warp >> 2;            // tile slot of this warpgroup
     const int wq = warp & 3;             // TMEM lane quadrant

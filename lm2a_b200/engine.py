@@ -991,9 +991,12 @@ class UNetPlan:
             main.wait_stream(side)
         return self.eps
 
-    def _time_op(self, fn, args, iters):
+    def _time_op(self, fn, args, iters, reps=3):
         """Device time of one launch: `iters` back-to-back launches captured in a CUDA Graph,
-        replayed once untimed and once between CUDA events on the launching stream."""
+        replayed twice untimed (the capture leaves the GPU idle for milliseconds: without a warm
+        replay a short burst is timed while the clocks ramp up - the per-launch sum then exceeded
+        the measured step on some boxes) and `reps` times between CUDA events on the launching
+        stream."""
         fn(*args)  # warm (first-launch attribute setup must not happen under capture)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
@@ -1001,14 +1004,16 @@ class UNetPlan:
             for _ in range(iters):
                 fn(*args)
         g.replay()
+        g.replay()
         stream = torch.cuda.current_stream(self.dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        g.replay()
+        for _ in range(reps):
+            g.replay()
         e1.record(stream)
         torch.cuda.synchronize(self.dev)
         del g
-        return e0.elapsed_time(e1) * 1e-3 / iters
+        return e0.elapsed_time(e1) * 1e-3 / (iters * reps)
 
     def autotune(self, iters=5, margin=0.97):
         """Picks the tile shape of every implicit-GEMM launch by measurement instead of the wave
