@@ -57,7 +57,9 @@ def test_torch_custom_ops_are_cuda_only():
     """torch.ops.lm2a.* (lm2a_b200/torch_ops.py) exist with CUDA kernels only: a CPU tensor finds no
     implementation (no fallback was registered)."""
     import lm2a_b200.torch_ops  # noqa: F401
-    for name in ("cfg_posterior", "cfg_ddim", "resample_seq", "mel_metrics", "gn_silu", "upsample2x"):
+    for name in ("cfg_posterior", "cfg_ddim", "resample_seq", "mel_metrics", "gn_silu", "upsample2x",
+                 "conv1d", "cross_attn", "cross_attn_cond", "cross_attn_tail", "transpose_kv",
+                 "time_mlp", "film", "philox_normal"):
         assert hasattr(torch.ops.lm2a, name)
     with pytest.raises(NotImplementedError):
         torch.ops.lm2a.resample_seq(torch.zeros(1, 4, 3), None, 8)
