@@ -41,8 +41,8 @@ constexpr int kBK = 64;
 // d_h = 32: THREE CTAs per SM. The softmax warps need ~136 registers, so three CTAs of 192 threads
 // do not fit the register file (two earlier attempts capped the registers instead: spills, or S
 // re-read from TMEM in halves - both slower). Instead the CTA is launched as two warpgroups at
-// 80 registers per thread and re-balanced with setmaxnreg: the softmax warpgroup grows to 136,
-// the producer / issuer warpgroup (two of its warps only pad the warpgroup) shrinks to 24.
+// 80 registers per thread and re-balanced with setmaxnreg: the softmax warpgroup grows to 128 - 136,
+// the producer / issuer warpgroup (two of its warps only pad the warpgroup) shrinks to 32 - 24.
 // 12 softmax warps per SM instead of 8: the kernel is latency-bound (ncu: XU pipe 42 % busy,
 // 1.46 IPC per SM, a quarter of the softmax warps' samples waiting for the first S tile of
 // their CTA), not MUFU-bound - moving a quarter of the exp2 to the FMA pipe changed nothing.
@@ -153,6 +153,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Register split of a three-CTA build (256 threads launched at 80 registers: softmax warpgroup +
+// other warpgroup = 160). d_h = 32: 128 / 32 - at 24 registers the producer / issuer loops spill
+// and the operand pipeline slows (72.8 vs 68.3 us per launch); d_h = 64: 136 / 24 - its softmax
+// (one S buffer, separate P buffer) spills at 128 (64.0 vs 58.1 us).
+template <int DH>
+__device__ __forceinline__ void tri_regs_softmax() {
+  if constexpr (AttnSmem<DH>::kTri) {
+    if constexpr (DH == 32) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+  }
+}
+template <int DH>
+__device__ __forceinline__ void tri_regs_other() {
+  if constexpr (AttnSmem<DH>::kTri) {
+    if constexpr (DH == 32) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  }
+}
+
 template <int DH>
 __global__ void __launch_bounds__(AttnSmem<DH>::kThreads, AttnSmem<DH>::kCtasPerSm)
 cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -255,7 +274,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   // kTri: each role's code is dominated by its own setmaxnreg (ptxas budgets the registers of a
   // region from the setmaxnreg that dominates it); warps 6, 7 only complete the warpgroup
   if (warp == 4) {
-    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    tri_regs_other<DH>();
     // ------------------------------------------------------------- TMA producer
     // Q, then K_{j+1} before V_j: a K slot frees when S_{j+1-KS} is done, a V slot when
     // P_{j-VS} V_{j-VS} is done, which happen in this order
@@ -295,7 +314,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       }
     }
   } else if (warp == 5) {
-    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    tri_regs_other<DH>();
     // --------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kBQ, kBK);
@@ -347,9 +366,9 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       umma_commit(o_full);
     }
   } else if (warp > 5) {
-    if constexpr (L::kTri) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    tri_regs_other<DH>();
   } else {
-    if constexpr (L::kTri) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    tri_regs_softmax<DH>();
     if (warp < valid_warps) {
     // ------------------------------------------------------------------ softmax
     const int row = warp * 32 + lane;  // TMEM lane == query row of the tile
