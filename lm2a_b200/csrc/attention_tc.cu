@@ -139,6 +139,16 @@ __device__ __forceinline__ void umma_bf16_ts_tc(uint32_t tmem_d, uint32_t tmem_a
       : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -273,6 +283,11 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
 
   // kTri: each role's code is dominated by its own setmaxnreg (ptxas budgets the registers of a
   // region from the setmaxnreg that dominates it); warps 6, 7 only complete the warpgroup
+  // producer / issuer: the lean wait in the three-CTA builds (24 - 32 registers per thread)
+  auto role_wait = [&](uint32_t bar, uint32_t parity) {
+    if constexpr (L::kTri) mbar_wait_lean(bar, parity);
+    else mbar_wait(bar, parity);
+  };
   if (warp == 4) {
     tri_regs_other<DH>();
     // ------------------------------------------------------------- TMA producer
@@ -283,7 +298,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const CUtensorMap* vm = stream ? &tmVt : &tmVm;
     auto load_k = [&](int j) {
       const int st = j % KS;
-      mbar_wait(k_empty(st), ((uint32_t)(j / KS) & 1u) ^ 1u);
+      role_wait(k_empty(st), ((uint32_t)(j / KS) & 1u) ^ 1u);
       mbar_expect_tx(k_full(st), L::kKBytes);
 #pragma unroll
       for (int p = 0; p < L::kPanels; ++p)
@@ -292,7 +307,7 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     };
     auto load_v = [&](int j) {
       const int st = j % VS;
-      mbar_wait(v_empty(st), ((uint32_t)(j / VS) & 1u) ^ 1u);
+      role_wait(v_empty(st), ((uint32_t)(j / VS) & 1u) ^ 1u);
       mbar_expect_tx(v_full(st), L::kVBytes);
 #pragma unroll
       for (int c = 0; c < L::kVBoxes; ++c)
@@ -322,8 +337,8 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kBQ, L::kVBoxRows);
       auto issue_pv = [&](int jj) {
         const int pb = jj % PB, st = jj % VS;
-        mbar_wait(v_full(st), (uint32_t)(jj / VS) & 1u);
-        mbar_wait(p_full(pb), (uint32_t)(jj / PB) & 1u);
+        role_wait(v_full(st), (uint32_t)(jj / VS) & 1u);
+        role_wait(p_full(pb), (uint32_t)(jj / PB) & 1u);
         tc_fence_after_sync();
         const int keys = min(kBK, lk - jj * kBK);
         const int ksteps = (keys + 15) >> 4;
@@ -341,12 +356,12 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         umma_commit(v_empty(st));
         umma_commit(pv_done(pb));
       };
-      mbar_wait(q_full, 0);
+      role_wait(q_full, 0);
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % KS, b = s_buf(j);
-        mbar_wait(k_full(st), (uint32_t)(j / KS) & 1u);
+        role_wait(k_full(st), (uint32_t)(j / KS) & 1u);
         // one S buffer: S_{j-1} must be in the softmax warps' registers
-        if (kSingleS && j >= 1) mbar_wait(s_free, (uint32_t)(j - 1) & 1u);
+        if (kSingleS && j >= 1) role_wait(s_free, (uint32_t)(j - 1) & 1u);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) {
@@ -435,14 +450,16 @@ cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         mbar_wait(pv_done((j - 1) % PB), (uint32_t)((j - 1) / PB) & 1u);
         tc_fence_after_sync();
+        // (16 columns at a time: the 64 scores of the chunk are live across this rare path, and
+        // 32 more registers would push them to local memory in the three-CTA builds)
 #pragma unroll
-        for (int c0 = 0; c0 < DH; c0 += 32) {
-          uint32_t ov[32];
-          tmem_ld_32x32(tmem_o + lane_off + c0, ov);
+        for (int c0 = 0; c0 < DH; c0 += 16) {
+          uint32_t ov[16];
+          tmem_ld_32x16(tmem_o + lane_off + c0, ov);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
-          tmem_st_32x32(tmem_o + lane_off + c0, ov);
+          for (int c = 0; c < 16; ++c) ov[c] = __float_as_uint(__uint_as_float(ov[c]) * corr);
+          tmem_st_32x16(tmem_o + lane_off + c0, ov);
         }
         tmem_st_wait();
       }

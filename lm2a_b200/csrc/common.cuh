@@ -164,6 +164,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// The same bounded wait without the diagnostic printf: for single-thread roles that run at a
+// small setmaxnreg budget (the printf's argument marshalling costs registers and a stack frame
+// in every loop that waits). A protocol bug still traps after ~4 s.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+
 // Wait that may last for a whole mainloop (epilogue warps waiting for an accumulator): the
 // try_wait carries a suspend-time hint, so the eight waiting warps do not keep the MIO queue
 // busy with polls (the default time limit re-polls every ~50 ns) while other warps of the CTA
