@@ -22,10 +22,12 @@
 // rows to the producer warps of the full tiles (CUDA-core and mma.sync variants, commit
 // "attention: tail query rows on the producer warp") measured neutral to slower on B200
 // (92 vs 94 / 67 vs 67 / 64 vs 60 us per launch at levels 0 / 1 / 2) and was removed. Three CTAs
-// per SM at dh = 32 (112-register cap, S walked in two 32-column halves, no spills) measured
-// 112 vs 91 us and was removed as well.
-// TMEM: S[0] cols 0-63, S[1] cols 64-127, O in dh further columns; two CTAs per SM for
-// dh <= 128. Head dims: any multiple of 64 up to 384 (64-channel operand panels, 128B
+// per SM at dh = 32 by CAPPING the registers (112-register cap, S walked in two 32-column halves,
+// no spills) measured 112 vs 91 us and was removed as well; three CTAs per SM by RE-BALANCING
+// the registers between the roles (setmaxnreg, below) is what dh = 32 / 64 run today.
+// TMEM: S[0] cols 0-63, S[1] cols 64-127, O in dh further columns (dh = 64 three-CTA build: one
+// S buffer, O behind it, P in a second 32-column allocation); two CTAs per SM for 64 < dh <= 128,
+// three for dh = 32 / 64. Head dims: any multiple of 64 up to 384 (64-channel operand panels, 128B
 // swizzle) plus 32 and 96 (32-channel panels, 64B swizzle) — the legacy UNet1D
 // (reference models/unet1d.py:17-29: 4 heads over 256..1536 channels) needs 192, 256 and 384.
 #include "../../include/lm2a_b200.h"
